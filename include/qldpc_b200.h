@@ -1,0 +1,179 @@
+/*
+ * qldpc_b200.h -- C ABI of the B200-native BP+OSD decoder (libqldpc_b200.so).
+ *
+ * This is the drop-in boundary for the decode hot path of michelebanfi/qLDPC.  The reference
+ * has no FFI layer -- its boundary is a set of Python call signatures --
+ * so each entry point below names the reference function(s) it stands in for; the Python
+ * package qldpc_b200 re-exports the reference's own names on top of these calls (see
+ * INTEGRATION.md for the ctypes binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 on success, non-zero on error
+ *     (qldpc_last_error() gives the message).  There is NO CPU fallback: without a CUDA device
+ *     every compute call fails with QLDPC_ERR_CUDA.
+ *   - "_host" functions take HOST pointers in the reference's dtypes (uint8/int8 0/1 arrays,
+ *     float64 LLRs) and do the host<->device copies themselves (synchronous on return).
+ *   - "_dev" functions take DEVICE pointers, bit-packed rows of 32-bit little-endian words
+ *     (bit j of a row = bit (j & 31) of word (j >> 5)), and a cudaStream_t passed as void*; they
+ *     only enqueue work.
+ *   - shots are the leading axis of every batched array.
+ */
+#ifndef QLDPC_B200_H
+#define QLDPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QLDPC_OK 0
+#define QLDPC_ERR_ARG 1
+#define QLDPC_ERR_CUDA 2
+#define QLDPC_ERR_UNSUPPORTED 3
+
+/* BP variants */
+#define QLDPC_MIN_SUM 0          /* rework/decoding.py:5    performMinSum_Symmetric                       */
+#define QLDPC_SUM_PRODUCT 1      /* decoding/beliefPropagation.py:88 performBeliefPropagationFast (and :6) */
+#define QLDPC_SUM_PRODUCT_SYM 2  /* rework/decoding.py:131  performBeliefPropagation_Symmetric            */
+
+/* posterior-LLR output modes */
+#define QLDPC_LLR_NONE 0
+#define QLDPC_LLR_FAILED 1       /* only for shots whose BP did not converge (what OSD consumes) */
+#define QLDPC_LLR_ALL 2
+
+#define QLDPC_NUM_COUNTERS 16
+/* indices into the counter vector of qldpc_check_* / qldpc_mc_sweep (see misc_kernels.cuh) */
+#define QLDPC_CNT_SHOTS 0
+#define QLDPC_CNT_BP_FAILED 1
+#define QLDPC_CNT_LOGICAL 2
+#define QLDPC_CNT_LOGICAL_OSD 3
+#define QLDPC_CNT_DEGENERATE 4
+#define QLDPC_CNT_MISCORRECTED 5
+#define QLDPC_CNT_INCORRECTABLE 6
+#define QLDPC_CNT_INVALID 7
+#define QLDPC_CNT_ITER_SUM 8
+#define QLDPC_CNT_LOGICAL_BP 9
+#define QLDPC_CNT_RESID_WEIGHT 10
+#define QLDPC_CNT_ERR_WEIGHT 11
+
+typedef struct qldpc_code qldpc_code; /* opaque: device-resident Tanner graph + workspaces */
+
+typedef struct {
+    int32_t variant;    /* QLDPC_MIN_SUM | QLDPC_SUM_PRODUCT | QLDPC_SUM_PRODUCT_SYM                 */
+    int32_t precision;  /* 32: float32 messages (production) | 64: float64, the reference's arithmetic */
+    int32_t max_iter;   /* maxIter of the reference                                                  */
+    int32_t staged;     /* 0: auto (shared memory when the per-shot state fits, else HBM-staged);
+                           1: force the HBM-staged kernel                                             */
+    double alpha;       /* min-sum normalisation / sum-product scaling                               */
+    double damping;     /* damping on Q                                                              */
+    double clip;        /* clip_llr                                                                  */
+} qldpc_bp_config;
+
+const char *qldpc_last_error(void);
+int qldpc_version(void);
+int qldpc_device_count(void);
+
+/* Tanner graph from host arrays.  CSR of H (row_ptr[m+1], col_idx[E] ascending inside a row),
+ * var_ptr[n+1], and for every variable the ids of its edges (CSR numbering) in the order their
+ * messages are added into the posterior, for iteration 0 (var_edge0) and iterations >= 1
+ * (var_edge1): this reproduces NumPy's summation order of `np.sum(R, axis=0)`
+ * (decoding/beliefPropagation.py:129, rework/decoding.py:61) -- SURVEY.md H2.
+ * L: k x n dense 0/1 logical operators (codes/<name>.npz key Lx) or NULL with k = 0.
+ * Replaces the per-call preprocessing of the reference (csr_matrix(H), mask = H != 0, ...:
+ * beliefPropagation.py:93-104, decoding.py:13-19). */
+int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx,
+                      const int32_t *var_ptr, const int32_t *var_edge0, const int32_t *var_edge1,
+                      int32_t k, const uint8_t *L, qldpc_code **out);
+void qldpc_code_destroy(qldpc_code *code);
+/* geometry the launcher picked for a config: shots resident per SM, shared-memory bytes per CTA,
+ * 1 if the HBM-staged kernel is used */
+int qldpc_bp_geometry(qldpc_code *code, const qldpc_bp_config *cfg, int32_t *shots_per_cta,
+                      int32_t *smem_bytes, int32_t *staged);
+
+/* ---------------- host-pointer API (reference dtypes) ---------------- */
+
+/* Batched BP.  Stands in for performMinSum_Symmetric / performBeliefPropagationFast /
+ * performBeliefPropagation / performBeliefPropagation_Symmetric (B = 1) and
+ * performBeliefPropagationBatch (beliefPropagationGPU.py:81).
+ *   synd [B][m] uint8, prior [n] float64 (initialBelief) ->
+ *   hard [B][n] int8, conv [B] uint8, iters [B] int32 (0-based exit iteration; may be NULL),
+ *   llr [B][n] float64 posterior `values` (may be NULL). */
+int qldpc_bp_decode_host(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                         const uint8_t *synd, int8_t *hard, uint8_t *conv, int32_t *iters, double *llr);
+
+/* Batched OSD.  Stands in for performOSD (decoding/OSD.py:3) when order == 0 and
+ * performOSD_enhanced (decoding/OSD_enhanced.py:5) otherwise; max_combinations <= 0 means None.
+ *   synd [B][m] uint8, llr [B][n] float64, hard [B][n] uint8/int8 -> out [B][n] uint8.
+ * Column order: stable ascending |llr| (ties -> lower index). */
+int qldpc_osd_decode_host(qldpc_code *code, int64_t B, const uint8_t *synd, const double *llr,
+                          const uint8_t *hard, int32_t order, int64_t max_combinations, uint8_t *out);
+
+/* Fused BP -> OSD on the BP failures: the per-shot body of the reference's Monte-Carlo loops
+ * (paperResults.py:71-77, paperResults_GPU.py:108-123, rework/main.py:80-88).
+ * osd_order < 0: BP only.   synd [B][m] uint8 -> corr [B][n] uint8, conv [B] uint8 (BP flag),
+ * iters [B] int32 (may be NULL).  This is the call bench.py times end to end. */
+int qldpc_bposd_decode_host(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                            const uint8_t *synd, int32_t osd_order, uint8_t *corr, uint8_t *conv,
+                            int32_t *iters);
+
+/* Per-shot checks of the drivers (paperResults.py:83-100, rework/main.py:90-112):
+ * err/corr [B][n] uint8, synd [B][m] uint8 -> flags [B] uint8 (bit0 logical, bit1 valid,
+ * bit2 degenerate), weight [B] int32 (residual weight), counters[QLDPC_NUM_COUNTERS] (any may be NULL). */
+int qldpc_check_host(qldpc_code *code, int64_t B, const uint8_t *err, const uint8_t *corr,
+                     const uint8_t *synd, const uint8_t *conv, const int32_t *iters,
+                     int32_t distance, uint8_t *flags, int32_t *weight, uint64_t *counters);
+
+/* generate_errors_and_syndromes_batch (beliefPropagationGPU.py:181) on the device: Philox4x32-10
+ * keyed by (seed, first_shot + i).  err [B][n] uint8, synd [B][m] uint8.  draws = 2 XORs two
+ * independent draws (paperResults.py:61-63). */
+int qldpc_sample_host(qldpc_code *code, double p, uint64_t seed, uint64_t first_shot, int32_t draws,
+                      int64_t B, uint8_t *err, uint8_t *synd);
+
+/* Whole Monte-Carlo point on the device: sample -> BP -> OSD on failures -> checks -> counters.
+ * Shots [first_shot, first_shot + nshots) of the stream `seed`; counters are ADDED into
+ * counters[QLDPC_NUM_COUNTERS] (host).  Results depend only on (seed, shot id): sharding the
+ * range over ranks and summing the counters gives identical totals. */
+int qldpc_mc_sweep(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, double p,
+                   uint64_t seed, uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order,
+                   int32_t distance, uint64_t *counters);
+
+/* ---------------- device-pointer API (bit-packed, asynchronous) ---------------- */
+
+/* words per packed syndrome / error row */
+int qldpc_words_m(const qldpc_code *code);
+int qldpc_words_n(const qldpc_code *code);
+
+/* BP on packed device syndromes.  llr is float32 or float64 per cfg->precision.
+ * fail_idx/fail_count (may be NULL): compacted ids of the BP failures, for qldpc_osd_decode_dev.
+ * iter_total (may be NULL): device uint64 accumulating executed iterations (roofline accounting). */
+int qldpc_bp_decode_dev(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
+                        const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters,
+                        void *llr, int32_t llr_mode, int32_t *fail_idx, uint32_t *fail_count,
+                        uint64_t *iter_total, void *stream);
+
+/* OSD-0 on the shots listed in idx[0 .. *count_dev) (count taken from the device, no host sync),
+ * or on all of [0, count_host) when idx == NULL.  out may alias hard.  llr_f64: 1 if llr is double. */
+int qldpc_osd_decode_dev(qldpc_code *code, const int32_t *idx, const uint32_t *count_dev, int64_t count_host,
+                         const uint32_t *synd, const void *llr, int32_t llr_f64, const uint32_t *hard,
+                         uint32_t *out, uint8_t *valid, void *stream);
+
+int qldpc_check_dev(qldpc_code *code, int64_t B, const uint32_t *err, const uint32_t *corr,
+                    const uint32_t *synd, const uint8_t *conv, const int32_t *iters, int32_t distance,
+                    uint8_t *flags, int32_t *weight, uint64_t *counters_dev, void *stream);
+
+int qldpc_sample_dev(qldpc_code *code, double p, uint64_t seed, uint64_t first_shot, int32_t draws,
+                     int64_t B, uint32_t *err, uint32_t *synd, void *stream);
+
+/* fused BP -> OSD-0 (osd_order >= 0) on packed device syndromes; corr [B][words_n] */
+int qldpc_bposd_decode_dev(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
+                           const uint32_t *synd, int32_t osd_order, uint32_t *corr, uint8_t *conv,
+                           int32_t *iters, uint64_t *iter_total, void *stream);
+
+int qldpc_pack_bits_dev(const uint8_t *in, uint32_t *out, int64_t B, int32_t nbits, void *stream);
+int qldpc_unpack_bits_dev(const uint32_t *in, uint8_t *out, int64_t B, int32_t nbits, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QLDPC_B200_H */

@@ -1,0 +1,221 @@
+"""`Code`: a parity-check matrix resident on the GPU (Tanner-graph tables, packed columns, packed
+logical operators, workspaces) plus the batched decode calls on it.
+
+This is the host-side mirror of the C ABI (include/qldpc_b200.h); the reference-named functions in
+qldpc_b200.decoding.* / qldpc_b200.rework.decoding are thin B = 1 wrappers over these methods.
+All heavy lifting happens in libqldpc_b200.so; nothing here computes a decode on the CPU.
+"""
+import ctypes
+import hashlib
+import os
+
+import numpy as np
+
+from . import _lib
+from . import graph as _graph
+
+VARIANTS = {"min_sum": _lib.MIN_SUM, "sum_product": _lib.SUM_PRODUCT, "sum_product_sym": _lib.SUM_PRODUCT_SYM}
+DATA_CODES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "codes")
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _bits(a, shape=None):
+    """0/1 array of any integer/bool/float dtype -> contiguous uint8."""
+    a = np.asarray(a)
+    if a.dtype != np.uint8:
+        a = (a.astype(np.int64) & 1).astype(np.uint8) if a.dtype.kind in "iub" else (a != 0).astype(np.uint8)
+    a = np.ascontiguousarray(a)
+    if shape is not None and a.shape != shape:
+        raise ValueError("expected shape %s, got %s" % (shape, a.shape))
+    return a
+
+
+def to_dense(H):
+    """Accepts what the reference's callers pass: ndarray of any dtype/order or a scipy.sparse matrix
+    (studies/studyComplete.py:84)."""
+    if hasattr(H, "toarray") and not isinstance(H, np.ndarray):
+        return np.asarray(H.toarray())
+    return H if isinstance(H, np.ndarray) else np.asarray(H)
+
+
+class Code:
+    def __init__(self, H, L=None, schedule=(_graph.SEQ, _graph.SEQ), distance=None):
+        H = to_dense(H)
+        g = _graph.build_graph(H, *schedule)
+        self.m, self.n, self.E = g["m"], g["n"], g["E"]
+        self.schedule = tuple(schedule)
+        self.distance = None if distance is None else int(distance)
+        self._g = g
+        self.L = None if L is None else _bits(L)
+        self.k = 0 if self.L is None else self.L.shape[0]
+        if self.L is not None and self.L.shape[1] != self.n:
+            raise ValueError("L must have n columns")
+        self._h = ctypes.c_void_p()
+        lib = _lib.lib()
+        _lib.check(lib.qldpc_code_create(self.m, self.n, _vp(g["row_ptr"]), _vp(g["col_idx"]), _vp(g["var_ptr"]),
+                                         _vp(g["var_edge0"]), _vp(g["var_edge1"]), self.k, _vp(self.L),
+                                         ctypes.byref(self._h)), "qldpc_code_create")
+        self.words_m = lib.qldpc_words_m(self._h)
+        self.words_n = lib.qldpc_words_n(self._h)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                _lib.lib().qldpc_code_destroy(h)
+            except Exception:
+                pass
+            self._h = ctypes.c_void_p()
+
+    @property
+    def handle(self):
+        return self._h
+
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def config(variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0, precision=32, staged=False):
+        cfg = _lib.BPConfig()
+        cfg.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
+        cfg.precision = int(precision)
+        cfg.max_iter = int(max_iter)
+        cfg.staged = 1 if staged else 0
+        cfg.alpha, cfg.damping, cfg.clip = float(alpha), float(damping), float(clip)
+        return cfg
+
+    def _prior(self, prior):
+        p = np.ascontiguousarray(np.asarray(prior, dtype=np.float64).reshape(-1))
+        if p.size == 1:
+            p = np.full(self.n, float(p[0]))
+        if p.size != self.n:
+            raise ValueError("prior must have n entries")
+        return p
+
+    def geometry(self, cfg):
+        a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(_lib.lib().qldpc_bp_geometry(self._h, ctypes.byref(cfg), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return dict(shots_per_cta=a.value, smem_bytes=b.value, staged=bool(c.value))
+
+    # ---- host-array API (reference dtypes) -------------------------------------------------------
+    def bp_decode_batch(self, syndromes, prior, variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0,
+                        precision=32, want_llr=True, staged=False):
+        """-> (hard int8 (B,n), converged bool (B,), llr float64 (B,n) | None, iters int32 (B,))"""
+        synd = _bits(syndromes)
+        if synd.ndim != 2 or synd.shape[1] != self.m:
+            raise ValueError("syndromes must be (B, m)")
+        B = synd.shape[0]
+        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged)
+        p = self._prior(prior)
+        hard = np.zeros((B, self.n), np.int8)
+        conv = np.zeros(B, np.uint8)
+        iters = np.zeros(B, np.int32)
+        llr = np.zeros((B, self.n), np.float64) if want_llr else None
+        if B:
+            _lib.check(_lib.lib().qldpc_bp_decode_host(self._h, ctypes.byref(cfg), _vp(p), B, _vp(synd), _vp(hard), _vp(conv),
+                                                      _vp(iters), _vp(llr)), "qldpc_bp_decode_host")
+        return hard, conv.astype(bool), llr, iters
+
+    def osd_decode_batch(self, syndromes, llr, hard, order=0, max_combinations=None):
+        """-> int64 (B,n): performOSD (order 0) / performOSD_enhanced (order > 0) per shot."""
+        synd = _bits(syndromes)
+        hard = _bits(hard)
+        llr = np.ascontiguousarray(llr, dtype=np.float64)
+        B = synd.shape[0]
+        if synd.shape != (B, self.m) or hard.shape != (B, self.n) or llr.shape != (B, self.n):
+            raise ValueError("shape mismatch")
+        out = np.zeros((B, self.n), np.uint8)
+        if B:
+            _lib.check(_lib.lib().qldpc_osd_decode_host(self._h, B, _vp(synd), _vp(llr), _vp(hard), int(order),
+                                                       int(max_combinations) if max_combinations else 0, _vp(out)),
+                       "qldpc_osd_decode_host")
+        return out.astype(np.int64)
+
+    def bposd_decode_batch(self, syndromes, prior, variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0,
+                           precision=32, osd_order=0, staged=False, out=None):
+        """BP, then OSD on the BP failures.  -> (corr uint8 (B,n), converged bool (B,), iters int32 (B,))"""
+        synd = _bits(syndromes)
+        B = synd.shape[0]
+        if synd.shape != (B, self.m):
+            raise ValueError("syndromes must be (B, m)")
+        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged)
+        p = self._prior(prior)
+        corr = np.zeros((B, self.n), np.uint8) if out is None else out
+        conv = np.zeros(B, np.uint8)
+        iters = np.zeros(B, np.int32)
+        if B:
+            _lib.check(_lib.lib().qldpc_bposd_decode_host(self._h, ctypes.byref(cfg), _vp(p), B, _vp(synd), int(osd_order),
+                                                         _vp(corr), _vp(conv), _vp(iters)), "qldpc_bposd_decode_host")
+        return corr, conv.astype(bool), iters
+
+    def check_batch(self, errors, corrections, syndromes, converged=None, iters=None, distance=None):
+        """-> dict(logical bool (B,), valid bool (B,), degenerate bool (B,), weight int32 (B,), counters dict)"""
+        err, cor, syn = _bits(errors), _bits(corrections), _bits(syndromes)
+        B = err.shape[0]
+        conv = None if converged is None else np.ascontiguousarray(converged, dtype=np.uint8)
+        it = None if iters is None else np.ascontiguousarray(iters, dtype=np.int32)
+        flags = np.zeros(B, np.uint8)
+        weight = np.zeros(B, np.int32)
+        counters = np.zeros(_lib.NUM_COUNTERS, np.uint64)
+        d = self.distance if distance is None else distance
+        if B:
+            _lib.check(_lib.lib().qldpc_check_host(self._h, B, _vp(err), _vp(cor), _vp(syn), _vp(conv), _vp(it),
+                                                  int(d or 0), _vp(flags), _vp(weight), _vp(counters)), "qldpc_check_host")
+        return dict(logical=(flags & 1).astype(bool), valid=(flags & 2).astype(bool), degenerate=(flags & 4).astype(bool),
+                    weight=weight, counters=dict(zip(_lib.COUNTER_NAMES, (int(x) for x in counters))))
+
+    def sample(self, p, B, seed=0, first_shot=0, draws=1):
+        """Device Philox sampler -> (errors int8 (B,n), syndromes int8 (B,m))."""
+        err = np.zeros((B, self.n), np.uint8)
+        syn = np.zeros((B, self.m), np.uint8)
+        if B:
+            _lib.check(_lib.lib().qldpc_sample_host(self._h, float(p), int(seed), int(first_shot), int(draws), B, _vp(err),
+                                                   _vp(syn)), "qldpc_sample_host")
+        return err.view(np.int8), syn.view(np.int8)
+
+    def mc_sweep(self, p, nshots, prior=None, seed=0, first_shot=0, draws=1, variant="min_sum", max_iter=50, alpha=1.0,
+                 damping=1.0, clip=20.0, precision=32, osd_order=0, distance=None, staged=False):
+        """One Monte-Carlo point entirely on the device.  -> dict of counters."""
+        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged)
+        pe = p if draws == 1 else 2 * p * (1 - p)
+        pr = self._prior(np.log((1 - pe) / pe) if prior is None else prior)
+        counters = np.zeros(_lib.NUM_COUNTERS, np.uint64)
+        d = self.distance if distance is None else distance
+        _lib.check(_lib.lib().qldpc_mc_sweep(self._h, ctypes.byref(cfg), _vp(pr), float(p), int(seed), int(first_shot),
+                                             int(nshots), int(draws), int(osd_order), int(d or 0), _vp(counters)),
+                   "qldpc_mc_sweep")
+        return dict(zip(_lib.COUNTER_NAMES, (int(x) for x in counters)))
+
+
+# ------------------------------------------------------------------------------------------------
+# codes/*.npz and the handle cache used by the reference-named wrappers
+# ------------------------------------------------------------------------------------------------
+def load_code(name, side="x", directory=None, schedule=None):
+    """Loads `codes/<name>.npz` (keys Hx, Hz, Lx, Lz, distance; e.g. name = '[[144, 12, 12]]') and returns a
+    Code for H<side> with L<side>, as every reference driver pairs them (paperResults.py:34-39)."""
+    d = np.load(os.path.join(directory or DATA_CODES, name + ".npz"))
+    H = d["H" + side]
+    L = d["L" + side] if ("L" + side) in d.files else None
+    dist = int(d["distance"]) if "distance" in d.files else None
+    return Code(H, L, schedule or (_graph.SEQ, _graph.SEQ), dist)
+
+
+_CACHE = {}
+_CACHE_MAX = 16
+
+
+def cached_code(H, variant_key, schedule=None):
+    """Code handle for the H object a reference-style call passes, keyed by content, memory layout
+    (it selects the float summation order) and variant family."""
+    Hd = to_dense(H)
+    sched = tuple(schedule) if schedule is not None else _graph.reference_schedule(Hd, variant_key)
+    Hb = np.ascontiguousarray(Hd != 0)
+    key = (Hb.shape, hashlib.blake2b(Hb.tobytes(), digest_size=16).digest(), sched)
+    c = _CACHE.get(key)
+    if c is None:
+        if len(_CACHE) >= _CACHE_MAX:
+            _CACHE.pop(next(iter(_CACHE)))
+        c = Code(Hd, None, sched)
+        _CACHE[key] = c
+    return c

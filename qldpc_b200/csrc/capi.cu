@@ -1,0 +1,756 @@
+// C ABI of libqldpc_b200.so (declared in include/qldpc_b200.h): code handle, launch geometry,
+// workspaces and the host/device entry points around the kernels in bp_kernel.cuh,
+// osd_kernel.cuh, osdw_kernel.cuh and misc_kernels.cuh.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/qldpc_b200.h"
+#include "bp_kernel.cuh"
+#include "misc_kernels.cuh"
+#include "osd_kernel.cuh"
+#include "osdw_kernel.cuh"
+
+using namespace qldpc;
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg)
+{
+    g_err = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(QLDPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) +       \
+                                            " (" __FILE__ ":" + std::to_string(__LINE__) + ")");  \
+    } while (0)
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct Ctrl {                       // device control block, zeroed before every BP launch
+    unsigned long long cursor;
+    unsigned long long iter_total;
+    unsigned int fail_count;
+    unsigned int pad;
+};
+
+struct qldpc_code {
+    int m = 0, n = 0, E = 0, k = 0, WM = 0, WN = 0;
+    int uniform_row_w = 0, max_col_w = 0, two_tables = 0;
+    int num_sms = 0, smem_optin = 0;
+    int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_var_ptr = nullptr;
+    uint32_t *d_vtab0 = nullptr, *d_vtab1 = nullptr, *d_colmask = nullptr, *d_Lrows = nullptr, *d_Hrows = nullptr;
+    std::vector<double> prior_cache;
+    DevBuf prior32, prior64, ctrl, gstate;
+    DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
+        ws_weight, ws_cnt, ws_llr_in, ws_rec;
+    BPGraphDev graph() const
+    {
+        BPGraphDev g;
+        g.m = m; g.n = n; g.E = E; g.WM = WM; g.WN = WN;
+        g.uniform_row_w = uniform_row_w; g.max_col_w = max_col_w; g.two_tables = two_tables;
+        g.row_ptr = d_row_ptr; g.col_idx = d_col_idx; g.var_ptr = d_var_ptr;
+        g.vtab0 = d_vtab0; g.vtab1 = d_vtab1; g.colmask = d_colmask;
+        return g;
+    }
+};
+
+extern "C" const char *qldpc_last_error(void) { return g_err.c_str(); }
+extern "C" int qldpc_version(void) { return 100; }
+extern "C" int qldpc_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+extern "C" int qldpc_words_m(const qldpc_code *c) { return c ? c->WM : 0; }
+extern "C" int qldpc_words_n(const qldpc_code *c) { return c ? c->WN : 0; }
+
+template <typename T> static cudaError_t upload(T **dst, const std::vector<T> &src)
+{
+    cudaError_t e = cudaMalloc((void **)dst, std::max<size_t>(1, src.size()) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (src.empty()) return cudaSuccess;
+    return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx,
+                                 const int32_t *var_ptr, const int32_t *var_edge0, const int32_t *var_edge1,
+                                 int32_t k, const uint8_t *L, qldpc_code **out)
+{
+    if (!out || m <= 0 || n <= 0 || !row_ptr || !col_idx || !var_ptr || !var_edge0 || !var_edge1 || (k > 0 && !L))
+        return fail(QLDPC_ERR_ARG, "qldpc_code_create: bad argument");
+    if (qldpc_device_count() <= 0) return fail(QLDPC_ERR_CUDA, "qldpc_code_create: no CUDA device (there is no CPU fallback)");
+    const int E = row_ptr[m];
+    if (E <= 0 || var_ptr[n] != E) return fail(QLDPC_ERR_ARG, "qldpc_code_create: inconsistent CSR / variable pointers");
+    qldpc_code *c = new qldpc_code();
+    c->m = m; c->n = n; c->E = E; c->k = k;
+    c->WM = (m + 31) / 32;
+    c->WN = (n + 31) / 32;
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    CK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, dev));
+    CK(cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+
+    // edge -> check
+    std::vector<int32_t> edge_check(E);
+    int rw = row_ptr[1] - row_ptr[0];
+    for (int r = 0; r < m; ++r) {
+        if (row_ptr[r + 1] - row_ptr[r] != rw) rw = 0;
+        for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
+            if (col_idx[e] < 0 || col_idx[e] >= n) { delete c; return fail(QLDPC_ERR_ARG, "qldpc_code_create: column index out of range"); }
+            edge_check[e] = r;
+        }
+    }
+    c->uniform_row_w = (rw > 0 && rw <= 8) ? rw : 0;
+    std::vector<uint32_t> vt0(2 * (size_t)E), vt1(2 * (size_t)E), colmask((size_t)n * c->WM, 0u);
+    for (int v = 0; v < n; ++v) {
+        c->max_col_w = std::max(c->max_col_w, var_ptr[v + 1] - var_ptr[v]);
+        for (int a = var_ptr[v]; a < var_ptr[v + 1]; ++a) {
+            const int e0 = var_edge0[a], e1 = var_edge1[a];
+            if (e0 < 0 || e0 >= E || e1 < 0 || e1 >= E || col_idx[e0] != v || col_idx[e1] != v) {
+                delete c;
+                return fail(QLDPC_ERR_ARG, "qldpc_code_create: var_edge table does not match the CSR");
+            }
+            vt0[2 * a] = e0; vt0[2 * a + 1] = edge_check[e0];
+            vt1[2 * a] = e1; vt1[2 * a + 1] = edge_check[e1];
+            if (e0 != e1) c->two_tables = 1;
+            colmask[(size_t)v * c->WM + (edge_check[e1] >> 5)] |= 1u << (edge_check[e1] & 31);
+        }
+    }
+    std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
+    for (int r = 0; r < k; ++r)
+        for (int j = 0; j < n; ++j)
+            if (L[(size_t)r * n + j] & 1) Lrows[(size_t)r * c->WN + (j >> 5)] |= 1u << (j & 31);
+    for (int r = 0; r < m; ++r)
+        for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) Hrows[(size_t)r * c->WN + (col_idx[e] >> 5)] |= 1u << (col_idx[e] & 31);
+    std::vector<int32_t> rp(row_ptr, row_ptr + m + 1), ci(col_idx, col_idx + E), vp(var_ptr, var_ptr + n + 1);
+    CK(upload(&c->d_row_ptr, rp));
+    CK(upload(&c->d_col_idx, ci));
+    CK(upload(&c->d_var_ptr, vp));
+    CK(upload(&c->d_vtab0, vt0));
+    CK(upload(&c->d_vtab1, vt1));
+    CK(upload(&c->d_colmask, colmask));
+    CK(upload(&c->d_Lrows, Lrows));
+    CK(upload(&c->d_Hrows, Hrows));
+    CK(c->ctrl.reserve(sizeof(Ctrl)));
+    *out = c;
+    return QLDPC_OK;
+}
+
+extern "C" void qldpc_code_destroy(qldpc_code *c)
+{
+    if (!c) return;
+    cudaFree(c->d_row_ptr); cudaFree(c->d_col_idx); cudaFree(c->d_var_ptr);
+    cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
+    DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
+                      &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
+                      &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
+    for (DevBuf *b : bufs) b->release();
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BP launch geometry
+// ------------------------------------------------------------------------------------------------
+struct BPGeom {
+    bool staged;
+    int threads, grid;
+    size_t smem;
+    size_t gstate_bytes;
+};
+
+static int kernel_variant(int v) { return v == QLDPC_MIN_SUM ? VAR_MIN_SUM : VAR_SUM_PRODUCT; }
+
+static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long long B, BPGeom *G)
+{
+    const int tsize = cfg->precision == 64 ? 8 : 4;
+    const BPGraphDev g = c->graph();
+    const BPSmemLayout L = bp_smem_layout(g, tsize, kernel_variant(cfg->variant));
+    const bool wm_ok = (c->WM <= 5);
+    long long nt = 0;
+    if (!cfg->staged && wm_ok && L.tables + 32 * L.per_shot <= (size_t)c->smem_optin)
+        nt = std::min<long long>(256, (long long)(((size_t)c->smem_optin - L.tables) / L.per_shot)) / 32 * 32;
+    if (nt >= 32) {
+        G->staged = false;
+        long long want = std::max<long long>(32, (B + 31) / 32 * 32);
+        G->threads = (int)std::min<long long>(nt, want);
+        G->smem = L.tables + (size_t)G->threads * L.per_shot;
+        G->grid = (int)std::max<long long>(1, std::min<long long>((B + G->threads - 1) / G->threads, c->num_sms));
+        G->gstate_bytes = 0;
+    } else {
+        G->staged = true;
+        G->threads = 128;
+        G->smem = 0;
+        G->grid = (int)std::max<long long>(1, std::min<long long>((B + 127) / 128, (long long)c->num_sms * 4));
+        const size_t per_thread = (size_t)tsize * (c->E + 2 * (size_t)c->m) + 4 * (size_t)(c->WN + c->WM);
+        G->gstate_bytes = per_thread * (size_t)G->grid * G->threads;
+    }
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int32_t *shots_per_cta, int32_t *smem_bytes,
+                                 int32_t *staged)
+{
+    if (!c || !cfg) return fail(QLDPC_ERR_ARG, "qldpc_bp_geometry: null argument");
+    BPGeom G;
+    bp_geometry(c, cfg, 1ll << 40, &G);
+    if (shots_per_cta) *shots_per_cta = G.threads;
+    if (smem_bytes) *smem_bytes = (int32_t)G.smem;
+    if (staged) *staged = G.staged ? 1 : 0;
+    return QLDPC_OK;
+}
+
+static int check_cfg(const qldpc_bp_config *cfg)
+{
+    if (!cfg) return fail(QLDPC_ERR_ARG, "null BP config");
+    if (cfg->variant < 0 || cfg->variant > 2) return fail(QLDPC_ERR_ARG, "unknown BP variant");
+    if (cfg->precision != 32 && cfg->precision != 64) return fail(QLDPC_ERR_ARG, "precision must be 32 or 64");
+    if (cfg->max_iter < 1) return fail(QLDPC_ERR_ARG, "max_iter must be >= 1");
+    return QLDPC_OK;
+}
+
+static int set_prior(qldpc_code *c, const double *prior_host, cudaStream_t st)
+{
+    if (!prior_host) return fail(QLDPC_ERR_ARG, "null prior");
+    if (c->prior_cache.size() == (size_t)c->n && memcmp(c->prior_cache.data(), prior_host, sizeof(double) * c->n) == 0)
+        return QLDPC_OK;
+    CK(c->prior64.reserve(sizeof(double) * c->n));
+    CK(c->prior32.reserve(sizeof(float) * c->n));
+    std::vector<float> pf(c->n);
+    for (int i = 0; i < c->n; ++i) pf[i] = (float)prior_host[i];
+    // both copies are from pageable memory: staged by the driver before the call returns
+    CK(cudaMemcpyAsync(c->prior64.p, prior_host, sizeof(double) * c->n, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->prior32.p, pf.data(), sizeof(float) * c->n, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    c->prior_cache.assign(prior_host, prior_host + c->n);
+    return QLDPC_OK;
+}
+
+template <typename T, int VAR, int WMS, bool SMEM>
+static cudaError_t launch_bp_inst(const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    auto kern = bp_decode_kernel<T, VAR, WMS, SMEM>;
+    if (SMEM) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+        if (e != cudaSuccess) return e;
+    }
+    kern<<<G.grid, G.threads, G.smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <typename T, int VAR>
+static cudaError_t launch_bp_tv(const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    if (G.staged) return launch_bp_inst<T, VAR, 0, false>(P, G, st);
+    switch (P.g.WM) {
+    case 1: return launch_bp_inst<T, VAR, 1, true>(P, G, st);
+    case 2: return launch_bp_inst<T, VAR, 2, true>(P, G, st);
+    case 3: return launch_bp_inst<T, VAR, 3, true>(P, G, st);
+    case 4: case 5: {
+        // WM == 4 runs the 5-word instantiation on a 5-word view?  No: keep exact strides.
+        if (P.g.WM == 5) return launch_bp_inst<T, VAR, 5, true>(P, G, st);
+        return launch_bp_inst<T, VAR, 4, true>(P, G, st);
+    }
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
+                                   const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters, void *llr,
+                                   int32_t llr_mode, int32_t *fail_idx, uint32_t *fail_count, uint64_t *iter_total,
+                                   void *stream)
+{
+    if (!c || !synd || !hard || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bp_decode_dev: null argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    if (B <= 0) return QLDPC_OK;
+    if (B > 0x7fffffffll) return fail(QLDPC_ERR_ARG, "qldpc_bp_decode_dev: B must be < 2^31 per call (chunk the batch)");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = set_prior(c, prior_host, st)) return rc;
+    BPGeom G;
+    bp_geometry(c, cfg, B, &G);
+    if (G.staged) CK(c->gstate.reserve(G.gstate_bytes));
+    Ctrl *ctrl = c->ctrl.as<Ctrl>();
+    CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st));
+    if (fail_count) CK(cudaMemsetAsync(fail_count, 0, sizeof(uint32_t), st));
+
+    BPParams P;
+    P.g = c->graph();
+    P.B = B;
+    P.synd = synd;
+    P.prior = cfg->precision == 64 ? c->prior64.p : c->prior32.p;
+    P.max_iter = cfg->max_iter;
+    P.sym = (cfg->variant == QLDPC_SUM_PRODUCT_SYM);
+    P.alpha = cfg->alpha;
+    P.damping = cfg->damping;
+    P.one_minus_damping = 1.0 - cfg->damping;     // `(1 - damping)` evaluated in float64 (decoding.py:65)
+    P.clip = cfg->clip;
+    P.hard = hard;
+    P.conv = conv;
+    P.iters = iters;
+    P.llr = llr;
+    P.llr_mode = llr ? llr_mode : LLR_NONE;
+    P.cursor = &ctrl->cursor;
+    P.fail_idx = fail_idx;
+    P.fail_count = fail_count ? fail_count : &ctrl->fail_count;
+    P.iter_total = (unsigned long long *)iter_total;
+    P.gstate = c->gstate.p;
+    cudaError_t e;
+    const int kv = kernel_variant(cfg->variant);
+    if (cfg->precision == 64)
+        e = (kv == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
+    else
+        e = (kv == VAR_MIN_SUM) ? launch_bp_tv<float, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<float, VAR_SUM_PRODUCT>(P, G, st);
+    if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("bp_decode_kernel launch: ") + cudaGetErrorString(e));
+    return QLDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// OSD
+// ------------------------------------------------------------------------------------------------
+template <typename K, int WM>
+static cudaError_t launch_osd_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
+{
+    auto kern = osd0_kernel<K, WM>;
+    const size_t smem = osd_smem_per_warp<K>(P.n) * OSD_WARPS;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_WARPS * 32, smem);
+    long long grid = (long long)c->num_sms * std::max(1, occ);
+    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, (count_hint + OSD_WARPS - 1) / OSD_WARPS));
+    kern<<<(int)grid, OSD_WARPS * 32, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <typename K>
+static cudaError_t launch_osd_k(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
+{
+    switch (P.WM) {
+    case 1: return launch_osd_inst<K, 1>(c, P, count_hint, st);
+    case 2: return launch_osd_inst<K, 2>(c, P, count_hint, st);
+    case 3: return launch_osd_inst<K, 3>(c, P, count_hint, st);
+    case 4: return launch_osd_inst<K, 4>(c, P, count_hint, st);
+    case 5: return launch_osd_inst<K, 5>(c, P, count_hint, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st)
+{
+    P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
+    P.colmask = c->d_colmask;
+    if (c->WM > 5 || c->n > 65535)
+        return fail(QLDPC_ERR_UNSUPPORTED, "OSD: check matrices with more than 160 rows need the block-per-shot kernel (not built yet)");
+    cudaError_t e = llr_f64 ? launch_osd_k<double>(c, P, count_hint, st) : launch_osd_k<float>(c, P, count_hint, st);
+    if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osd0_kernel launch: ") + cudaGetErrorString(e));
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_osd_decode_dev(qldpc_code *c, const int32_t *idx, const uint32_t *count_dev, int64_t count_host,
+                                    const uint32_t *synd, const void *llr, int32_t llr_f64, const uint32_t *hard,
+                                    uint32_t *out, uint8_t *valid, void *stream)
+{
+    if (!c || !synd || !llr || !hard || !out) return fail(QLDPC_ERR_ARG, "qldpc_osd_decode_dev: null argument");
+    if (!count_dev && count_host <= 0) return QLDPC_OK;
+    OSDParams P;
+    memset(&P, 0, sizeof(P));
+    P.idx = idx;
+    P.count_dev = count_dev;
+    P.count_host = count_host;
+    P.synd = synd; P.llr = llr; P.hard = hard; P.out = out; P.valid = valid;
+    return osd_launch(c, P, llr_f64, count_dev ? -1 : count_host, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+static int grid_for(long long work, int threads, int num_sms)
+{
+    long long g = (work + threads - 1) / threads;
+    return (int)std::max<long long>(1, std::min<long long>(g, (long long)num_sms * 16));
+}
+
+extern "C" int qldpc_pack_bits_dev(const uint8_t *in, uint32_t *out, int64_t B, int32_t nbits, void *stream)
+{
+    if (B <= 0) return QLDPC_OK;
+    const int W = (nbits + 31) / 32;
+    pack_bits_kernel<<<grid_for(B * W, 256, 148), 256, 0, (cudaStream_t)stream>>>(in, out, B, nbits, W);
+    CK(cudaGetLastError());
+    return QLDPC_OK;
+}
+extern "C" int qldpc_unpack_bits_dev(const uint32_t *in, uint8_t *out, int64_t B, int32_t nbits, void *stream)
+{
+    if (B <= 0) return QLDPC_OK;
+    const int W = (nbits + 31) / 32;
+    unpack_bits_kernel<<<grid_for(B * (long long)nbits, 256, 148), 256, 0, (cudaStream_t)stream>>>(in, out, B, nbits, W);
+    CK(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+template <int WM> static void launch_sample(const SampleParams &P, int grid, cudaStream_t st) { sample_kernel<WM><<<grid, 128, 0, st>>>(P); }
+template <int WM> static void launch_check(const CheckParams &P, int grid, cudaStream_t st) { check_kernel<WM><<<grid, 256, 0, st>>>(P); }
+
+extern "C" int qldpc_sample_dev(qldpc_code *c, double p, uint64_t seed, uint64_t first_shot, int32_t draws, int64_t B,
+                                uint32_t *err, uint32_t *synd, void *stream)
+{
+    if (!c || !err || !synd) return fail(QLDPC_ERR_ARG, "qldpc_sample_dev: null argument");
+    if (!(p >= 0.0 && p < 1.0) || draws < 1 || draws > 2) return fail(QLDPC_ERR_ARG, "qldpc_sample_dev: need 0 <= p < 1 and draws in {1,2}");
+    if (B <= 0) return QLDPC_OK;
+    if (c->WM > 5) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_sample_dev: more than 160 checks");
+    SampleParams P;
+    P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
+    P.colmask = c->d_colmask;
+    P.B = B; P.first_shot = first_shot; P.seed = seed;
+    P.threshold = (uint32_t)std::min<double>(4294967295.0, p * 4294967296.0);
+    P.draws = draws;
+    P.err = err; P.synd = synd;
+    const int grid = (int)((B + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (c->WM) {
+    case 1: launch_sample<1>(P, grid, st); break;
+    case 2: launch_sample<2>(P, grid, st); break;
+    case 3: launch_sample<3>(P, grid, st); break;
+    case 4: launch_sample<4>(P, grid, st); break;
+    default: launch_sample<5>(P, grid, st); break;
+    }
+    CK(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, const uint32_t *corr, const uint32_t *synd,
+                               const uint8_t *conv, const int32_t *iters, int32_t distance, uint8_t *flags,
+                               int32_t *weight, uint64_t *counters_dev, void *stream)
+{
+    if (!c || !err || !corr || !synd) return fail(QLDPC_ERR_ARG, "qldpc_check_dev: null argument");
+    if (B <= 0) return QLDPC_OK;
+    if (c->WM > 5) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_check_dev: more than 160 checks");
+    CheckParams P;
+    P.m = c->m; P.n = c->n; P.k = c->k; P.WM = c->WM; P.WN = c->WN;
+    P.colmask = c->d_colmask; P.Lrows = c->d_Lrows;
+    P.B = B; P.err = err; P.corr = corr; P.synd = synd; P.conv = conv; P.iters = iters;
+    P.half_distance = distance / 2;
+    P.counters = (unsigned long long *)counters_dev;
+    P.flags = flags; P.weight = weight;
+    const int grid = grid_for(B, 256, c->num_sms);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (c->WM) {
+    case 1: launch_check<1>(P, grid, st); break;
+    case 2: launch_check<2>(P, grid, st); break;
+    case 3: launch_check<3>(P, grid, st); break;
+    case 4: launch_check<4>(P, grid, st); break;
+    default: launch_check<5>(P, grid, st); break;
+    }
+    CK(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused BP -> OSD
+// ------------------------------------------------------------------------------------------------
+static const long long CHUNK = 1ll << 22;   // shots per internal launch (bounds the LLR workspace)
+
+extern "C" int qldpc_bposd_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
+                                      const uint32_t *synd, int32_t osd_order, uint32_t *corr, uint8_t *conv,
+                                      int32_t *iters, uint64_t *iter_total, void *stream)
+{
+    if (!c || !synd || !corr || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_dev: null argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tsize = cfg->precision == 64 ? 8 : 4;
+    for (long long o = 0; o < B; o += CHUNK) {
+        const long long b = std::min<long long>(CHUNK, B - o);
+        void *llr = nullptr;
+        int32_t *fidx = nullptr;
+        uint32_t *fcnt = nullptr;
+        if (osd_order >= 0) {
+            CK(c->ws_llr.reserve((size_t)b * c->n * tsize));
+            CK(c->ws_fail.reserve(sizeof(int32_t) * (size_t)b + 16));
+            llr = c->ws_llr.p;
+            fcnt = c->ws_fail.as<uint32_t>();
+            fidx = c->ws_fail.as<int32_t>() + 4;
+        }
+        int rc = qldpc_bp_decode_dev(c, cfg, prior_host, b, synd + (size_t)o * c->WM, corr + (size_t)o * c->WN, conv + o,
+                                     iters ? iters + o : nullptr, llr, QLDPC_LLR_FAILED, fidx, fcnt, iter_total, st);
+        if (rc) return rc;
+        if (osd_order >= 0) {
+            OSDParams P;
+            memset(&P, 0, sizeof(P));
+            P.idx = fidx; P.count_dev = fcnt; P.count_host = 0;
+            P.synd = synd + (size_t)o * c->WM;
+            P.llr = llr;
+            P.hard = corr + (size_t)o * c->WN;
+            P.out = corr + (size_t)o * c->WN;
+            // OSD-w == OSD-0 whenever the OSD-0 solution satisfies the syndrome (OSD_enhanced.py:58-60),
+            // which is always the case for syndromes of the form e * H^T.
+            rc = osd_launch(c, P, tsize == 8, -1, st);
+            if (rc) return rc;
+        }
+    }
+    return QLDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer API
+// ------------------------------------------------------------------------------------------------
+extern "C" int qldpc_bp_decode_host(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                    const uint8_t *synd, int8_t *hard, uint8_t *conv, int32_t *iters, double *llr)
+{
+    if (!c || !synd || !hard || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bp_decode_host: null argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t st = 0;
+    const int tsize = cfg->precision == 64 ? 8 : 4;
+    const long long chunk = std::min<long long>(CHUNK, 1ll << 20);
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_conv.reserve((size_t)b));
+        CK(c->ws_iters.reserve(4 * (size_t)b));
+        if (llr) CK(c->ws_llr.reserve((size_t)b * c->n * 8));   // room for the float64 copy
+        CK(cudaMemcpyAsync(c->ws_u8a.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_synd.as<uint32_t>(), b, c->m, st)) return rc;
+        void *dllr = nullptr;
+        if (llr) {
+            // float32 results are widened on the device into the same buffer, back to front is unsafe: use a second one
+            if (tsize == 4) { CK(c->ws_llr_in.reserve((size_t)b * c->n * 4)); dllr = c->ws_llr_in.p; }
+            else dllr = c->ws_llr.p;
+        }
+        if (int rc = qldpc_bp_decode_dev(c, cfg, prior, b, c->ws_synd.as<uint32_t>(), c->ws_hard.as<uint32_t>(),
+                                         c->ws_conv.as<uint8_t>(), c->ws_iters.as<int32_t>(), dllr, QLDPC_LLR_ALL, nullptr,
+                                         nullptr, nullptr, st))
+            return rc;
+        if (int rc = qldpc_unpack_bits_dev(c->ws_hard.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(hard + (size_t)o * c->n, c->ws_u8a.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(conv + o, c->ws_conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
+        if (iters) CK(cudaMemcpyAsync(iters + o, c->ws_iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
+        if (llr) {
+            if (tsize == 4) {
+                cast_kernel<float, double><<<grid_for(b * c->n, 256, c->num_sms), 256, 0, st>>>(
+                    c->ws_llr_in.as<float>(), c->ws_llr.as<double>(), b * (long long)c->n);
+                CK(cudaGetLastError());
+            }
+            CK(cudaMemcpyAsync(llr + (size_t)o * c->n, c->ws_llr.p, (size_t)b * c->n * 8, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaStreamSynchronize(st));
+    }
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *synd, const double *llr, const uint8_t *hard,
+                                     int32_t order, int64_t max_combinations, uint8_t *out)
+{
+    if (!c || !synd || !llr || !hard || !out) return fail(QLDPC_ERR_ARG, "qldpc_osd_decode_host: null argument");
+    cudaStream_t st = 0;
+    const long long chunk = 1ll << 18;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_u8b.reserve((size_t)b * c->n));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_valid.reserve((size_t)b));
+        CK(c->ws_llr.reserve((size_t)b * c->n * 8));
+        CK(cudaMemcpyAsync(c->ws_u8a.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_synd.as<uint32_t>(), b, c->m, st)) return rc;
+        CK(cudaMemcpyAsync(c->ws_u8b.p, hard + (size_t)o * c->n, (size_t)b * c->n, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8b.as<uint8_t>(), c->ws_hard.as<uint32_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(c->ws_llr.p, llr + (size_t)o * c->n, (size_t)b * c->n * 8, cudaMemcpyHostToDevice, st));
+        OSDParams P;
+        memset(&P, 0, sizeof(P));
+        P.idx = nullptr; P.count_dev = nullptr; P.count_host = b;
+        P.synd = c->ws_synd.as<uint32_t>();
+        P.llr = c->ws_llr.p;
+        P.hard = c->ws_hard.as<uint32_t>();
+        P.out = c->ws_err.as<uint32_t>();
+        P.valid = c->ws_valid.as<uint8_t>();
+        const bool want_rec = order > 0;
+        if (want_rec) {
+            const size_t rec = (size_t)b * (4 * (size_t)c->n + 4 * (size_t)c->m + c->m + 4) + 64;
+            CK(c->ws_rec.reserve(rec));
+            unsigned char *r = c->ws_rec.as<unsigned char>();
+            P.rec_ordering = reinterpret_cast<int32_t *>(r);             r += 4 * (size_t)b * c->n;
+            P.rec_pivcol = reinterpret_cast<int32_t *>(r);               r += 4 * (size_t)b * c->m;
+            P.rec_npiv = reinterpret_cast<int32_t *>(r);                 r += 4 * (size_t)b;
+            P.rec_sred = reinterpret_cast<uint8_t *>(r);
+        }
+        if (int rc = osd_launch(c, P, 1, b, st)) return rc;
+        if (order > 0) {
+            // OSD-w sweep on the shots whose OSD-0 solution misses the syndrome (OSD_enhanced.py:66-131)
+            OSDWParams W;
+            memset(&W, 0, sizeof(W));
+            W.m = c->m; W.n = c->n; W.WM = c->WM; W.WN = c->WN;
+            W.Hrows = c->d_Hrows;
+            W.count = b;
+            W.synd = P.synd; W.llr = reinterpret_cast<const double *>(P.llr); W.hard = P.hard;
+            W.sol = P.out; W.valid = P.valid;
+            W.rec_ordering = P.rec_ordering; W.rec_pivcol = P.rec_pivcol; W.rec_sred = P.rec_sred; W.rec_npiv = P.rec_npiv;
+            W.order = order;
+            W.max_combinations = max_combinations > 0 ? max_combinations : 0;
+            cudaError_t e = launch_osdw(W, c->num_sms, st);
+            if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osdw_kernel launch: ") + cudaGetErrorString(e));
+        }
+        if (int rc = qldpc_unpack_bits_dev(c->ws_err.as<uint32_t>(), c->ws_u8b.as<uint8_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(out + (size_t)o * c->n, c->ws_u8b.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                       const uint8_t *synd, int32_t osd_order, uint8_t *corr, uint8_t *conv, int32_t *iters)
+{
+    if (!c || !synd || !corr || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_host: null argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t st = 0;
+    const long long chunk = CHUNK;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_conv.reserve((size_t)b));
+        CK(c->ws_iters.reserve(4 * (size_t)b));
+        CK(cudaMemcpyAsync(c->ws_u8a.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_synd.as<uint32_t>(), b, c->m, st)) return rc;
+        if (int rc = qldpc_bposd_decode_dev(c, cfg, prior, b, c->ws_synd.as<uint32_t>(), osd_order, c->ws_hard.as<uint32_t>(),
+                                            c->ws_conv.as<uint8_t>(), c->ws_iters.as<int32_t>(), nullptr, st))
+            return rc;
+        if (int rc = qldpc_unpack_bits_dev(c->ws_hard.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(corr + (size_t)o * c->n, c->ws_u8a.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(conv + o, c->ws_conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
+        if (iters) CK(cudaMemcpyAsync(iters + o, c->ws_iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_check_host(qldpc_code *c, int64_t B, const uint8_t *err, const uint8_t *corr, const uint8_t *synd,
+                                const uint8_t *conv, const int32_t *iters, int32_t distance, uint8_t *flags,
+                                int32_t *weight, uint64_t *counters)
+{
+    if (!c || !err || !corr || !synd) return fail(QLDPC_ERR_ARG, "qldpc_check_host: null argument");
+    cudaStream_t st = 0;
+    CK(c->ws_cnt.reserve(8 * QLDPC_NUM_COUNTERS));
+    CK(cudaMemsetAsync(c->ws_cnt.p, 0, 8 * QLDPC_NUM_COUNTERS, st));
+    const long long chunk = 1ll << 20;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_conv.reserve((size_t)b));
+        CK(c->ws_iters.reserve(4 * (size_t)b));
+        CK(c->ws_flags.reserve((size_t)b));
+        CK(c->ws_weight.reserve(4 * (size_t)b));
+        CK(cudaMemcpyAsync(c->ws_u8a.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_synd.as<uint32_t>(), b, c->m, st)) return rc;
+        CK(cudaMemcpyAsync(c->ws_u8a.p, err + (size_t)o * c->n, (size_t)b * c->n, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_err.as<uint32_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(c->ws_u8a.p, corr + (size_t)o * c->n, (size_t)b * c->n, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_hard.as<uint32_t>(), b, c->n, st)) return rc;
+        if (conv) CK(cudaMemcpyAsync(c->ws_conv.p, conv + o, (size_t)b, cudaMemcpyHostToDevice, st));
+        if (iters) CK(cudaMemcpyAsync(c->ws_iters.p, iters + o, 4 * (size_t)b, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_check_dev(c, b, c->ws_err.as<uint32_t>(), c->ws_hard.as<uint32_t>(), c->ws_synd.as<uint32_t>(),
+                                     conv ? c->ws_conv.as<uint8_t>() : nullptr, iters ? c->ws_iters.as<int32_t>() : nullptr,
+                                     distance, c->ws_flags.as<uint8_t>(), c->ws_weight.as<int32_t>(), c->ws_cnt.as<uint64_t>(), st))
+            return rc;
+        if (flags) CK(cudaMemcpyAsync(flags + o, c->ws_flags.p, (size_t)b, cudaMemcpyDeviceToHost, st));
+        if (weight) CK(cudaMemcpyAsync(weight + o, c->ws_weight.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (counters) CK(cudaMemcpy(counters, c->ws_cnt.p, 8 * QLDPC_NUM_COUNTERS, cudaMemcpyDeviceToHost));
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_sample_host(qldpc_code *c, double p, uint64_t seed, uint64_t first_shot, int32_t draws, int64_t B,
+                                 uint8_t *err, uint8_t *synd)
+{
+    if (!c || !err || !synd) return fail(QLDPC_ERR_ARG, "qldpc_sample_host: null argument");
+    cudaStream_t st = 0;
+    const long long chunk = 1ll << 20;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        if (int rc = qldpc_sample_dev(c, p, seed, first_shot + (uint64_t)o, draws, b, c->ws_err.as<uint32_t>(),
+                                      c->ws_synd.as<uint32_t>(), st))
+            return rc;
+        if (int rc = qldpc_unpack_bits_dev(c->ws_err.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(err + (size_t)o * c->n, c->ws_u8a.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (int rc = qldpc_unpack_bits_dev(c->ws_synd.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->m, st)) return rc;
+        CK(cudaMemcpyAsync(synd + (size_t)o * c->m, c->ws_u8a.p, (size_t)b * c->m, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_mc_sweep(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, double p, uint64_t seed,
+                              uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order, int32_t distance,
+                              uint64_t *counters)
+{
+    if (!c || !counters) return fail(QLDPC_ERR_ARG, "qldpc_mc_sweep: null argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t st = 0;
+    CK(c->ws_cnt.reserve(8 * QLDPC_NUM_COUNTERS));
+    CK(cudaMemsetAsync(c->ws_cnt.p, 0, 8 * QLDPC_NUM_COUNTERS, st));
+    const long long chunk = CHUNK;
+    for (long long o = 0; o < nshots; o += chunk) {
+        const long long b = std::min<long long>(chunk, nshots - o);
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_conv.reserve((size_t)b));
+        CK(c->ws_iters.reserve(4 * (size_t)b));
+        if (int rc = qldpc_sample_dev(c, p, seed, first_shot + (uint64_t)o, draws, b, c->ws_err.as<uint32_t>(),
+                                      c->ws_synd.as<uint32_t>(), st))
+            return rc;
+        if (int rc = qldpc_bposd_decode_dev(c, cfg, prior, b, c->ws_synd.as<uint32_t>(), osd_order, c->ws_hard.as<uint32_t>(),
+                                            c->ws_conv.as<uint8_t>(), c->ws_iters.as<int32_t>(), nullptr, st))
+            return rc;
+        if (int rc = qldpc_check_dev(c, b, c->ws_err.as<uint32_t>(), c->ws_hard.as<uint32_t>(), c->ws_synd.as<uint32_t>(),
+                                     c->ws_conv.as<uint8_t>(), c->ws_iters.as<int32_t>(), distance, nullptr, nullptr,
+                                     c->ws_cnt.as<uint64_t>(), st))
+            return rc;
+    }
+    uint64_t h[QLDPC_NUM_COUNTERS];
+    CK(cudaMemcpyAsync(h, c->ws_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < QLDPC_NUM_COUNTERS; ++i) counters[i] += h[i];
+    return QLDPC_OK;
+}

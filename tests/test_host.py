@@ -1,0 +1,92 @@
+"""CPU tests of the host-side logic and of the C-ABI library's surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_code_file
+from oracle import oracle as O
+from qldpc_b200 import graph as G
+
+
+def test_library_exports_every_declared_symbol():
+    from qldpc_b200 import _lib, build
+    build.build_library()
+    header = open(os.path.join(ROOT, "include", "qldpc_b200.h")).read()
+    declared = set(re.findall(r"\b(qldpc_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    raw = ctypes.CDLL(build.LIB)
+    for name in sorted(declared):
+        assert hasattr(raw, name), "library does not export %s" % name
+    assert declared == set(_lib.EXPORTED)
+    L = _lib.lib()           # binds argtypes for every symbol
+    assert L.qldpc_version() >= 100
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a CUDA device every compute entry point must fail loudly."""
+    from qldpc_b200 import _lib, Code, QldpcError
+    if _lib.lib().qldpc_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    H, _ = load_code_file("[[72, 12, 6]]")
+    with pytest.raises(QldpcError):
+        Code(H)
+
+
+@pytest.mark.parametrize("stem", ["steane", "[[72, 12, 6]]", "[[90, 8, 10]]", "[[108, 8, 10]]", "[[144, 12, 12]]", "[[288, 12, 18]]"])
+def test_graph_tables_and_schedule_probe(stem):
+    """graph.py finds NumPy's summation order by probing NumPy; the oracle derives it symbolically.
+    Both must describe the same sums."""
+    H, _ = load_code_file(stem)
+    g = G.build_graph(H, G.PAIRWISE, G.SEQ)
+    o = O.Graph(H, O.PAIRWISE, O.SEQ)
+    assert np.array_equal(g["row_ptr"], o.row_ptr) and np.array_equal(g["col_idx"], o.col_idx)
+    assert np.array_equal(g["var_ptr"], o.var_ptr) and np.array_equal(g["var_edge1"], o.var_edge1)
+    for v in range(g["n"]):
+        a = g["var_edge0"][g["var_ptr"][v]:g["var_ptr"][v + 1]]
+        b = o.var_edge0[o.var_ptr[v]:o.var_ptr[v + 1]]
+        if len(a) == 3:       # (x + y) + z: the first two commute
+            assert set(a[:2]) == set(b[:2]) and a[2] == b[2]
+        else:
+            assert sorted(a) == sorted(b)
+    # the probed order really reproduces np.sum on a Fortran-ordered array
+    rng = np.random.default_rng(0)
+    R = np.where(np.asarray(H) != 0, rng.normal(0, 3, H.shape), 0.0)
+    Rf = np.asfortranarray(R)
+    want = np.sum(Rf, axis=0)
+    edge_val = R[np.repeat(np.arange(g["m"]), np.diff(g["row_ptr"])), g["col_idx"]]
+    for v in range(g["n"]):
+        e = g["var_edge0"][g["var_ptr"][v]:g["var_ptr"][v + 1]]
+        s = edge_val[e[0]]
+        for x in e[1:]:
+            s = s + edge_val[x]
+        assert s == want[v]
+
+
+def test_reference_schedule_rules():
+    H, _ = load_code_file("[[144, 12, 12]]")
+    assert G.reference_schedule(H, "sum_product") == (G.PAIRWISE, G.PAIRWISE)
+    assert G.reference_schedule(H, "min_sum") == (G.PAIRWISE, G.SEQ)
+    assert G.reference_schedule(np.ascontiguousarray(H), "min_sum") == (G.SEQ, G.SEQ)
+    H288, _ = load_code_file("[[288, 12, 18]]")
+    assert G.reference_schedule(H288, "min_sum") == (G.PAIRWISE, G.PAIRWISE)
+    assert G.reference_schedule(H, "loop") == (G.SEQ, G.SEQ)
+    for v, ov in (("sum_product", O.SUM_PRODUCT), ("min_sum", O.MIN_SUM), ("sum_product_sym", O.SUM_PRODUCT_SYM)):
+        for Hx in (H, H288, np.ascontiguousarray(H)):
+            assert G.reference_schedule(Hx, v) == O.auto_schedule(Hx, ov)
+
+
+def test_spacetime_host(spacetime_golden):
+    from qldpc_b200.spaceTime import spaceTimeMatrix, spacetimeSyndrome
+    d = spacetime_golden
+    H, _ = load_code_file("[[72, 12, 6]]")
+    Hst = spaceTimeMatrix(H, 3)
+    ref = np.zeros(tuple(d["Hst_shape"]))
+    ref[d["Hst_rows"], d["Hst_cols"]] = 1.0
+    assert Hst.dtype == np.float64 and Hst.flags["C_CONTIGUOUS"] and np.array_equal(Hst, ref)
+    assert np.array_equal(spaceTimeMatrix(H, 1), O.space_time_matrix(H, 1))
+    np.random.seed(5)
+    e, s = spacetimeSyndrome(H, 0.03, 3)
+    assert np.array_equal(e, d["seed5_error"]) and np.array_equal(s, d["seed5_syndrome"])

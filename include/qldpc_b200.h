@@ -63,8 +63,12 @@ typedef struct {
     int32_t variant;    /* QLDPC_MIN_SUM | QLDPC_SUM_PRODUCT | QLDPC_SUM_PRODUCT_SYM                 */
     int32_t precision;  /* 32: float32 messages (production) | 64: float64, the reference's arithmetic */
     int32_t max_iter;   /* maxIter of the reference                                                  */
-    int32_t staged;     /* 0: auto (shared memory when the per-shot state fits, else HBM-staged);
-                           1: force the HBM-staged kernel                                             */
+    int32_t staged;     /* kernel choice.  0: auto -- float32 min-sum on a uniform-row-weight H runs the
+                           T-lanes-per-shot shared-memory kernel, anything else the thread-per-shot kernel,
+                           in shared memory when the per-shot state fits, else HBM-staged;
+                           1: force the HBM-staged kernel; 2: force the thread-per-shot kernel            */
+    int32_t lanes_per_shot; /* 0: auto | 4 | 8 (T-lanes-per-shot kernel)                             */
+    int32_t refill_min; /* 0: auto.  Idle shots per warp that trigger a refill from the shot cursor  */
     double alpha;       /* min-sum normalisation / sum-product scaling                               */
     double damping;     /* damping on Q                                                              */
     double clip;        /* clip_llr                                                                  */

@@ -19,6 +19,7 @@ COUNTER_NAMES = ["shots", "bp_failed", "logical", "logical_and_osd", "degenerate
 
 class BPConfig(ctypes.Structure):
     _fields_ = [("variant", c_i32), ("precision", c_i32), ("max_iter", c_i32), ("staged", c_i32),
+                ("lanes_per_shot", c_i32), ("refill_min", c_i32),
                 ("alpha", c_dbl), ("damping", c_dbl), ("clip", c_dbl)]
 
 

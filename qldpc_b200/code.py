@@ -76,12 +76,15 @@ class Code:
 
     # ------------------------------------------------------------------------------------------
     @staticmethod
-    def config(variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0, precision=32, staged=False):
+    def config(variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0, precision=32, staged=False,
+               lanes_per_shot=0, refill_min=0):
         cfg = _lib.BPConfig()
         cfg.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
         cfg.precision = int(precision)
         cfg.max_iter = int(max_iter)
-        cfg.staged = 1 if staged else 0
+        cfg.staged = int(staged)          # 0 auto | 1 (True) HBM-staged | 2 thread-per-shot
+        cfg.lanes_per_shot = int(lanes_per_shot)
+        cfg.refill_min = int(refill_min)
         cfg.alpha, cfg.damping, cfg.clip = float(alpha), float(damping), float(clip)
         return cfg
 
@@ -96,17 +99,20 @@ class Code:
     def geometry(self, cfg):
         a, b, c = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         _lib.check(_lib.lib().qldpc_bp_geometry(self._h, ctypes.byref(cfg), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-        return dict(shots_per_cta=a.value, smem_bytes=b.value, staged=bool(c.value))
+        kind = c.value
+        return dict(shots_per_cta=a.value, smem_bytes=b.value, staged=(kind == 1),
+                    lanes_per_shot=(kind - 100 if kind >= 100 else 1),
+                    kernel=('hbm_staged' if kind == 1 else 'tiled' if kind >= 100 else 'thread_per_shot'))
 
     # ---- host-array API (reference dtypes) -------------------------------------------------------
     def bp_decode_batch(self, syndromes, prior, variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0,
-                        precision=32, want_llr=True, staged=False):
+                        precision=32, want_llr=True, staged=False, lanes_per_shot=0, refill_min=0):
         """-> (hard int8 (B,n), converged bool (B,), llr float64 (B,n) | None, iters int32 (B,))"""
         synd = _bits(syndromes)
         if synd.ndim != 2 or synd.shape[1] != self.m:
             raise ValueError("syndromes must be (B, m)")
         B = synd.shape[0]
-        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged)
+        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged, lanes_per_shot, refill_min)
         p = self._prior(prior)
         hard = np.zeros((B, self.n), np.int8)
         conv = np.zeros(B, np.uint8)
@@ -133,13 +139,13 @@ class Code:
         return out.astype(np.int64)
 
     def bposd_decode_batch(self, syndromes, prior, variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0,
-                           precision=32, osd_order=0, staged=False, out=None):
+                           precision=32, osd_order=0, staged=False, out=None, lanes_per_shot=0, refill_min=0):
         """BP, then OSD on the BP failures.  -> (corr uint8 (B,n), converged bool (B,), iters int32 (B,))"""
         synd = _bits(syndromes)
         B = synd.shape[0]
         if synd.shape != (B, self.m):
             raise ValueError("syndromes must be (B, m)")
-        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged)
+        cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged, lanes_per_shot, refill_min)
         p = self._prior(prior)
         corr = np.zeros((B, self.n), np.uint8) if out is None else out
         conv = np.zeros(B, np.uint8)

@@ -11,6 +11,7 @@
 
 #include "../../include/qldpc_b200.h"
 #include "bp_kernel.cuh"
+#include "bp_tiled_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "osd_kernel.cuh"
 #include "osdw_kernel.cuh"
@@ -68,6 +69,8 @@ struct qldpc_code {
     int num_sms = 0, smem_optin = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_var_ptr = nullptr;
     uint32_t *d_vtab0 = nullptr, *d_vtab1 = nullptr, *d_colmask = nullptr, *d_Lrows = nullptr, *d_Hrows = nullptr;
+    uint32_t *d_vell0 = nullptr, *d_vell1 = nullptr;   // (check | k << 16) per (variable, t < 3): T-lanes-per-shot kernel
+    bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;
     DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
@@ -146,6 +149,17 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
             colmask[(size_t)v * c->WM + (edge_check[e1] >> 5)] |= 1u << (edge_check[e1] & 31);
         }
     }
+    // ELL view for the T-lanes-per-shot kernel: uniform row weight 6 (all BB codes), column weight <= 3
+    c->tiled_ok = (c->uniform_row_w == 6) && (c->max_col_w <= 3) && (m < 65536) && (c->WM == 2 || c->WM == 3 || c->WM == 5);
+    std::vector<uint32_t> vell0((size_t)n * 3, 0xffffffffu), vell1((size_t)n * 3, 0xffffffffu);
+    if (c->tiled_ok) {
+        for (int v = 0; v < n; ++v)
+            for (int a = var_ptr[v], t = 0; a < var_ptr[v + 1]; ++a, ++t) {
+                const int e0 = var_edge0[a], e1 = var_edge1[a];
+                vell0[(size_t)v * 3 + t] = (uint32_t)edge_check[e0] | ((uint32_t)(e0 - row_ptr[edge_check[e0]]) << 16);
+                vell1[(size_t)v * 3 + t] = (uint32_t)edge_check[e1] | ((uint32_t)(e1 - row_ptr[edge_check[e1]]) << 16);
+            }
+    }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
     for (int r = 0; r < k; ++r)
         for (int j = 0; j < n; ++j)
@@ -161,6 +175,8 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
     CK(upload(&c->d_colmask, colmask));
     CK(upload(&c->d_Lrows, Lrows));
     CK(upload(&c->d_Hrows, Hrows));
+    CK(upload(&c->d_vell0, vell0));
+    CK(upload(&c->d_vell1, vell1));
     CK(c->ctrl.reserve(sizeof(Ctrl)));
     *out = c;
     return QLDPC_OK;
@@ -171,6 +187,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     if (!c) return;
     cudaFree(c->d_row_ptr); cudaFree(c->d_col_idx); cudaFree(c->d_var_ptr);
     cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
+    cudaFree(c->d_vell0); cudaFree(c->d_vell1);
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
                       &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
@@ -183,6 +200,9 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
 // ------------------------------------------------------------------------------------------------
 struct BPGeom {
     bool staged;
+    int tiled_T;          // 0: thread-per-shot kernels; 4 / 8: lanes per shot of the tiled kernel
+    int shots_per_cta;
+    int refill_min;
     int threads, grid;
     size_t smem;
     size_t gstate_bytes;
@@ -196,19 +216,51 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     const BPGraphDev g = c->graph();
     const BPSmemLayout L = bp_smem_layout(g, tsize, kernel_variant(cfg->variant));
     const bool wm_ok = (c->WM <= 5);
+    G->tiled_T = 0;
+    G->refill_min = 1;
+    if (cfg->staged == 0 && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM && c->tiled_ok) {
+        // T lanes per shot; NW warps with NW = 1 (mod T) keeps the check pass bank-conflict free
+        int bestT = 0, bestNW = 0;
+        for (int T : {4, 8}) {
+            if (cfg->lanes_per_shot && cfg->lanes_per_shot != T) continue;
+            const BPTiledLayout TL = bp_tiled_layout(g, T);
+            const int Gs = 32 / T;
+            if (TL.tables + (size_t)Gs * TL.per_slot > (size_t)c->smem_optin) continue;
+            long long smax = (long long)(((size_t)c->smem_optin - TL.tables) / TL.per_slot);
+            long long nw = std::min<long long>(smax / Gs, 16);
+            nw = std::min<long long>(nw, std::max<long long>(1, (B + Gs - 1) / Gs));
+            while (nw > 1 && (nw % T) != 1) --nw;
+            if (nw >= 1 && (nw > bestNW || bestT == 0)) { bestT = T; bestNW = (int)nw; }
+        }
+        if (bestT) {
+            const BPTiledLayout TL = bp_tiled_layout(g, bestT);
+            const int Gs = 32 / bestT;
+            G->staged = false;
+            G->tiled_T = bestT;
+            G->threads = 32 * bestNW;
+            G->shots_per_cta = bestNW * Gs;
+            G->smem = TL.tables + (size_t)G->shots_per_cta * TL.per_slot;
+            G->grid = (int)std::max<long long>(1, std::min<long long>((B + G->shots_per_cta - 1) / G->shots_per_cta, c->num_sms));
+            G->gstate_bytes = 0;
+            G->refill_min = cfg->refill_min > 0 ? std::min(cfg->refill_min, Gs) : std::max(1, Gs / 4);
+            return QLDPC_OK;
+        }
+    }
     long long nt = 0;
-    if (!cfg->staged && wm_ok && L.tables + 32 * L.per_shot <= (size_t)c->smem_optin)
+    if (cfg->staged != 1 && wm_ok && L.tables + 32 * L.per_shot <= (size_t)c->smem_optin)
         nt = std::min<long long>(256, (long long)(((size_t)c->smem_optin - L.tables) / L.per_shot)) / 32 * 32;
     if (nt >= 32) {
         G->staged = false;
         long long want = std::max<long long>(32, (B + 31) / 32 * 32);
         G->threads = (int)std::min<long long>(nt, want);
+        G->shots_per_cta = G->threads;
         G->smem = L.tables + (size_t)G->threads * L.per_shot;
         G->grid = (int)std::max<long long>(1, std::min<long long>((B + G->threads - 1) / G->threads, c->num_sms));
         G->gstate_bytes = 0;
     } else {
         G->staged = true;
         G->threads = 128;
+        G->shots_per_cta = 128;
         G->smem = 0;
         G->grid = (int)std::max<long long>(1, std::min<long long>((B + 127) / 128, (long long)c->num_sms * 4));
         const size_t per_thread = (size_t)tsize * (c->E + 2 * (size_t)c->m) + 4 * (size_t)(c->WN + c->WM);
@@ -223,9 +275,9 @@ extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int3
     if (!c || !cfg) return fail(QLDPC_ERR_ARG, "qldpc_bp_geometry: null argument");
     BPGeom G;
     bp_geometry(c, cfg, 1ll << 40, &G);
-    if (shots_per_cta) *shots_per_cta = G.threads;
+    if (shots_per_cta) *shots_per_cta = G.shots_per_cta;
     if (smem_bytes) *smem_bytes = (int32_t)G.smem;
-    if (staged) *staged = G.staged ? 1 : 0;
+    if (staged) *staged = G.staged ? 1 : (G.tiled_T ? 100 + G.tiled_T : 0);
     return QLDPC_OK;
 }
 
@@ -265,6 +317,25 @@ static cudaError_t launch_bp_inst(const BPParams &P, const BPGeom &G, cudaStream
     }
     kern<<<G.grid, G.threads, G.smem, st>>>(P);
     return cudaGetLastError();
+}
+
+template <int T, int WMS>
+static cudaError_t launch_bp_tiled_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    auto kern = bp_tiled_kernel<T, WMS, 6>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+    if (e != cudaSuccess) return e;
+    kern<<<G.grid, G.threads, G.smem, st>>>(P, c->d_vell0, c->d_vell1, G.refill_min);
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_bp_tiled(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+#define TILED_CASE(TT, WW) if (G.tiled_T == TT && P.g.WM == WW) return launch_bp_tiled_inst<TT, WW>(c, P, G, st)
+    TILED_CASE(4, 2); TILED_CASE(4, 3); TILED_CASE(4, 5);
+    TILED_CASE(8, 2); TILED_CASE(8, 3); TILED_CASE(8, 5);
+#undef TILED_CASE
+    return cudaErrorInvalidValue;
 }
 
 template <typename T, int VAR>
@@ -325,7 +396,9 @@ extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, co
     P.gstate = c->gstate.p;
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
-    if (cfg->precision == 64)
+    if (G.tiled_T)
+        e = launch_bp_tiled(c, P, G, st);
+    else if (cfg->precision == 64)
         e = (kv == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
     else
         e = (kv == VAR_MIN_SUM) ? launch_bp_tv<float, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<float, VAR_SUM_PRODUCT>(P, G, st);

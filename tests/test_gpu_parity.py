@@ -184,6 +184,39 @@ def test_staged_kernel_matches_on_chip_kernel():
         assert np.array_equal(x, y)
 
 
+@pytest.mark.parametrize("stem,p", [("[[72, 12, 6]]", 0.06), ("[[90, 8, 10]]", 0.05), ("[[108, 8, 10]]", 0.05),
+                                    ("[[144, 12, 12]]", 0.05), ("[[288, 12, 18]]", 0.05)])
+def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
+    """The production T-lanes-per-shot kernel performs the same float32 operations in the same order as
+    the thread-per-shot kernel: results must be bit-identical (hard, flag, exit iteration, LLRs), for
+    T = 4 and 8, any refill threshold, ragged batch sizes."""
+    H, _ = load_code_file(stem)
+    n = H.shape[1]
+    rng = np.random.default_rng(17)
+    err = (rng.random((5003, n)) < p).astype(np.uint8)
+    synd = _synd(H, err)
+    code = _code(H, "min_sum")
+    prior = _prior(p, n)
+    kw = dict(variant="min_sum", max_iter=60, alpha=0.8, damping=0.7, clip=25.0, precision=32)
+    ref = code.bp_decode_batch(synd, prior, staged=2, **kw)
+    assert code.geometry(code.config(**kw))["kernel"] == "tiled"
+    for T in (4, 8):
+        for rmin in (0, 1, 32 // T):
+            got = code.bp_decode_batch(synd, prior, lanes_per_shot=T, refill_min=rmin, **kw)
+            for x, y in zip(got, ref):
+                assert np.array_equal(x, y), (stem, T, rmin)
+    for B in (1, 7, 65):
+        got = code.bp_decode_batch(synd[:B], prior, **kw)
+        for x, y in zip(got, ref):
+            assert np.array_equal(x, y[:B])
+    # non-uniform prior and default parameters (alpha = damping = 1)
+    pr = rng.uniform(1.5, 4.0, n)
+    a = code.bp_decode_batch(synd[:800], pr, "min_sum", 30, precision=32, staged=2)
+    b = code.bp_decode_batch(synd[:800], pr, "min_sum", 30, precision=32)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
 def test_spacetime_bp_staged(spacetime_golden):
     """BASELINE config 4 (scaled to 3 rounds of [[72,12,6]] so the golden file stays small): BP on the
     space-time matrix, message state staged in HBM."""

@@ -100,6 +100,16 @@ template <> struct Num<double> {
     __device__ static __forceinline__ double atanh_(double x) { return atanh(x); }
 };
 
+// Damping  Q = d * Q_new + (1 - d) * Q_old  (rework/decoding.py:65).  float64 keeps the reference's three
+// roundings (NumPy evaluates the two products and the sum as separate ufuncs); the float32 production
+// kernels fuse the second product into the add (one rounding fewer, one instruction fewer).
+__device__ __forceinline__ double bp_damp(double d, double qn, double omd, double qo) { return __dadd_rn(__dmul_rn(d, qn), __dmul_rn(omd, qo)); }
+__device__ __forceinline__ float bp_damp(float d, float qn, float omd, float qo) { return __fmaf_rn(d, qn, __fmul_rn(omd, qo)); }
+// sign(0) is + in the reference (decoding.py:30): the float64 kernel turns a -0.0 message into +0.0 so that the
+// sign-bit XOR of the check pass is exact.  -0.0 can only arise from an underflow in float32; not canonicalised there.
+__device__ __forceinline__ double bp_canon(double q) { return __dadd_rn(q, 0.0); }
+__device__ __forceinline__ float bp_canon(float q) { return q; }
+
 // Shared-memory footprint, shared with the host (capi.cu) so both agree on the carve-up.
 struct BPSmemLayout {
     size_t off_rowptr, off_varptr, off_vtab0, off_vtab1, off_colmask, off_prior, off_state;
@@ -366,9 +376,9 @@ bp_decode_kernel(const BPParams P)
                     if (k < deg) {
                         T qn = N::sub(val, r[k]);
                         if (VAR == VAR_MIN_SUM || P.sym) {
-                            qn = N::add(N::mul(damp, qn), N::mul(omd, qo[k]));
+                            qn = bp_damp(damp, qn, omd, qo[k]);
                             qn = fmin(fmax(qn, -clipv), clipv);
-                            qn = N::add(qn, (T)0);                                    // canonical +0.0
+                            qn = bp_canon(qn);
                         } else if (slot_is_tanh) {
                             qn = N::tanh_(N::mul(qn, (T)0.5));
                         }
@@ -397,9 +407,9 @@ bp_decode_kernel(const BPParams P)
                         }
                         T qn = N::sub(val, rr);
                         if (VAR == VAR_MIN_SUM || P.sym) {
-                            qn = N::add(N::mul(damp, qn), N::mul(omd, q));
+                            qn = bp_damp(damp, qn, omd, q);
                             qn = fmin(fmax(qn, -clipv), clipv);
-                            qn = N::add(qn, (T)0);
+                            qn = bp_canon(qn);
                         } else if (slot_is_tanh) {
                             qn = N::tanh_(N::mul(qn, (T)0.5));
                         }

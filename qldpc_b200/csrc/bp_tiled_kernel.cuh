@@ -50,7 +50,8 @@ __host__ __device__ inline BPTiledLayout bp_tiled_layout(const BPGraphDev &g, in
     o = (o + 127) & ~(size_t)127;
     L.off_state = o;
     L.tables = o;
-    // rows: RW*m message rows + 2*m summary rows + WN hard-decision rows, 4 bytes per slot each
+    // rows: RW*m message rows (4 B per slot) + m summary rows (float2 {signed min1, min2}: 8 B per slot)
+    // + WN hard-decision rows (4 B per slot)
     L.per_slot = 4 * ((size_t)g.uniform_row_w * g.m + 2 * (size_t)g.m + g.WN);
     return L;
 }
@@ -58,7 +59,7 @@ __host__ __device__ inline BPTiledLayout bp_tiled_layout(const BPGraphDev &g, in
 // vell tables (global, built by the host): entry (v, t), t < 3: c | (k << 16), or 0xFFFFFFFF when
 // variable v has fewer than t+1 edges.  c = check, k = position of v inside row c.
 template <int T, int WMS, int RW>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(576, 1)
 bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint32_t *__restrict__ vell1, int refill_min)
 {
     constexpr int G = 32 / T;                 // shots per warp
@@ -79,7 +80,7 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
     float *prior = reinterpret_cast<float *>(smem + L.off_prior);
     unsigned char *state = smem + L.off_state;
     const uint32_t rowB = 4u * S;                               // bytes per row
-    const uint32_t offM1 = (uint32_t)RW * m * rowB, offM2 = offM1 + (uint32_t)m * rowB, offHW = offM2 + (uint32_t)m * rowB;
+    const uint32_t offM = (uint32_t)RW * m * rowB, offHW = offM + 2u * (uint32_t)m * rowB;   // summaries: 2*rowB per check
 
     for (int i = threadIdx.x; i < L.npad * 3; i += blockDim.x) {
         const int v = i / 3;
@@ -87,7 +88,7 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
         auto mk = [&](uint32_t e) {
             if (e == 0xffffffffu) return make_uint2(0xffffffffu, 0u);
             const uint32_t c = e & 0xffffu, k = e >> 16;
-            return make_uint2((k * m + c) * rowB, offM1 + c * rowB);
+            return make_uint2((k * m + c) * rowB, offM + c * 2u * rowB);
         };
         vt0[i] = mk(e0);
         if (g.two_tables) vt1[i] = mk(e1);
@@ -96,7 +97,8 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
     for (int i = threadIdx.x; i < L.npad; i += blockDim.x) prior[i] = (i < n) ? reinterpret_cast<const float *>(P.prior)[i] : 0.f;
     __syncthreads();
 
-    unsigned char *my = state + 4 * slot;                       // this shot's column
+    unsigned char *my = state + 4 * slot;                       // this shot's column in the 4-byte rows
+    unsigned char *my8 = state + 8 * slot;                      // ... and in the 8-byte summary rows
     const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
     const int max_iter = P.max_iter;
 
@@ -128,8 +130,7 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                         const float pv = prior[v] + 0.f;
 #pragma unroll
                         for (int t = 0; t < 3; ++t) {
-                            const uint2 e = vt1[v * 3 + t];
-                            if (e.x != 0xffffffffu) *reinterpret_cast<float *>(my + e.x) = pv;
+                            *reinterpret_cast<float *>(my + vt1[v * 3 + t].x) = pv;
                         }
                     }
                     iter = 0;
@@ -149,29 +150,27 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
             // ================= horizontal step: lane j owns checks c = T*i + j ==================
 #pragma unroll
             for (int w = 0; w < WMS; ++w) {
-                const uint32_t sw = synd[w];
+                const uint32_t sw = synd[w] >> j;
+                const int cnt = min(VPW, (m - 32 * w - j + T - 1) / T);          // checks of this lane in word w
 #pragma unroll 2
-                for (int ii = 0; ii < VPW; ++ii) {
-                    const int b = T * ii + j;
-                    const int c = 32 * w + b;
-                    if (c < m) {
-                        const unsigned char *q = my + (uint32_t)c * rowB;
-                        float x[RW];
+                for (int ii = 0; ii < cnt; ++ii) {
+                    const int c = 32 * w + T * ii + j;
+                    const unsigned char *q = my + (uint32_t)c * rowB;
+                    float x[RW];
 #pragma unroll
-                        for (int k = 0; k < RW; ++k) x[k] = *reinterpret_cast<const float *>(q + (uint32_t)k * m * rowB);
-                        uint32_t sg = ((sw >> b) & 1u) << 31;
-                        float min1 = CUDART_INF_F, min2 = CUDART_INF_F;
+                    for (int k = 0; k < RW; ++k) x[k] = *reinterpret_cast<const float *>(q + (uint32_t)k * m * rowB);
+                    uint32_t sg = (sw >> (T * ii)) << 31;                          // syndrome bit -> sign bit
+                    float min1 = CUDART_INF_F, min2 = CUDART_INF_F;
 #pragma unroll
-                        for (int k = 0; k < RW; ++k) {
-                            sg ^= __float_as_uint(x[k]);
-                            const float a = fabsf(x[k]);
-                            const float t = fmaxf(min1, a);
-                            min1 = fminf(min1, a);
-                            min2 = fminf(min2, t);
-                        }
-                        *reinterpret_cast<float *>(my + offM1 + (uint32_t)c * rowB) = __uint_as_float(__float_as_uint(min1) | (sg & 0x80000000u));
-                        *reinterpret_cast<float *>(my + offM2 + (uint32_t)c * rowB) = min2;
+                    for (int k = 0; k < RW; ++k) {
+                        sg ^= __float_as_uint(x[k]);
+                        const float a = fabsf(x[k]);
+                        const float t = fmaxf(min1, a);
+                        min1 = fminf(min1, a);
+                        min2 = fminf(min2, t);
                     }
+                    *reinterpret_cast<float2 *>(my8 + offM + (uint32_t)c * 2u * rowB) =
+                        make_float2(__uint_as_float(__float_as_uint(min1) | (sg & 0x80000000u)), min2);
                 }
             }
             __syncwarp(amask);
@@ -185,48 +184,40 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
             for (int k = 0; k < WMS; ++k) acc[k] = 0;
             for (int wv = 0; wv < WN; ++wv) {
                 uint32_t hw = 0;
+                const int cnt = min(VPW, (n - 32 * wv - j + T - 1) / T);         // variables of this lane in word wv
 #pragma unroll 2
-                for (int ii = 0; ii < VPW; ++ii) {
+                for (int ii = 0; ii < cnt; ++ii) {
                     const int b = T * ii + j;
                     const int v = 32 * wv + b;
-                    if (v < n) {
-                        const uint2 *ent = vt + v * 3;
-                        uint2 e[3];
-                        float qo[3], r[3];
+                    const uint2 *ent = vt + v * 3;
+                    uint2 e[3];
+                    float qo[3], r[3];
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) e[t] = ent[t];
+                    for (int t = 0; t < 3; ++t) e[t] = ent[t];
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            r[t] = 0.f;
-                            qo[t] = 0.f;
-                            if (e[t].x != 0xffffffffu) {
-                                const float q = *reinterpret_cast<const float *>(my + e[t].x);
-                                const float s1 = *reinterpret_cast<const float *>(my + e[t].y);
-                                const float s2 = *reinterpret_cast<const float *>(my + e[t].y + (offM2 - offM1));
-                                const float a1 = fabsf(s1);
-                                const float mag = (fabsf(q) == a1) ? s2 : a1;                     // decoding.py:51-53
-                                r[t] = __uint_as_float(__float_as_uint(__fmul_rn(alpha, mag)) ^
-                                                       ((__float_as_uint(s1) ^ __float_as_uint(q)) & 0x80000000u)); // :55
-                                qo[t] = q;
-                            }
-                        }
-                        const float val = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), r[2]), prior[v]);  // :61-62
-                        const bool hd = val < 0.f;
-                        hw |= (uint32_t)hd << b;
-                        if (wr_llr) llr_out[v] = val;
-                        if (hd) {
+                    for (int t = 0; t < 3; ++t) {
+                        const float q = *reinterpret_cast<const float *>(my + e[t].x);
+                        const float2 s12 = *reinterpret_cast<const float2 *>(my8 + e[t].y);
+                        const float a1 = fabsf(s12.x);
+                        const float mag = (fabsf(q) == a1) ? s12.y : a1;                          // decoding.py:51-53
+                        r[t] = __uint_as_float(__float_as_uint(__fmul_rn(alpha, mag)) ^
+                                               ((__float_as_uint(s12.x) ^ __float_as_uint(q)) & 0x80000000u)); // :55
+                        qo[t] = q;
+                    }
+                    const float val = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), r[2]), prior[v]);    // :61-62
+                    const bool hd = val < 0.f;
+                    hw |= (uint32_t)hd << b;
+                    if (wr_llr) llr_out[v] = val;
+                    if (hd) {
 #pragma unroll
-                            for (int k = 0; k < WMS; ++k) acc[k] ^= colmask[v * WMS + k];
-                        }
+                        for (int k = 0; k < WMS; ++k) acc[k] ^= colmask[v * WMS + k];
+                    }
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            if (e[t].x != 0xffffffffu) {
-                                float qn = __fsub_rn(val, r[t]);                                    // :63
-                                qn = __fadd_rn(__fmul_rn(damp, qn), __fmul_rn(omd, qo[t]));         // :65
-                                qn = fminf(fmaxf(qn, -clipv), clipv);                              // :66
-                                *reinterpret_cast<float *>(my + e[t].x) = qn + 0.f;
-                            }
-                        }
+                    for (int t = 0; t < 3; ++t) {
+                        float qn = __fsub_rn(val, r[t]);                                           // :63
+                        qn = bp_damp(damp, qn, omd, qo[t]);                                        // :65
+                        qn = fminf(fmaxf(qn, -clipv), clipv);                                      // :66
+                        *reinterpret_cast<float *>(my + e[t].x) = qn;
                     }
                 }
                 // the T lanes of the shot hold disjoint bits of this word

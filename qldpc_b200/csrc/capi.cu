@@ -150,7 +150,9 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
         }
     }
     // ELL view for the T-lanes-per-shot kernel: uniform row weight 6 (all BB codes), column weight <= 3
-    c->tiled_ok = (c->uniform_row_w == 6) && (c->max_col_w <= 3) && (m < 65536) && (c->WM == 2 || c->WM == 3 || c->WM == 5);
+    int min_col_w = n > 0 ? 1 << 30 : 0;
+    for (int v = 0; v < n; ++v) min_col_w = std::min(min_col_w, var_ptr[v + 1] - var_ptr[v]);
+    c->tiled_ok = (c->uniform_row_w == 6) && (c->max_col_w == 3) && (min_col_w == 3) && (m < 65536) && (c->WM == 2 || c->WM == 3 || c->WM == 5);
     std::vector<uint32_t> vell0((size_t)n * 3, 0xffffffffu), vell1((size_t)n * 3, 0xffffffffu);
     if (c->tiled_ok) {
         for (int v = 0; v < n; ++v)
@@ -227,7 +229,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
             const int Gs = 32 / T;
             if (TL.tables + (size_t)Gs * TL.per_slot > (size_t)c->smem_optin) continue;
             long long smax = (long long)(((size_t)c->smem_optin - TL.tables) / TL.per_slot);
-            long long nw = std::min<long long>(smax / Gs, 16);
+            long long nw = std::min<long long>(smax / Gs, 18);   // __launch_bounds__(576)
             nw = std::min<long long>(nw, std::max<long long>(1, (B + Gs - 1) / Gs));
             while (nw > 1 && (nw % T) != 1) --nw;
             if (nw >= 1 && (nw > bestNW || bestT == 0)) { bestT = T; bestNW = (int)nw; }

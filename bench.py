@@ -290,7 +290,8 @@ def main():
         peak_laneops = n_sm * 128 * sm_max * 1e6
         achieved = iters_exec * A / bp_s
         hbm_bytes_per_shot = 4 * WM + 4 * WN + 1 + 4   # packed syndrome in, packed correction + flag + iteration out
-        roofline = {"bound": "alu", "kernel": "bp_decode_kernel<float,MIN_SUM,3,smem>",
+        kname = ("bp_tiled_kernel<T=%d,WM=%d,RW=6>" % (geom["lanes_per_shot"], WM)) if geom["kernel"] == "tiled" else "bp_decode_kernel<float,MIN_SUM>"
+        roofline = {"bound": "alu", "kernel": kname,
                     "achieved": achieved / 1e12, "peak": peak_laneops / 1e12, "unit": "Tlane-op/s",
                     "frac": achieved / peak_laneops,
                     "peak_def": f"{n_sm} SMs x 128 lanes x {sm_max:.0f} MHz (max clock; median clock under this kernel {sm_mhz:.0f} MHz)",
@@ -316,13 +317,12 @@ def main():
                         "matches_device_path": e2e_matches},
                 "gpu_launches": launches, "clocks": clocks}
         if world == 1 and not args.no_cpu:
-            S = 60000
-            synd_cpu = synd_h[:S].numpy()
+            synd_cpu = synd_h.numpy()
             v, cores, sample, dt, r = cpu_port_throughput(H, synd_cpu, prior)
-            same = bool(np.array_equal(r["corr"], corr_h[:sample].numpy()))
+            same = float((r["corr"] == corr_h[:sample].numpy()).all(1).mean())
             line["cpu_baseline"] = {"value": v, "unit": "shots/s", "cores": cores, "kind": "port",
                                     "sample": f"first {sample} shots of the same workload ({dt:.1f} s; float64 C port of min-sum BP + OSD, OpenMP)",
-                                    "corrections_equal_gpu_f32": same}
+                                    "fraction_of_shots_with_identical_correction_vs_gpu_f32": same}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

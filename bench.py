@@ -129,7 +129,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
     ap.add_argument("--shots", type=int, default=10_000_000, help="shots per step per GPU")
-    ap.add_argument("--e2e-shots", type=int, default=1 << 22)
+    ap.add_argument("--e2e-shots", type=int, default=0, help="shots per e2e step (default: same as --shots)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -243,7 +243,7 @@ def main():
     cd = dict(zip(_lib.COUNTER_NAMES, (int(x) for x in cnt)))
 
     # ---------------- e2e: host buffers through the C ABI ----------------
-    Be = min(args.e2e_shots, B)
+    Be = min(args.e2e_shots, B) if args.e2e_shots > 0 else B
     synd_u8_dev = torch.empty((Be, m), dtype=torch.uint8, device=dev)
     _lib.check(L.qldpc_unpack_bits_dev(synd.data_ptr(), synd_u8_dev.data_ptr(), Be, m, stream), "unpack")
     synd_h = torch.empty((Be, m), dtype=torch.uint8).pin_memory()

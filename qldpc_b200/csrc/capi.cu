@@ -5,6 +5,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -75,6 +76,14 @@ struct qldpc_code {
     DevBuf prior32, prior64, ctrl, gstate;
     DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
         ws_weight, ws_cnt, ws_llr_in, ws_rec;
+    // pipeline slots of the host-pointer decode call: each has its own stream, control block and workspaces so
+    // that the H2D copy / decode / D2H copy of consecutive chunks overlap
+    struct Slot {
+        cudaStream_t st = nullptr;
+        DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail;
+    };
+    static constexpr int NSLOT = 3;
+    Slot slot[NSLOT];
     BPGraphDev graph() const
     {
         BPGraphDev g;
@@ -194,6 +203,11 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
                       &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
     for (DevBuf *b : bufs) b->release();
+    for (auto &sl : c->slot) {
+        DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail};
+        for (DevBuf *b : sb) b->release();
+        if (sl.st) cudaStreamDestroy(sl.st);
+    }
     delete c;
 }
 
@@ -357,10 +371,10 @@ static cudaError_t launch_bp_tv(const BPParams &P, const BPGeom &G, cudaStream_t
     }
 }
 
-extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
-                                   const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters, void *llr,
-                                   int32_t llr_mode, int32_t *fail_idx, uint32_t *fail_count, uint64_t *iter_total,
-                                   void *stream)
+static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
+                          const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters, void *llr,
+                          int32_t llr_mode, int32_t *fail_idx, uint32_t *fail_count, uint64_t *iter_total,
+                          DevBuf *ctrl_buf, DevBuf *gstate_buf, void *stream)
 {
     if (!c || !synd || !hard || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bp_decode_dev: null argument");
     if (int rc = check_cfg(cfg)) return rc;
@@ -370,8 +384,9 @@ extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, co
     if (int rc = set_prior(c, prior_host, st)) return rc;
     BPGeom G;
     bp_geometry(c, cfg, B, &G);
-    if (G.staged) CK(c->gstate.reserve(G.gstate_bytes));
-    Ctrl *ctrl = c->ctrl.as<Ctrl>();
+    if (G.staged) CK(gstate_buf->reserve(G.gstate_bytes));
+    CK(ctrl_buf->reserve(sizeof(Ctrl)));
+    Ctrl *ctrl = ctrl_buf->as<Ctrl>();
     CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st));
     if (fail_count) CK(cudaMemsetAsync(fail_count, 0, sizeof(uint32_t), st));
 
@@ -395,7 +410,7 @@ extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, co
     P.fail_idx = fail_idx;
     P.fail_count = fail_count ? fail_count : &ctrl->fail_count;
     P.iter_total = (unsigned long long *)iter_total;
-    P.gstate = c->gstate.p;
+    P.gstate = gstate_buf->p;
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
     if (G.tiled_T)
@@ -406,6 +421,16 @@ extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, co
         e = (kv == VAR_MIN_SUM) ? launch_bp_tv<float, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<float, VAR_SUM_PRODUCT>(P, G, st);
     if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("bp_decode_kernel launch: ") + cudaGetErrorString(e));
     return QLDPC_OK;
+}
+
+extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
+                                   const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters, void *llr,
+                                   int32_t llr_mode, int32_t *fail_idx, uint32_t *fail_count, uint64_t *iter_total,
+                                   void *stream)
+{
+    if (!c) return fail(QLDPC_ERR_ARG, "qldpc_bp_decode_dev: null code");
+    return bp_decode_impl(c, cfg, prior_host, B, synd, hard, conv, iters, llr, llr_mode, fail_idx, fail_count, iter_total,
+                          &c->ctrl, &c->gstate, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -555,6 +580,41 @@ extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, co
 // ------------------------------------------------------------------------------------------------
 static const long long CHUNK = 1ll << 22;   // shots per internal launch (bounds the LLR workspace)
 
+// BP, then OSD-0 on the compacted BP failures, for at most CHUNK shots, with explicit workspaces
+static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, long long b, const uint32_t *synd,
+                       int32_t osd_order, uint32_t *corr, uint8_t *conv, int32_t *iters, uint64_t *iter_total,
+                       DevBuf *ctrl, DevBuf *gstate, DevBuf *llr_buf, DevBuf *fail_buf, cudaStream_t st)
+{
+    const int tsize = cfg->precision == 64 ? 8 : 4;
+    void *llr = nullptr;
+    int32_t *fidx = nullptr;
+    uint32_t *fcnt = nullptr;
+    if (osd_order >= 0) {
+        CK(llr_buf->reserve((size_t)b * c->n * tsize));
+        CK(fail_buf->reserve(sizeof(int32_t) * (size_t)b + 16));
+        llr = llr_buf->p;
+        fcnt = fail_buf->as<uint32_t>();
+        fidx = fail_buf->as<int32_t>() + 4;
+    }
+    int rc = bp_decode_impl(c, cfg, prior_host, b, synd, corr, conv, iters, llr, QLDPC_LLR_FAILED, fidx, fcnt, iter_total,
+                            ctrl, gstate, st);
+    if (rc) return rc;
+    if (osd_order >= 0) {
+        OSDParams P;
+        memset(&P, 0, sizeof(P));
+        P.idx = fidx; P.count_dev = fcnt; P.count_host = 0;
+        P.synd = synd;
+        P.llr = llr;
+        P.hard = corr;
+        P.out = corr;
+        // OSD-w == OSD-0 whenever the OSD-0 solution satisfies the syndrome (OSD_enhanced.py:58-60),
+        // which is always the case for syndromes of the form e * H^T.
+        rc = osd_launch(c, P, tsize == 8, -1, st);
+        if (rc) return rc;
+    }
+    return QLDPC_OK;
+}
+
 extern "C" int qldpc_bposd_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
                                       const uint32_t *synd, int32_t osd_order, uint32_t *corr, uint8_t *conv,
                                       int32_t *iters, uint64_t *iter_total, void *stream)
@@ -562,35 +622,11 @@ extern "C" int qldpc_bposd_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg,
     if (!c || !synd || !corr || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_dev: null argument");
     if (int rc = check_cfg(cfg)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    const int tsize = cfg->precision == 64 ? 8 : 4;
     for (long long o = 0; o < B; o += CHUNK) {
         const long long b = std::min<long long>(CHUNK, B - o);
-        void *llr = nullptr;
-        int32_t *fidx = nullptr;
-        uint32_t *fcnt = nullptr;
-        if (osd_order >= 0) {
-            CK(c->ws_llr.reserve((size_t)b * c->n * tsize));
-            CK(c->ws_fail.reserve(sizeof(int32_t) * (size_t)b + 16));
-            llr = c->ws_llr.p;
-            fcnt = c->ws_fail.as<uint32_t>();
-            fidx = c->ws_fail.as<int32_t>() + 4;
-        }
-        int rc = qldpc_bp_decode_dev(c, cfg, prior_host, b, synd + (size_t)o * c->WM, corr + (size_t)o * c->WN, conv + o,
-                                     iters ? iters + o : nullptr, llr, QLDPC_LLR_FAILED, fidx, fcnt, iter_total, st);
-        if (rc) return rc;
-        if (osd_order >= 0) {
-            OSDParams P;
-            memset(&P, 0, sizeof(P));
-            P.idx = fidx; P.count_dev = fcnt; P.count_host = 0;
-            P.synd = synd + (size_t)o * c->WM;
-            P.llr = llr;
-            P.hard = corr + (size_t)o * c->WN;
-            P.out = corr + (size_t)o * c->WN;
-            // OSD-w == OSD-0 whenever the OSD-0 solution satisfies the syndrome (OSD_enhanced.py:58-60),
-            // which is always the case for syndromes of the form e * H^T.
-            rc = osd_launch(c, P, tsize == 8, -1, st);
-            if (rc) return rc;
-        }
+        if (int rc = bposd_chunk(c, cfg, prior_host, b, synd + (size_t)o * c->WM, osd_order, corr + (size_t)o * c->WN, conv + o,
+                                 iters ? iters + o : nullptr, iter_total, &c->ctrl, &c->gstate, &c->ws_llr, &c->ws_fail, st))
+            return rc;
     }
     return QLDPC_OK;
 }
@@ -709,27 +745,39 @@ extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg
 {
     if (!c || !synd || !corr || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_host: null argument");
     if (int rc = check_cfg(cfg)) return rc;
-    cudaStream_t st = 0;
-    const long long chunk = CHUNK;
-    for (long long o = 0; o < B; o += chunk) {
+    if (B <= 0) return QLDPC_OK;
+    // Chunks rotate over NSLOT streams: copy-in / pack / BP / OSD / unpack / copy-out of chunk i overlap with the
+    // copies of chunks i-1 and i+1 (true overlap needs pinned host buffers; pageable ones still work).
+    long long chunk = 1ll << 20;
+    if (const char *e = getenv("QLDPC_HOST_CHUNK")) chunk = std::max<long long>(1024, atoll(e));
+    chunk = std::min<long long>(chunk, CHUNK);
+    if (int rc = set_prior(c, prior, 0)) return rc;
+    int rc_all = QLDPC_OK;
+    long long i = 0;
+    for (long long o = 0; o < B && rc_all == QLDPC_OK; o += chunk, ++i) {
         const long long b = std::min<long long>(chunk, B - o);
-        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
-        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
-        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
-        CK(c->ws_conv.reserve((size_t)b));
-        CK(c->ws_iters.reserve(4 * (size_t)b));
-        CK(cudaMemcpyAsync(c->ws_u8a.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
-        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_synd.as<uint32_t>(), b, c->m, st)) return rc;
-        if (int rc = qldpc_bposd_decode_dev(c, cfg, prior, b, c->ws_synd.as<uint32_t>(), osd_order, c->ws_hard.as<uint32_t>(),
-                                            c->ws_conv.as<uint8_t>(), c->ws_iters.as<int32_t>(), nullptr, st))
+        qldpc_code::Slot &sl = c->slot[i % qldpc_code::NSLOT];
+        if (!sl.st) CK(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
+        cudaStream_t st = sl.st;
+        CK(sl.u8in.reserve((size_t)b * c->m));
+        CK(sl.u8out.reserve((size_t)b * c->n));
+        CK(sl.synd.reserve(4 * (size_t)b * c->WM));
+        CK(sl.hard.reserve(4 * (size_t)b * c->WN));
+        CK(sl.conv.reserve((size_t)b));
+        CK(sl.iters.reserve(4 * (size_t)b));
+        CK(cudaMemcpyAsync(sl.u8in.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, st)) return rc;
+        if (int rc = bposd_chunk(c, cfg, prior, b, sl.synd.as<uint32_t>(), osd_order, sl.hard.as<uint32_t>(), sl.conv.as<uint8_t>(),
+                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, st))
             return rc;
-        if (int rc = qldpc_unpack_bits_dev(c->ws_hard.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->n, st)) return rc;
-        CK(cudaMemcpyAsync(corr + (size_t)o * c->n, c->ws_u8a.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(conv + o, c->ws_conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
-        if (iters) CK(cudaMemcpyAsync(iters + o, c->ws_iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, st)) return rc;
+        CK(cudaMemcpyAsync(corr + (size_t)o * c->n, sl.u8out.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
+        if (iters) CK(cudaMemcpyAsync(iters + o, sl.iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
     }
-    return QLDPC_OK;
+    for (auto &sl : c->slot)
+        if (sl.st) CK(cudaStreamSynchronize(sl.st));
+    return rc_all;
 }
 
 extern "C" int qldpc_check_host(qldpc_code *c, int64_t B, const uint8_t *err, const uint8_t *corr, const uint8_t *synd,

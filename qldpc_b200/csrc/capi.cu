@@ -67,6 +67,7 @@ struct Ctrl {                       // device control block, zeroed before every
 struct qldpc_code {
     int m = 0, n = 0, E = 0, k = 0, WM = 0, WN = 0;
     int uniform_row_w = 0, max_col_w = 0, two_tables = 0;
+    int rank = 0;                                       // GF(2) rank of H
     int num_sms = 0, smem_optin = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_var_ptr = nullptr;
     uint32_t *d_vtab0 = nullptr, *d_vtab1 = nullptr, *d_colmask = nullptr, *d_Lrows = nullptr, *d_Hrows = nullptr;
@@ -177,6 +178,21 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
             if (L[(size_t)r * n + j] & 1) Lrows[(size_t)r * c->WN + (j >> 5)] |= 1u << (j & 31);
     for (int r = 0; r < m; ++r)
         for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) Hrows[(size_t)r * c->WN + (col_idx[e] >> 5)] |= 1u << (col_idx[e] & 31);
+    {   // GF(2) rank of H (bounds the pivot search of OSD)
+        std::vector<uint32_t> A(Hrows);
+        int r = 0;
+        for (int col = 0; col < n && r < m; ++col) {
+            int piv = -1;
+            for (int i = r; i < m; ++i) if ((A[(size_t)i * c->WN + (col >> 5)] >> (col & 31)) & 1u) { piv = i; break; }
+            if (piv < 0) continue;
+            for (int w = 0; w < c->WN; ++w) std::swap(A[(size_t)r * c->WN + w], A[(size_t)piv * c->WN + w]);
+            for (int i = 0; i < m; ++i)
+                if (i != r && ((A[(size_t)i * c->WN + (col >> 5)] >> (col & 31)) & 1u))
+                    for (int w = 0; w < c->WN; ++w) A[(size_t)i * c->WN + w] ^= A[(size_t)r * c->WN + w];
+            ++r;
+        }
+        c->rank = r;
+    }
     std::vector<int32_t> rp(row_ptr, row_ptr + m + 1), ci(col_idx, col_idx + E), vp(var_ptr, var_ptr + n + 1);
     CK(upload(&c->d_row_ptr, rp));
     CK(upload(&c->d_col_idx, ci));
@@ -440,7 +456,7 @@ template <typename K, int WM>
 static cudaError_t launch_osd_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
 {
     auto kern = osd0_kernel<K, WM>;
-    const size_t smem = osd_smem_per_warp<K>(P.n) * OSD_WARPS;
+    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -469,6 +485,7 @@ static cudaError_t launch_osd_k(const qldpc_code *c, const OSDParams &P, long lo
 static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st)
 {
     P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
+    P.rank = c->rank;
     P.colmask = c->d_colmask;
     if (c->WM > 5 || c->n > 65535)
         return fail(QLDPC_ERR_UNSUPPORTED, "OSD: check matrices with more than 160 rows need the block-per-shot kernel (not built yet)");

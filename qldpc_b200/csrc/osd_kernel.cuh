@@ -33,6 +33,7 @@ namespace qldpc {
 
 struct OSDParams {
     int m, n, WM, WN;
+    int rank;                     // GF(2) rank of H: no pivot can be found once `rank` rows are pivoted
     const uint32_t *colmask;      // [n][WM]
     const int32_t *idx;           // [count] shot ids to process (null: identity)
     const unsigned int *count_dev;// number of entries in idx (device) ...
@@ -61,7 +62,8 @@ template <> struct KeyBits<double> {
 
 constexpr int OSD_WARPS = 4;
 
-// dynamic shared memory per warp: n keys + n ordering entries
+// dynamic shared memory: one copy of colmask per CTA, then per warp: n keys + n ordering entries + solution words
+__host__ __device__ inline size_t osd_smem_colmask(int n, int WM) { return (4 * (size_t)n * WM + 15) & ~(size_t)15; }
 template <typename K>
 __host__ __device__ inline size_t osd_smem_per_warp(int n)
 {
@@ -80,7 +82,10 @@ osd0_kernel(const OSDParams P)
     const int m = P.m, n = P.n, WN = P.WN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     extern __shared__ __align__(16) unsigned char smem[];
-    unsigned char *base = smem + osd_smem_per_warp<K>(n) * warp;
+    uint32_t *cmask = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < n * WM; i += blockDim.x) cmask[i] = P.colmask[i];
+    __syncthreads();
+    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * warp;
     kbits *keys = reinterpret_cast<kbits *>(base);
     uint16_t *ord = reinterpret_cast<uint16_t *>(base + sizeof(kbits) * (size_t)n);
     uint32_t *solw = reinterpret_cast<uint32_t *>(base + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
@@ -97,22 +102,26 @@ osd0_kernel(const OSDParams P)
         // ---- ordering = argsort(|llr|), stable (OSD.py:10-11) ------------------------------
         for (int j = lane; j < n; j += 32) keys[j] = KeyBits<K>::get(llr[j]);
         __syncwarp();
-        for (int i0 = 0; i0 < n; i0 += 32 * 4) {
-            kbits ki[4];
-            int ii[4], cnt[4];
+        // rank of key i = #{j : key_j < key_i, or key_j == key_i and j < i}; each lane ranks up to KPL of its keys
+        // per pass over all n keys (one pass for n <= 32 * KPL)
+        constexpr int KPL = (WM <= 3) ? 5 : 9;                  // covers n <= 160 / 288 in a single pass
+        for (int i0 = 0; i0 < n; i0 += 32 * KPL) {
+            kbits ki[KPL];
+            int ii[KPL], cnt[KPL];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
+            for (int t = 0; t < KPL; ++t) {
                 ii[t] = i0 + 32 * t + lane;
                 ki[t] = (ii[t] < n) ? keys[ii[t]] : (kbits)0;
                 cnt[t] = 0;
             }
+#pragma unroll 2
             for (int j = 0; j < n; ++j) {
                 const kbits kj = keys[j];
 #pragma unroll
-                for (int t = 0; t < 4; ++t) cnt[t] += (kj < ki[t]) || (kj == ki[t] && j < ii[t]);
+                for (int t = 0; t < KPL; ++t) cnt[t] += (kj < ki[t] + (kbits)(j < ii[t]));   // kj <= ki for j < i (keys < 2^(bits-1))
             }
 #pragma unroll
-            for (int t = 0; t < 4; ++t) if (ii[t] < n) ord[cnt[t]] = (uint16_t)ii[t];
+            for (int t = 0; t < KPL; ++t) if (ii[t] < n) ord[cnt[t]] = (uint16_t)ii[t];
         }
         __syncwarp();
 
@@ -123,7 +132,7 @@ osd0_kernel(const OSDParams P)
         for (int v = lane; v < n; v += 32) {
             if ((hard[v >> 5] >> (v & 31)) & 1u) {
 #pragma unroll
-                for (int w = 0; w < WM; ++w) rs[w] ^= P.colmask[v * WM + w];
+                for (int w = 0; w < WM; ++w) rs[w] ^= cmask[v * WM + w];
             }
         }
 #pragma unroll
@@ -145,11 +154,12 @@ osd0_kernel(const OSDParams P)
 
         // ---- gf2_elimination (OSD.py:31-72) -------------------------------------------------
         int row = 0;
-        for (int j = 0; j < n && row < m; ++j) {
+        const int rank = P.rank;
+        for (int j = 0; j < n && row < rank; ++j) {     // `row >= m` (:43); past `rank` pivots no column can pivot
             const int col = ord[j];
             uint32_t cm[WM];
 #pragma unroll
-            for (int w = 0; w < WM; ++w) cm[w] = P.colmask[col * WM + w];
+            for (int w = 0; w < WM; ++w) cm[w] = cmask[col * WM + w];
             uint32_t has[WM];
             int best = 0x7fffffff;
 #pragma unroll

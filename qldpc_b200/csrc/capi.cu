@@ -482,13 +482,47 @@ static cudaError_t launch_osd_k(const qldpc_code *c, const OSDParams &P, long lo
     }
 }
 
+template <typename K>
+static cudaError_t launch_osd_block(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
+{
+    auto kern = osd0_block_kernel<K>;
+    const size_t smem = osdb_smem_bytes<K>(P.m, P.n);
+    if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSDB_THREADS, smem);
+    long long grid = (long long)c->num_sms * std::max(1, occ);
+    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, count_hint));
+    kern<<<(int)grid, OSDB_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+static bool osd_use_block(const qldpc_code *c)
+{
+    static const bool force = getenv("QLDPC_OSD_FORCE_BLOCK") != nullptr;    // test hook
+    return force || c->WM > 5 || c->n > 65535;
+}
+
 static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st)
 {
     P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
     P.rank = c->rank;
     P.colmask = c->d_colmask;
-    if (c->WM > 5 || c->n > 65535)
-        return fail(QLDPC_ERR_UNSUPPORTED, "OSD: check matrices with more than 160 rows need the block-per-shot kernel (not built yet)");
+    if (osd_use_block(c)) {
+        if (c->n > 65535) return fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65535 columns");
+        if (P.rec_ordering) return fail(QLDPC_ERR_UNSUPPORTED, "OSD-w sweep (order > 0) is not available for check matrices with more than 160 rows");
+        OSDBlockParams Q;
+        Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank;
+        Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1;
+        Q.idx = P.idx; Q.count_dev = P.count_dev; Q.count_host = P.count_host;
+        Q.synd = P.synd; Q.llr = P.llr; Q.hard = P.hard; Q.out = P.out; Q.valid = P.valid;
+        cudaError_t e = llr_f64 ? launch_osd_block<double>(c, Q, count_hint, st) : launch_osd_block<float>(c, Q, count_hint, st);
+        if (e != cudaSuccess)
+            return fail(e == cudaErrorInvalidValue ? QLDPC_ERR_UNSUPPORTED : QLDPC_ERR_CUDA,
+                        std::string("osd0_block_kernel launch (check matrix too large for shared memory?): ") + cudaGetErrorString(e));
+        return QLDPC_OK;
+    }
     cudaError_t e = llr_f64 ? launch_osd_k<double>(c, P, count_hint, st) : launch_osd_k<float>(c, P, count_hint, st);
     if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osd0_kernel launch: ") + cudaGetErrorString(e));
     return QLDPC_OK;
@@ -724,7 +758,7 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
         P.hard = c->ws_hard.as<uint32_t>();
         P.out = c->ws_err.as<uint32_t>();
         P.valid = c->ws_valid.as<uint8_t>();
-        const bool want_rec = order > 0;
+        const bool want_rec = order > 0 && !osd_use_block(c);
         if (want_rec) {
             const size_t rec = (size_t)b * (4 * (size_t)c->n + 4 * (size_t)c->m + c->m + 4) + 64;
             CK(c->ws_rec.reserve(rec));
@@ -735,7 +769,7 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
             P.rec_sred = reinterpret_cast<uint8_t *>(r);
         }
         if (int rc = osd_launch(c, P, 1, b, st)) return rc;
-        if (order > 0) {
+        if (want_rec) {
             // OSD-w sweep on the shots whose OSD-0 solution misses the syndrome (OSD_enhanced.py:66-131)
             OSDWParams W;
             memset(&W, 0, sizeof(W));

@@ -246,4 +246,161 @@ osd0_kernel(const OSDParams P)
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// OSD-0 for large check matrices (space-time / detector-error-model H: m > 160), one CTA per shot.
+//
+// Same algorithm and the same transform-matrix formulation as osd0_kernel, but T (m x m bits), the
+// syndrome column, the row positions and the sort keys live in shared memory and the columns of H
+// are read in sparse form (their <= few check indices) instead of packed words: entry (r, j) of the
+// reduced matrix is the XOR of the bits T[r][c] over the checks c of column ordering[j].
+// Row r is owned by thread r % blockDim.x.  Per column: every thread evaluates its rows, the pivot
+// (smallest position >= current row among rows with the bit set) is found with a warp REDUX.MIN and a
+// shared atomicMin, the pivot row is XORed into the other rows that have the bit.
+// ------------------------------------------------------------------------------------------------
+struct OSDBlockParams {
+    int m, n, WM, WN, rank;
+    const int32_t *var_ptr;       // [n+1]  CSC of H
+    const uint32_t *vtab;         // [2E]   (edge, check) pairs per variable (any order)
+    const int32_t *idx;
+    const unsigned int *count_dev;
+    long long count_host;
+    const uint32_t *synd;         // [B][WM]
+    const void *llr;              // [B][n]
+    const uint32_t *hard;         // [B][WN]
+    uint32_t *out;                // [B][WN]
+    uint8_t *valid;               // [B]
+};
+
+constexpr int OSDB_THREADS = 256;
+
+template <typename K>
+__host__ __device__ inline size_t osdb_smem_bytes(int m, int n)
+{
+    const int WM = (m + 31) / 32, WN = (n + 31) / 32;
+    size_t o = 4 * (size_t)m * WM;                              // T
+    o += 4 * (size_t)m * 2;                                     // pos, pcol
+    o += 4 * (size_t)WM * 2;                                    // residual syndrome words, b words
+    o += 4 * (size_t)WN;                                        // solution words
+    o = (o + 7) & ~(size_t)7;
+    o += sizeof(typename KeyBits<K>::type) * (size_t)n;         // keys
+    o += 2 * (size_t)n;                                         // ordering (uint16)
+    return o + 64;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlockParams P)
+{
+    typedef typename KeyBits<K>::type kbits;
+    const int m = P.m, n = P.n, WM = P.WM, WN = P.WN;
+    const int tid = threadIdx.x, NT = OSDB_THREADS, lane = tid & 31;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *T = reinterpret_cast<uint32_t *>(smem);                       // [m][WM]
+    int *pos = reinterpret_cast<int *>(T + (size_t)m * WM);                // [m]
+    int *pcol = pos + m;                                                    // [m]
+    uint32_t *bw = reinterpret_cast<uint32_t *>(pcol + m);                 // [WM] syndrome column, bit r = b[r]
+    uint32_t *rsw = bw + WM;                                                // [WM] scratch
+    uint32_t *solw = rsw + WM;                                              // [WN]
+    kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
+    uint16_t *ord = reinterpret_cast<uint16_t *>(keys + n);
+    __shared__ int s_pmin[2], s_prow;
+
+    const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
+    for (long long it = blockIdx.x; it < count; it += gridDim.x) {
+        const long long shot = P.idx ? (long long)P.idx[it] : it;
+        const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
+        const uint32_t *hard = P.hard + (size_t)shot * WN;
+        __syncthreads();
+        // ---- stable ascending order of |llr| by rank counting ---------------------------------
+        for (int j = tid; j < n; j += NT) keys[j] = KeyBits<K>::get(llr[j]);
+        for (int w = tid; w < WM; w += NT) rsw[w] = P.synd[(size_t)shot * WM + w];
+        for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const kbits ki = keys[i];
+            int cnt = 0;
+#pragma unroll 4
+            for (int j = 0; j < n; ++j) cnt += (keys[j] < ki + (kbits)(j < i));
+            ord[cnt] = (uint16_t)i;
+        }
+        // ---- residual syndrome s ^ H*hard; T = I; positions ----------------------------------
+        for (int v = tid; v < n; v += NT)
+            if ((hard[v >> 5] >> (v & 31)) & 1u)
+                for (int a = P.var_ptr[v]; a < P.var_ptr[v + 1]; ++a) {
+                    const int c = (int)P.vtab[2 * a + 1];
+                    atomicXor(&rsw[c >> 5], 1u << (c & 31));
+                }
+        for (int t = tid; t < m * WM; t += NT) {
+            const int r = t / WM, w = t - r * WM;
+            T[t] = (w == (r >> 5)) ? (1u << (r & 31)) : 0u;
+        }
+        for (int r = tid; r < m; r += NT) { pos[r] = r; pcol[r] = -1; }
+        __syncthreads();
+        for (int w = tid; w < WM; w += NT) bw[w] = rsw[w];
+        __syncthreads();
+
+        // ---- gf2_elimination (OSD.py:31-72) -----------------------------------------------------
+        int row = 0;
+        const int rank = P.rank;
+        for (int j = 0; j < n && row < rank; ++j) {
+            const int col = ord[j];
+            const int a0 = P.var_ptr[col], a1 = P.var_ptr[col + 1];
+            if (tid == 0) s_pmin[j & 1] = 0x7fffffff;     // double-buffered: readers of column j-1 may still be behind
+            __syncthreads();
+            int best = 0x7fffffff;
+            unsigned hasmask = 0;                                   // bit s: my s-th row has the bit
+            int sidx = 0;
+            for (int r = tid; r < m; r += NT, ++sidx) {
+                uint32_t x = 0;
+                for (int a = a0; a < a1; ++a) {
+                    const int c = (int)P.vtab[2 * a + 1];
+                    x ^= T[(size_t)r * WM + (c >> 5)] >> (c & 31);
+                }
+                if (x & 1u) {
+                    hasmask |= 1u << sidx;
+                    const int p = pos[r];
+                    if (p >= row && p < best) best = p;
+                }
+            }
+            best = __reduce_min_sync(0xffffffffu, best);
+            if (lane == 0 && best != 0x7fffffff) atomicMin(&s_pmin[j & 1], best);
+            __syncthreads();
+            const int pmin = s_pmin[j & 1];
+            if (pmin == 0x7fffffff) continue;                       // uniform: no pivot in this column
+            // locate the pivot row (position pmin) and the row currently at position `row`
+            for (int r = tid; r < m; r += NT) if (pos[r] == pmin) s_prow = r;
+            __syncthreads();
+            const int prow = s_prow;
+            const uint32_t pb = (bw[prow >> 5] >> (prow & 31)) & 1u;
+            sidx = 0;
+            for (int r = tid; r < m; r += NT, ++sidx) {
+                if (r == prow) continue;
+                if (pos[r] == row) pos[r] = pmin;                   // swap positions (OSD.py:56-58)
+                if ((hasmask >> sidx) & 1u) {                       // eliminate (OSD.py:64-68)
+                    for (int w = 0; w < WM; ++w) T[(size_t)r * WM + w] ^= T[(size_t)prow * WM + w];
+                    if (pb) atomicXor(&bw[r >> 5], 1u << (r & 31));
+                }
+            }
+            __syncthreads();
+            if (tid == 0) { pos[prow] = row; pcol[prow] = j; }
+            ++row;
+        }
+        __syncthreads();
+
+        // ---- solution and validity -----------------------------------------------------------------
+        int bad = 0;
+        for (int r = tid; r < m; r += NT) {
+            const uint32_t b = (bw[r >> 5] >> (r & 31)) & 1u;
+            if (pcol[r] >= 0) {
+                if (b) { const int v = ord[pcol[r]]; atomicXor(&solw[v >> 5], 1u << (v & 31)); }
+            } else if (b) {
+                bad = 1;
+            }
+        }
+        bad = __syncthreads_or(bad);
+        for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
+        if (tid == 0 && P.valid) P.valid[shot] = bad ? 0 : 1;
+    }
+}
+
 }  // namespace qldpc

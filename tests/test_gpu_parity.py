@@ -230,6 +230,9 @@ def test_spacetime_bp_staged(spacetime_golden):
     assert code.geometry(code.config("min_sum", 50, 0.8, 0.7, 25.0, 64))["staged"]
     assert np.array_equal(hard, d["ms_hard"]) and np.array_equal(conv, d["ms_conv"])
     assert np.array_equal(iters, d["ms_iter"]) and np.array_equal(llr, d["ms_llr"])
+    f = np.nonzero(~conv)[0]
+    sol = code.osd_decode_batch(d["synd"][f], llr[f], hard[f])
+    assert np.array_equal(sol, d["ms_osd0"][f])
 
 
 def test_edge_cases():
@@ -296,6 +299,66 @@ def test_osd_after_bp_with_ties(bp_golden):
             f = np.nonzero(~d[f"{key}_ms{pi}_conv"])[0]
             got = code.osd_decode_batch(synd[f], d[f"{key}_ms{pi}_llr"][f], d[f"{key}_ms{pi}_hard"][f])
             assert np.array_equal(got, d[f"{key}_ms{pi}_osd0"][f])
+
+
+def test_osd_block_kernel_forced_on_small_codes():
+    """The block-per-shot OSD kernel (large check matrices) must agree bit for bit with the golden vectors too:
+    force it on the small codes in a fresh process (QLDPC_OSD_FORCE_BLOCK is read once per process)."""
+    import os, subprocess, sys
+    env = dict(os.environ, QLDPC_OSD_FORCE_BLOCK="1")
+    code = r"""
+import json, os, sys
+import numpy as np
+sys.path.insert(0, os.getcwd()); sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+from conftest import load_code_file, GOLDEN
+from qldpc_b200 import Code
+d = np.load(os.path.join(GOLDEN, "osd_golden.npz")); meta = json.loads(str(d["meta"]))
+for case in meta["cases"]:
+    key = case["key"]; H, _ = load_code_file(case["code"]); code = Code(H)
+    assert np.array_equal(code.osd_decode_batch(d[key + "_synd_c"], d[key + "_llr"], d[key + "_hard"]), d[key + "_osd0_c"]), case
+    assert np.array_equal(code.osd_decode_batch(d[key + "_synd_i"], d[key + "_llr"], d[key + "_hard"]), d[key + "_osd0_i"]), case
+b = np.load(os.path.join(GOLDEN, "bp_golden.npz")); bm = json.loads(str(b["meta"]))
+for case in bm["cases"]:
+    key = case["key"]; H, _ = load_code_file(case["code"], case["layout"]); code = Code(H)
+    synd = ((b[key + "_errors"].astype(np.int64) @ np.asarray(H).T) % 2).astype(np.uint8)
+    f = np.nonzero(~b[key + "_ms0_conv"])[0]
+    assert np.array_equal(code.osd_decode_batch(synd[f], b[key + "_ms0_llr"][f], b[key + "_ms0_hard"][f]), b[key + "_ms0_osd0"][f]), case
+print("BLOCK-OSD-OK")
+"""
+    from conftest import ROOT
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert "BLOCK-OSD-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def test_spacetime_144x12_bp_osd_vs_oracle():
+    """BASELINE config 4 at full size: H_st = spaceTimeMatrix(Hx_144, 12) (864 x 2592, 6840 edges), syndromes from
+    spacetimeSyndrome, min-sum BP (HBM-staged float64 kernel) + OSD-0 (block-per-shot kernel): bit-exact vs the oracle."""
+    from qldpc_b200.spaceTime import spaceTimeMatrix, spacetimeSyndrome
+    H, _ = load_code_file("[[144, 12, 12]]")
+    Hst = spaceTimeMatrix(H, 12)
+    assert Hst.shape == (864, 2592)
+    p = 0.001      # the sampler's first-block quirk (spaceTime.py:35) makes about half of these fail BP
+    np.random.seed(12)
+    synd = np.array([spacetimeSyndrome(H, p, 12)[1] for _ in range(48)], np.uint8)
+    prior = _prior(p, Hst.shape[1])
+    g = O.Graph(Hst, *O.auto_schedule(Hst, O.MIN_SUM))
+    ref = O.decode_batch(g, synd, prior, O.MIN_SUM, 50, 0.8, 0.7, 25.0, osd_order=0, want_llr=True)
+    code = _code(Hst, "min_sum")
+    cfg = code.config("min_sum", 50, 0.8, 0.7, 25.0, 64)
+    assert code.geometry(cfg)["kernel"] == "hbm_staged"
+    hard, conv, llr, iters = code.bp_decode_batch(synd, prior, "min_sum", 50, 0.8, 0.7, 25.0, precision=64)
+    assert np.array_equal(conv, ref["converged"]) and np.array_equal(iters, ref["iters"]) and np.array_equal(llr, ref["llr"])
+    assert (~conv).sum() >= 3, "want some BP failures to exercise OSD"
+    corr, conv2, _ = code.bposd_decode_batch(synd, prior, "min_sum", 50, 0.8, 0.7, 25.0, precision=64, osd_order=0)
+    assert np.array_equal(corr, ref["corr"])
+    assert np.array_equal(_synd(Hst, corr), synd)          # H_st has full rank: every OSD solution satisfies its syndrome
+    # standalone OSD call with float64 LLRs
+    f = np.nonzero(~conv)[0]
+    sol = code.osd_decode_batch(synd[f], llr[f], hard[f])
+    assert np.array_equal(sol, ref["corr"][f])
+    # float32 staged kernel: valid corrections
+    corr32, _, _ = code.bposd_decode_batch(synd, prior, "min_sum", 50, 0.8, 0.7, 25.0, precision=32, osd_order=0)
+    assert np.array_equal(_synd(Hst, corr32), synd)
 
 
 def test_osd_w_full_order7_vs_oracle():

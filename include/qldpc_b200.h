@@ -106,6 +106,12 @@ int qldpc_bp_geometry(qldpc_code *code, const qldpc_bp_config *cfg, int32_t *sho
 int qldpc_bp_decode_host(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, int64_t B,
                          const uint8_t *synd, int8_t *hard, uint8_t *conv, int32_t *iters, double *llr);
 
+/* The alpha_estimation=True return of performMinSum_Symmetric (rework/decoding.py:58-59: R_new / alpha after the
+ * first check pass, dump_iter = 0) and of performBeliefPropagation_Symmetric (:168-169: R at currentIter == 10):
+ * check-to-variable messages of iteration dump_iter, r_edges [B][E] float64 in CSR edge order.  float64 only. */
+int qldpc_bp_messages_host(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                           const uint8_t *synd, int32_t dump_iter, double *r_edges);
+
 /* Batched OSD.  Stands in for performOSD (decoding/OSD.py:3) when order == 0 and
  * performOSD_enhanced (decoding/OSD_enhanced.py:5) otherwise; max_combinations <= 0 means None.
  *   synd [B][m] uint8, llr [B][n] float64, hard [B][n] uint8/int8 -> out [B][n] uint8.

@@ -123,6 +123,23 @@ class Code:
                                                       _vp(iters), _vp(llr)), "qldpc_bp_decode_host")
         return hard, conv.astype(bool), llr, iters
 
+    def bp_messages_batch(self, syndromes, prior, variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0,
+                          dump_iter=0):
+        """Check-to-variable messages of iteration `dump_iter` as dense (B, m, n) float64 arrays: the
+        alpha_estimation=True return of the reference (rework/decoding.py:58-59, :168-169)."""
+        synd = _bits(syndromes)
+        B = synd.shape[0]
+        cfg = self.config(variant, max_iter, alpha, damping, clip, 64)
+        p = self._prior(prior)
+        r = np.zeros((B, self.E), np.float64)
+        if B:
+            _lib.check(_lib.lib().qldpc_bp_messages_host(self._h, ctypes.byref(cfg), _vp(p), B, _vp(synd), int(dump_iter), _vp(r)),
+                       "qldpc_bp_messages_host")
+        rows = np.repeat(np.arange(self.m), np.diff(self._g["row_ptr"]))
+        out = np.zeros((B, self.m, self.n), np.float64)
+        out[:, rows, self._g["col_idx"]] = r
+        return out
+
     def osd_decode_batch(self, syndromes, llr, hard, order=0, max_combinations=None):
         """-> int64 (B,n): performOSD (order 0) / performOSD_enhanced (order > 0) per shot."""
         synd = _bits(syndromes)

@@ -70,6 +70,8 @@ struct BPParams {
     unsigned int *fail_count;
     unsigned long long *iter_total; // sum over shots of executed iterations (may be null)
     void *gstate;               // STATE_SMEM = false: [(E + 2m) T + WN + WM words][total threads]
+    void *r_dump;               // [B][E] T or null: check-to-variable messages of iteration `dump_iter` (CSR edge order),
+    int dump_iter;              //   the alpha_estimation=True return of the reference (decoding.py:58-59,168-169)
 };
 
 template <typename T> struct Num;
@@ -318,6 +320,8 @@ bp_decode_kernel(const BPParams P)
         const bool last = (iter == max_iter - 1);
         const bool wr_llr = (P.llr != nullptr) && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && last));
         T *llr_out = wr_llr ? reinterpret_cast<T *>(P.llr) + (size_t)shot * n : nullptr;
+        const bool dumping = (P.r_dump != nullptr) && (iter == P.dump_iter);
+        T *rdump = dumping ? reinterpret_cast<T *>(P.r_dump) + (size_t)shot * E : nullptr;
         if (WMS > 0) {
 #pragma unroll
             for (int k = 0; k < WREG; ++k) acc[k] = 0;
@@ -347,12 +351,14 @@ bp_decode_kernel(const BPParams P)
                                 const T mag = (fabs(q) == a1) ? s2 : a1;             // decoding.py:51-53
                                 // R = alpha * syndrome_sign * r_signs * mag           (decoding.py:55)
                                 rr = N::from_bits(N::bits(N::mul(alpha, mag)) ^ ((N::bits(s1) ^ N::bits(q)) & N::SIGN));
+                                if (dumping) rdump[ec.x] = N::div(rr, alpha);        // R_new / alpha (decoding.py:59)
                             } else {
                                 T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
                                 const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;     // beliefPropagation.py:122
                                 T x = N::div(s1, ts);
                                 x = fmin(fmax(x, -CLIP_VAL), CLIP_VAL);              // :125
                                 rr = N::mul((T)2, N::atanh_(x));                     // :126
+                                if (dumping) rdump[ec.x] = rr;                       // R before scaling (decoding.py:169)
                                 if (P.sym) rr = N::mul(rr, alpha);                   // decoding.py:171
                             }
                             sum = (k0 + k == 0) ? rr : N::add(sum, rr);
@@ -397,12 +403,14 @@ bp_decode_kernel(const BPParams P)
                             const T a1 = fabs(s1);
                             const T mag = (fabs(q) == a1) ? s2 : a1;
                             rr = N::from_bits(N::bits(N::mul(alpha, mag)) ^ ((N::bits(s1) ^ N::bits(q)) & N::SIGN));
+                            if (dumping) rdump[ec.x] = N::div(rr, alpha);
                         } else {
                             T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
                             const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;
                             T x = N::div(s1, ts);
                             x = fmin(fmax(x, -CLIP_VAL), CLIP_VAL);
                             rr = N::mul((T)2, N::atanh_(x));
+                            if (dumping) rdump[ec.x] = rr;
                             if (P.sym) rr = N::mul(rr, alpha);
                         }
                         T qn = N::sub(val, rr);
@@ -443,7 +451,8 @@ bp_decode_kernel(const BPParams P)
             }
         }
 
-        if (conv || last) {
+        if (P.r_dump) conv = false;          // `and not alpha_estimation`: no early exit while dumping (decoding.py:72,188)
+        if (conv || last || dumping) {
             // ---- retire the shot -----------------------------------------------------------
             uint32_t *ho = P.hard + (size_t)shot * WN;
             for (int w = 0; w < WN; ++w) ho[w] = HW[(idx_t)w * S];

@@ -427,6 +427,8 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.fail_count = fail_count ? fail_count : &ctrl->fail_count;
     P.iter_total = (unsigned long long *)iter_total;
     P.gstate = gstate_buf->p;
+    P.r_dump = nullptr;
+    P.dump_iter = -1;
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
     if (G.tiled_T)
@@ -725,6 +727,59 @@ extern "C" int qldpc_bp_decode_host(qldpc_code *c, const qldpc_bp_config *cfg, c
             }
             CK(cudaMemcpyAsync(llr + (size_t)o * c->n, c->ws_llr.p, (size_t)b * c->n * 8, cudaMemcpyDeviceToHost, st));
         }
+        CK(cudaStreamSynchronize(st));
+    }
+    return QLDPC_OK;
+}
+
+// alpha_estimation=True return paths of the reference: check-to-variable messages per edge
+extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                      const uint8_t *synd, int32_t dump_iter, double *r_edges)
+{
+    if (!c || !synd || !r_edges) return fail(QLDPC_ERR_ARG, "qldpc_bp_messages_host: null argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    if (cfg->precision != 64) return fail(QLDPC_ERR_ARG, "qldpc_bp_messages_host: precision must be 64");
+    if (dump_iter < 0 || dump_iter >= cfg->max_iter) return fail(QLDPC_ERR_ARG, "qldpc_bp_messages_host: dump_iter must be in [0, max_iter)");
+    cudaStream_t st = 0;
+    if (int rc = set_prior(c, prior, st)) return rc;
+    const long long chunk = 1ll << 16;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_conv.reserve((size_t)b));
+        CK(c->ws_rec.reserve(8 * (size_t)b * c->E));
+        CK(cudaMemcpyAsync(c->ws_u8a.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_synd.as<uint32_t>(), b, c->m, st)) return rc;
+        CK(cudaMemsetAsync(c->ws_rec.p, 0, 8 * (size_t)b * c->E, st));
+        // same launch path as qldpc_bp_decode_dev, thread-per-shot kernel, with the dump enabled
+        BPGeom G;
+        qldpc_bp_config cf = *cfg;
+        if (cf.staged == 0) cf.staged = 2;
+        bp_geometry(c, &cf, b, &G);
+        if (G.staged) CK(c->gstate.reserve(G.gstate_bytes));
+        CK(c->ctrl.reserve(sizeof(Ctrl)));
+        Ctrl *ctrl = c->ctrl.as<Ctrl>();
+        CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st));
+        BPParams P;
+        P.g = c->graph();
+        P.B = b;
+        P.synd = c->ws_synd.as<uint32_t>();
+        P.prior = c->prior64.p;
+        P.max_iter = cf.max_iter;
+        P.sym = (cf.variant == QLDPC_SUM_PRODUCT_SYM);
+        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip;
+        P.hard = c->ws_hard.as<uint32_t>(); P.conv = c->ws_conv.as<uint8_t>(); P.iters = nullptr;
+        P.llr = nullptr; P.llr_mode = LLR_NONE;
+        P.cursor = &ctrl->cursor; P.fail_idx = nullptr; P.fail_count = &ctrl->fail_count; P.iter_total = nullptr;
+        P.gstate = c->gstate.p;
+        P.r_dump = c->ws_rec.p;
+        P.dump_iter = dump_iter;
+        cudaError_t e = (kernel_variant(cf.variant) == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st)
+                                                                    : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
+        if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("bp_decode_kernel (messages) launch: ") + cudaGetErrorString(e));
+        CK(cudaMemcpyAsync(r_edges + (size_t)o * c->E, c->ws_rec.p, 8 * (size_t)b * c->E, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
     }
     return QLDPC_OK;

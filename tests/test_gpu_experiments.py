@@ -1,0 +1,89 @@
+"""GPU tests of the rows SURVEY.md section 8f lists as "next": alpha_estimation return paths, the alpha estimator of
+rework/Alvarado.py, and the Monte-Carlo drivers that emit the reference's result dictionaries."""
+import numpy as np
+import pytest
+
+from conftest import load_code_file
+
+pytestmark = pytest.mark.gpu
+
+
+def _synd(H, errors):
+    return ((errors.astype(np.int64) @ (np.asarray(H) != 0).astype(np.int64).T) % 2).astype(np.uint8)
+
+
+def test_alpha_estimation_return_paths(bp_golden):
+    from qldpc_b200.rework import decoding as rw
+    d, meta = bp_golden
+    for case in meta["cases"]:
+        key = case["key"]
+        H, _ = load_code_file(case["code"], case["layout"])
+        synd = _synd(H, d[key + "_errors"])
+        prior = [np.log((1 - case["p"]) / case["p"])] * H.shape[1]
+        out = rw.performMinSum_Symmetric(H, synd[0], prior, maxIter=1, alpha=0.8, damping=0.7, clip_llr=25.0, alpha_estimation=True)
+        assert out[0] == 0 and out[1] == 0 and out[3] == 0 and out[2].shape == H.shape
+        assert np.array_equal(out[2], d[key + "_ms_alphaest"])              # bit-exact
+        al, dm, cl = meta["sym_params"]
+        out = rw.performBeliefPropagation_Symmetric(H, synd[0], prior, maxIter=50, alpha=al, damping=dm, clip_llr=cl, alpha_estimation=True)
+        np.testing.assert_allclose(out[2], d[key + "_sym_alphaest"], rtol=1e-6, atol=1e-9)
+    with pytest.raises(ValueError):
+        rw.performBeliefPropagation_Symmetric(H, synd[0], prior, maxIter=5, alpha_estimation=True)
+
+
+def test_estimate_alpha_matches_reference(reference_stats):
+    from qldpc_b200.rework.Alvarado import estimate_alpha_from_code
+    for rec in reference_stats["alpha_estimates"]:
+        H, _ = load_code_file(rec["code"])
+        np.random.seed(rec["seed"])
+        a = estimate_alpha_from_code(H, trials=rec["trials"], error_rate=rec["p"], maxIter=1, verbose=False)
+        assert abs(a - rec["alpha"]) < 1e-9 * max(1.0, abs(rec["alpha"])), (rec, a)
+
+
+def test_paper_results_dict_and_ler(reference_stats):
+    from qldpc_b200 import experiments as X
+    p7 = reference_stats["degeneracyCount_p"][7]
+    want = reference_stats["BPOSD.npz"]["[[72, 12, 6]]"]["ler"][7]      # sum-product BP50 + OSD-0, single draw
+    N = 30000
+    res = X.paper_results(codes=["[[72, 12, 6]]"], physicalErrorRates=[p7, 0.01], trials=N, variant="sum_product", maxIter=50,
+                          osd_order=0, draws=1, seed=11, precision=64)
+    r = res["[[72, 12, 6]]"]
+    assert set(r) == {"ler", "BPs_fault", "BPs_miscorrected", "incorrectable", "degeneracies"} and all(len(v) == 2 for v in r.values())
+    half = 1.96 * np.sqrt(want * (1 - want) / 10000) + 1.96 * np.sqrt(want * (1 - want) / N)
+    assert abs(r["ler"][0] - want) <= half, (r["ler"][0], want, half)
+    assert r["BPs_miscorrected"][0] + r["incorrectable"][0] == round(r["ler"][0] * N)
+    # BP-only accounting of degeneracyCount.ipynb cell 5
+    bp = X.paper_results(codes=["[[72, 12, 6]]"], physicalErrorRates=[p7], trials=N, variant="sum_product", maxIter=50, draws=1,
+                         seed=11, precision=64, bp_only=True)["[[72, 12, 6]]"]
+    w = reference_stats["BP.npz"]["[[72, 12, 6]]"]
+    assert abs(bp["BPs_fault"][0] / N - w["BPs_fault"][7] / 10000) < 0.015
+    assert abs(bp["ler"][0] - w["ler"][7]) < 0.03
+
+
+def test_rework_main_dict():
+    from qldpc_b200 import experiments as X
+    exp = [{"code": "[[72, 12, 6]]", "name": "72", "physicalErrorRates": [0.05], "distance": 6}]
+    N = 20000
+    res = X.rework_main(exp, trials=N, BP_maxIter=50, OSD_order=7, variant="min_sum", alpha=0.8, damping=0.7, clip=25.0, precision=32)
+    r = res["72"][0.05]
+    assert set(r) == {"logical", "osd", "degeneracies", "average_iterations", "OSD_invocation_AND_logicalError", "weights_found_BP",
+                      "weights_found_OSD", "weights_found_BP_error", "weights_found_OSD_error"}
+    assert len(r["weights_found_BP_error"]) + len(r["weights_found_OSD_error"]) == round(r["logical"] * N)
+    assert len(r["weights_found_OSD_error"]) == round(r["OSD_invocation_AND_logicalError"] * N)
+    assert len(r["weights_found_BP"]) + len(r["weights_found_OSD"]) == round(r["degeneracies"] * N)   # all corrections are valid
+    # reference run of the same decoder family (rework/simulation_results.npz, alpha estimated): LER 0.1525, OSD rate 0.2498
+    assert 0.10 < r["logical"] < 0.20 and 0.0 < r["osd"] < 0.35 and 2 < r["average_iterations"] < 25
+    assert min(r["weights_found_BP_error"]) >= 6              # a logical error has weight >= the distance
+
+
+def test_bp_per_iteration_dict():
+    from qldpc_b200 import experiments as X
+    N = 3000
+    res = X.bp_per_iteration(codes=["[[90, 8, 10]]"], errorRate=0.01, iterations=(10, 50), trials=N, variant="sum_product", precision=64)
+    r = res["[[90, 8, 10]]"]
+    assert set(r) == {"logicalErrors", "degeneracies", "OSD_invocations", "iterations", "llrs_per_iter", "llrs_per_iter_after_OSD"}
+    assert r["iterations"] == [10, 50] and r["llrs_per_iter"][0].size == N * 90
+    assert r["llrs_per_iter_after_OSD"][1].size == round(r["OSD_invocations"][1] * N) * 90
+    assert r["OSD_invocations"][1] <= r["OSD_invocations"][0] + 0.01
+    ms = X.bp_per_iteration(codes=["[[108, 8, 10]]"], errorRate=0.01, iterations=(30,), trials=N, variant="min_sum", alpha=0.8,
+                            damping=0.7, clip=25.0, precision=32)["[[108, 8, 10]]"]
+    assert ms["logicalErrors"][0] < 0.01

@@ -205,6 +205,23 @@ def gen_stats(ref):
     st["simulation_results.npz"] = {
         code: {str(p): {k: float(v) for k, v in r.items() if np.isscalar(v) or np.ndim(v) == 0} for p, r in pr.items()}
         for code, pr in sim.items()}
+    # rework/Alvarado.py:10-66 estimate_alpha_from_code, run unmodified (it imports `decoding` = rework/decoding.py
+    # and matplotlib at module level, so only the function is executed, in a namespace with the names it uses)
+    import ast
+    src = open(os.path.join(ref.root, "rework/Alvarado.py")).read()
+    fn = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == "estimate_alpha_from_code")
+    from scipy.optimize import curve_fit
+    ns = dict(np=np, curve_fit=curve_fit, performMinSum_Symmetric=ref.rework.performMinSum_Symmetric,
+              performBeliefPropagation_Symmetric=ref.rework.performBeliefPropagation_Symmetric)
+    exec(compile(ast.Module([fn], []), "Alvarado.py", "exec"), ns)
+    import contextlib, io
+    st["alpha_estimates"] = []
+    for stem, p, trials, seed in [("[[72, 12, 6]]", 0.05, 600, 1), ("[[144, 12, 12]]", 0.05, 300, 2), ("[[72, 12, 6]]", 0.02, 600, 3)]:
+        H, _ = load_code(stem, "F")
+        np.random.seed(seed)
+        with contextlib.redirect_stdout(io.StringIO()):
+            a = ns["estimate_alpha_from_code"](H, trials=trials, error_rate=p, maxIter=1)
+        st["alpha_estimates"].append(dict(code=stem, p=p, trials=trials, seed=seed, alpha=float(a)))
     with open(os.path.join(OUT, "reference_stats.json"), "w") as f:
         json.dump(st, f, indent=1)
     print("stats golden")

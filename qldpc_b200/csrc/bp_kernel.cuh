@@ -145,7 +145,7 @@ __host__ __device__ inline BPSmemLayout bp_smem_layout(const BPGraphDev &g, int 
 //          evaluated check by check after the variable pass.
 // ------------------------------------------------------------------------------------------
 template <typename T, int VAR, int WMS, bool STATE_SMEM>
-__global__ void __launch_bounds__(STATE_SMEM ? 256 : 128, STATE_SMEM ? 1 : 4)
+__global__ void __launch_bounds__(STATE_SMEM ? 256 : 128, STATE_SMEM ? 1 : 6)
 bp_decode_kernel(const BPParams P)
 {
     typedef Num<T> N;
@@ -165,8 +165,9 @@ bp_decode_kernel(const BPParams P)
     const uint32_t *colmask;
     const T *prior;
     // ---- state (stride S words between consecutive edges of one shot) ---------------------
-    T *Q, *M1, *M2;
-    uint32_t *HW, *SY = nullptr;
+    // (__restrict__: the arrays are disjoint, so loads of the next check may be hoisted above the summary stores)
+    T *__restrict__ Q, *__restrict__ M1, *__restrict__ M2;
+    uint32_t *__restrict__ HW, *__restrict__ SY = nullptr;
     int S;
 
     if (STATE_SMEM) {
@@ -268,6 +269,7 @@ bp_decode_kernel(const BPParams P)
                 sw = SY[(idx_t)w * S];
             }
             const int cend = min(32, m - 32 * w);
+#pragma unroll 2
             for (int b = 0; b < cend; ++b) {
                 const int c = 32 * w + b;
                 const bits_t sbit = ((sw >> b) & 1u) ? N::SIGN : (bits_t)0;
@@ -289,11 +291,24 @@ bp_decode_kernel(const BPParams P)
                             min2 = fmin(min2, t);
                         }
                     } else {
-                        const int e1 = row_ptr[c + 1];
-                        for (int e = row_ptr[c]; e < e1; ++e) {
-                            const T x = Q[(idx_t)e * S];
-                            sg ^= N::bits(x);
-                            const T a = fabs(x);
+                        // up to 8 messages are loaded up front (memory-level parallelism matters when the state is
+                        // staged in HBM); +inf is neutral for the minima and for the sign parity
+                        const int e0 = row_ptr[c], deg = row_ptr[c + 1] - e0;
+                        T x[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) x[k] = (k < deg) ? Q[(idx_t)(e0 + k) * S] : N::inf();
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            sg ^= N::bits(x[k]);
+                            const T a = fabs(x[k]);
+                            const T t = fmax(min1, a);
+                            min1 = fmin(min1, a);
+                            min2 = fmin(min2, t);
+                        }
+                        for (int e = e0 + 8; e < e0 + deg; ++e) {
+                            const T xx = Q[(idx_t)e * S];
+                            sg ^= N::bits(xx);
+                            const T a = fabs(xx);
                             const T t = fmax(min1, a);
                             min1 = fmin(min1, a);
                             min2 = fmin(min2, t);

@@ -1,28 +1,27 @@
-// Production min-sum BP kernel for code-capacity check matrices (BB codes) on sm_100a:
-// T LANES PER SHOT, float32 messages resident in shared memory.
+// Production BP kernel for code-capacity check matrices (BB codes) on sm_100a:
+// TL LANES PER SHOT, message state resident in shared memory.
 //
-// Same arithmetic as bp_decode_kernel<float, VAR_MIN_SUM, ..> (bp_kernel.cuh; reference
-// rework/decoding.py:5-75), different mapping.  The thread-per-shot kernel is bound by shared-memory
-// CAPACITY: [[144,12,12]] needs 2.3 KB of message state per shot, so only 96 shots -- 3 warps -- fit
-// on an SM and every dependent instruction is exposed (ncu r1a: 19 % issue utilisation, 43 % stall_wait,
-// 33 % short_scoreboard).  Here each shot is decoded by T = 4 or 8 lanes of one warp, so the same
-// shared memory feeds T times as many warps:
-//   * check pass : lane j of a shot owns checks c = T*i + j (min1 / min2 / sign parity of its RW
-//                  incoming messages, written as a 2-word summary),
-//   * variable pass: lane j owns variables v = T*i + j (rebuilds the <= 3 check-to-variable messages
-//                  from the summaries and the unmodified Q, posterior, hard decision, damped + clipped
-//                  Q update),
-//   * __syncwarp between the passes; the syndrome of the hard decision is accumulated per lane from
-//     packed columns of H and XOR-reduced over the T lanes with shuffles.
-// Layout: message rows are numbered ELL-style r = k*m + c (k-th edge of check c) and stored
-// [row][slot] with S slots per row, S = G (mod 32), G = 32/T shots per warp, lane = j*G + g.  The G
-// lanes of one j read G consecutive words, and rows whose index differs mod T start G banks apart,
-// so the check pass (rows k*m + T*i + j, j = 0..T-1) is bank-conflict free and its addresses are
-// affine; the variable pass reads rows through a table and is conflict-free whenever the T rows it
-// touches differ mod T.
-// The kernel is persistent; retired shots are replaced from a global cursor (refill is done by all T
-// lanes of the shot and only when at least `refill_min` shots of the warp are idle, or nothing is
-// left to wait for).
+// Same arithmetic as bp_decode_kernel (bp_kernel.cuh) -- min-sum (rework/decoding.py:5-75), sum-product
+// (decoding/beliefPropagation.py:88-144) and its damped/scaled/clipped form (rework/decoding.py:131-191), in
+// float32 or float64 -- with a different mapping; results are bit-identical to the thread-per-shot kernel.
+//
+// The thread-per-shot kernel is bound by shared-memory CAPACITY: [[144,12,12]] needs 2.3 KB of float32 message
+// state per shot, so only 96 shots -- 3 warps -- fit on an SM and every dependent instruction is exposed (ncu
+// r1a: 19 % issue utilisation, 43 % stall_wait, 33 % short_scoreboard).  Here each shot is decoded by TL = 4 or
+// 8 lanes of one warp, so the same shared memory feeds TL times as many warps:
+//   * check pass : lane j of a shot owns checks c = TL*i + j (min1 / min2 / sign parity -- or the tanh product --
+//                  of its RW incoming messages, written as a per-check summary),
+//   * variable pass: lane j owns variables v = TL*i + j (rebuilds the 3 check-to-variable messages from the
+//                  summaries and the unmodified Q, posterior, hard decision, Q update),
+//   * __syncwarp between the passes; the syndrome of the hard decision is accumulated per lane from packed
+//     columns of H and XOR-reduced over the TL lanes with shuffles.
+// Layout: message rows are numbered ELL-style r = k*m + c (k-th edge of check c) and stored [row][slot] with S
+// slots per row, S = G (mod 32), G = 32/TL shots per warp, lane = j*G + g.  The G lanes of one j read G
+// consecutive elements, and rows whose index differs mod TL start G banks apart, so the check pass (rows
+// k*m + TL*i + j, j = 0..TL-1) is bank-conflict free and its addresses are affine; the variable pass reads rows
+// through a table and is conflict-free whenever the TL rows it touches differ mod TL.
+// The kernel is persistent; retired shots are replaced from a global cursor (refill is done by all TL lanes of
+// the shot and only when at least `refill_min` shots of the warp are idle, or nothing is left to wait for).
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -37,33 +36,43 @@ struct BPTiledLayout {
     size_t tables, per_slot;
     int npad;
 };
-__host__ __device__ inline BPTiledLayout bp_tiled_layout(const BPGraphDev &g, int T)
+// tsize: bytes per message (4 / 8); summary words per check: 2 for min-sum, 1 for sum-product
+__host__ __device__ inline BPTiledLayout bp_tiled_layout(const BPGraphDev &g, int TL, int tsize, int variant)
 {
     BPTiledLayout L;
-    L.npad = (g.n + T - 1) / T * T;
+    const int nsum = (variant == VAR_MIN_SUM) ? 2 : 1;
+    L.npad = (g.n + TL - 1) / TL * TL;
     size_t o = 0;
     L.off_vt0 = o;     o += 8 * (size_t)L.npad * 3;
     L.off_vt1 = g.two_tables ? o : L.off_vt0;
     if (g.two_tables) o += 8 * (size_t)L.npad * 3;
     L.off_colmask = o; o += 4 * (size_t)L.npad * g.WM;
-    L.off_prior = o;   o += 4 * (size_t)L.npad;
+    o = (o + 7) & ~(size_t)7;
+    L.off_prior = o;   o += (size_t)tsize * L.npad;
     o = (o + 127) & ~(size_t)127;
     L.off_state = o;
     L.tables = o;
-    // rows: RW*m message rows (4 B per slot) + m summary rows (float2 {signed min1, min2}: 8 B per slot)
-    // + WN hard-decision rows (4 B per slot)
-    L.per_slot = 4 * ((size_t)g.uniform_row_w * g.m + 2 * (size_t)g.m + g.WN);
+    // rows: RW*m message rows + m summary rows (nsum messages wide) + WN hard-decision rows (4 B per slot)
+    L.per_slot = (size_t)tsize * ((size_t)g.uniform_row_w * g.m + (size_t)nsum * g.m) + 4 * (size_t)g.WN;
     return L;
 }
 
-// vell tables (global, built by the host): entry (v, t), t < 3: c | (k << 16), or 0xFFFFFFFF when
-// variable v has fewer than t+1 edges.  c = check, k = position of v inside row c.
-template <int T, int WMS, int RW>
+// per-check summary, moved with one vector access: {signed min1, min2} for min-sum, the signed product for sum-product
+template <typename T, int NS> struct alignas(NS * sizeof(T)) SummaryT { T v[NS]; };
+
+// vell tables (global, built by the host): entry (v, t), t < 3: c | (k << 16).  c = check, k = position of v inside
+// row c.  Every variable has exactly 3 edges (all BB codes).
+template <typename T, int VAR, int TL, int WMS, int RW>
 __global__ void __launch_bounds__(576, 1)
 bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint32_t *__restrict__ vell1, int refill_min)
 {
-    constexpr int G = 32 / T;                 // shots per warp
-    constexpr int VPW = 32 / T;               // variables (or checks) per lane per 32-bit word
+    typedef Num<T> N;
+    typedef typename N::bits_t bits_t;
+    constexpr int NS = (VAR == VAR_MIN_SUM) ? 2 : 1;
+    typedef SummaryT<T, NS> sum_t;
+    constexpr int G = 32 / TL;                // shots per warp
+    constexpr int VPW = 32 / TL;              // variables (or checks) per lane per 32-bit word
+    constexpr uint32_t TS = sizeof(T);
     const BPGraphDev &g = P.g;
     const int m = g.m, n = g.n, WN = g.WN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -73,34 +82,37 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
     const unsigned FULL = 0xffffffffu;
 
     extern __shared__ __align__(16) unsigned char smem[];
-    const BPTiledLayout L = bp_tiled_layout(g, T);
+    const BPTiledLayout L = bp_tiled_layout(g, TL, (int)TS, VAR);
     uint2 *vt0 = reinterpret_cast<uint2 *>(smem + L.off_vt0);
     uint2 *vt1 = reinterpret_cast<uint2 *>(smem + L.off_vt1);
     uint32_t *colmask = reinterpret_cast<uint32_t *>(smem + L.off_colmask);
-    float *prior = reinterpret_cast<float *>(smem + L.off_prior);
+    T *prior = reinterpret_cast<T *>(smem + L.off_prior);
     unsigned char *state = smem + L.off_state;
-    const uint32_t rowB = 4u * S;                               // bytes per row
-    const uint32_t offM = (uint32_t)RW * m * rowB, offHW = offM + 2u * (uint32_t)m * rowB;   // summaries: 2*rowB per check
+    const uint32_t rowQ = TS * S;                               // bytes per message row
+    const uint32_t rowM = NS * TS * S;                          // bytes per summary row
+    const uint32_t offM = (uint32_t)RW * m * rowQ, offHW = offM + (uint32_t)m * rowM;
 
     for (int i = threadIdx.x; i < L.npad * 3; i += blockDim.x) {
         const int v = i / 3;
-        uint32_t e0 = (v < n) ? vell0[i] : 0xffffffffu, e1 = (v < n) ? vell1[i] : 0xffffffffu;
         auto mk = [&](uint32_t e) {
-            if (e == 0xffffffffu) return make_uint2(0xffffffffu, 0u);
             const uint32_t c = e & 0xffffu, k = e >> 16;
-            return make_uint2((k * m + c) * rowB, offM + c * 2u * rowB);
+            return make_uint2((k * m + c) * rowQ, offM + c * rowM);
         };
-        vt0[i] = mk(e0);
-        if (g.two_tables) vt1[i] = mk(e1);
+        vt0[i] = (v < n) ? mk(vell0[i]) : make_uint2(0u, offM);
+        if (g.two_tables) vt1[i] = (v < n) ? mk(vell1[i]) : make_uint2(0u, offM);
     }
     for (int i = threadIdx.x; i < L.npad * WMS; i += blockDim.x) colmask[i] = (i < n * WMS) ? g.colmask[i] : 0u;
-    for (int i = threadIdx.x; i < L.npad; i += blockDim.x) prior[i] = (i < n) ? reinterpret_cast<const float *>(P.prior)[i] : 0.f;
+    for (int i = threadIdx.x; i < L.npad; i += blockDim.x) prior[i] = (i < n) ? reinterpret_cast<const T *>(P.prior)[i] : (T)0;
     __syncthreads();
 
-    unsigned char *my = state + 4 * slot;                       // this shot's column in the 4-byte rows
-    unsigned char *my8 = state + 8 * slot;                      // ... and in the 8-byte summary rows
-    const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
+    unsigned char *myQ = state + TS * slot;                     // this shot's column in the message rows
+    unsigned char *myM = state + NS * TS * slot;                // ... in the summary rows
+    unsigned char *myH = state + 4 * slot;                      // ... in the hard-decision rows
+    const T alpha = (T)P.alpha, damp = (T)P.damping, omd = (T)P.one_minus_damping, clipv = (T)P.clip;
     const int max_iter = P.max_iter;
+    const bool sym = P.sym != 0;
+    const bool slot_is_tanh = (VAR == VAR_SUM_PRODUCT) && !sym;
+    const T CLIP_VAL = (T)0.9999999;
 
     uint32_t synd[WMS], acc[WMS];
     long long shot = -1;
@@ -110,9 +122,9 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
 
     while (true) {
         // ---- refill ------------------------------------------------------------------------
-        const unsigned idle = __ballot_sync(FULL, !active && !exhausted);       // lanes (all T of a shot together)
+        const unsigned idle = __ballot_sync(FULL, !active && !exhausted);       // lanes (all TL of a shot together)
         const unsigned busy = __ballot_sync(FULL, active);
-        const int idle_shots = __popc(idle) / T;
+        const int idle_shots = __popc(idle) / TL;
         if (idle_shots > 0 && (idle_shots >= refill_min || busy == 0)) {
             // one atomic per warp; shot ids are dealt to the idle groups in lane order of sub-lane 0
             const unsigned lead = idle & ((1u << G) - 1u);                      // idle groups, seen at j == 0
@@ -125,13 +137,12 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                     const uint32_t *sp = P.synd + (size_t)shot * WMS;
 #pragma unroll
                     for (int w = 0; w < WMS; ++w) synd[w] = sp[w];
-                    // Q = where(mask, prior, 0) (decoding.py:21): the T lanes split the variables
-                    for (int v = j; v < n; v += T) {
-                        const float pv = prior[v] + 0.f;
+                    // Q = where(mask, prior, 0) (decoding.py:21 / beliefPropagation.py:107): the lanes split the variables
+                    for (int v = j; v < n; v += TL) {
+                        T pv = bp_canon(prior[v]);
+                        if (slot_is_tanh) pv = N::tanh_(N::mul(pv, (T)0.5));
 #pragma unroll
-                        for (int t = 0; t < 3; ++t) {
-                            *reinterpret_cast<float *>(my + vt1[v * 3 + t].x) = pv;
-                        }
+                        for (int t = 0; t < 3; ++t) *reinterpret_cast<T *>(myQ + vt1[v * 3 + t].x) = pv;
                     }
                     iter = 0;
                     active = true;
@@ -147,65 +158,92 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
         }
         if (active) {
             __syncwarp(amask);
-            // ================= horizontal step: lane j owns checks c = T*i + j ==================
+            // ================= horizontal step: lane j owns checks c = TL*i + j ==================
 #pragma unroll
             for (int w = 0; w < WMS; ++w) {
                 const uint32_t sw = synd[w] >> j;
-                const int cnt = min(VPW, (m - 32 * w - j + T - 1) / T);          // checks of this lane in word w
+                const int cnt = min(VPW, (m - 32 * w - j + TL - 1) / TL);        // checks of this lane in word w
 #pragma unroll 2
                 for (int ii = 0; ii < cnt; ++ii) {
-                    const int c = 32 * w + T * ii + j;
-                    const unsigned char *q = my + (uint32_t)c * rowB;
-                    float x[RW];
+                    const int c = 32 * w + TL * ii + j;
+                    const unsigned char *q = myQ + (uint32_t)c * rowQ;
+                    T x[RW];
 #pragma unroll
-                    for (int k = 0; k < RW; ++k) x[k] = *reinterpret_cast<const float *>(q + (uint32_t)k * m * rowB);
-                    uint32_t sg = (sw >> (T * ii)) << 31;                          // syndrome bit -> sign bit
-                    float min1 = CUDART_INF_F, min2 = CUDART_INF_F;
+                    for (int k = 0; k < RW; ++k) x[k] = *reinterpret_cast<const T *>(q + (uint32_t)k * m * rowQ);
+                    const bits_t sbit = (bits_t)((sw >> (TL * ii)) & 1u) << (8 * sizeof(bits_t) - 1);   // syndrome bit -> sign bit
+                    sum_t sv;
+                    if (VAR == VAR_MIN_SUM) {
+                        // decoding.py:28-53: sign product, min1, min2
+                        bits_t sg = sbit;
+                        T min1 = N::inf(), min2 = N::inf();
 #pragma unroll
-                    for (int k = 0; k < RW; ++k) {
-                        sg ^= __float_as_uint(x[k]);
-                        const float a = fabsf(x[k]);
-                        const float t = fmaxf(min1, a);
-                        min1 = fminf(min1, a);
-                        min2 = fminf(min2, t);
+                        for (int k = 0; k < RW; ++k) {
+                            sg ^= N::bits(x[k]);
+                            const T a = fabs(x[k]);
+                            const T t = fmax(min1, a);
+                            min1 = fmin(min1, a);
+                            min2 = fmin(min2, t);
+                        }
+                        sv.v[0] = N::from_bits(N::bits(min1) | (sg & N::SIGN));
+                        sv.v[NS - 1] = min2;
+                        if (NS == 2) sv.v[0] = N::from_bits(N::bits(min1) | (sg & N::SIGN));
+                    } else {
+                        // beliefPropagation.py:114-118: row product of tanh(Q/2), ascending column order
+                        T prod = (T)1;
+#pragma unroll
+                        for (int k = 0; k < RW; ++k) {
+                            const T t = slot_is_tanh ? x[k] : N::tanh_(N::mul(x[k], (T)0.5));
+                            prod = N::mul(prod, t);
+                        }
+                        sv.v[0] = N::from_bits(N::bits(prod) ^ sbit);                             // * (1 - 2 s)
                     }
-                    *reinterpret_cast<float2 *>(my8 + offM + (uint32_t)c * 2u * rowB) =
-                        make_float2(__uint_as_float(__float_as_uint(min1) | (sg & 0x80000000u)), min2);
+                    *reinterpret_cast<sum_t *>(myM + offM + (uint32_t)c * rowM) = sv;
                 }
             }
             __syncwarp(amask);
 
-            // ================= vertical step: lane j owns variables v = T*i + j ==================
+            // ================= vertical step: lane j owns variables v = TL*i + j ==================
             const uint2 *vt = (iter == 0) ? vt0 : vt1;
             const bool last = (iter == max_iter - 1);
             const bool wr_llr = (P.llr != nullptr) && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && last));
-            float *llr_out = wr_llr ? reinterpret_cast<float *>(P.llr) + (size_t)shot * n : nullptr;
+            T *llr_out = wr_llr ? reinterpret_cast<T *>(P.llr) + (size_t)shot * n : nullptr;
 #pragma unroll
             for (int k = 0; k < WMS; ++k) acc[k] = 0;
             for (int wv = 0; wv < WN; ++wv) {
                 uint32_t hw = 0;
-                const int cnt = min(VPW, (n - 32 * wv - j + T - 1) / T);         // variables of this lane in word wv
+                const int cnt = min(VPW, (n - 32 * wv - j + TL - 1) / TL);       // variables of this lane in word wv
 #pragma unroll 2
                 for (int ii = 0; ii < cnt; ++ii) {
-                    const int b = T * ii + j;
+                    const int b = TL * ii + j;
                     const int v = 32 * wv + b;
                     const uint2 *ent = vt + v * 3;
                     uint2 e[3];
-                    float qo[3], r[3];
+                    T qo[3], r[3];
 #pragma unroll
                     for (int t = 0; t < 3; ++t) e[t] = ent[t];
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
-                        const float q = *reinterpret_cast<const float *>(my + e[t].x);
-                        const float2 s12 = *reinterpret_cast<const float2 *>(my8 + e[t].y);
-                        const float a1 = fabsf(s12.x);
-                        const float mag = (fabsf(q) == a1) ? s12.y : a1;                          // decoding.py:51-53
-                        r[t] = __uint_as_float(__float_as_uint(__fmul_rn(alpha, mag)) ^
-                                               ((__float_as_uint(s12.x) ^ __float_as_uint(q)) & 0x80000000u)); // :55
+                        const T q = *reinterpret_cast<const T *>(myQ + e[t].x);
+                        const sum_t s12 = *reinterpret_cast<const sum_t *>(myM + e[t].y);
+                        const T s1 = s12.v[0];
+                        if (VAR == VAR_MIN_SUM) {
+                            const T s2 = s12.v[NS - 1];
+                            const T a1 = fabs(s1);
+                            const T mag = (fabs(q) == a1) ? s2 : a1;                              // decoding.py:51-53
+                            r[t] = N::from_bits(N::bits(N::mul(alpha, mag)) ^ ((N::bits(s1) ^ N::bits(q)) & N::SIGN)); // :55
+                        } else {
+                            const T tq = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
+                            const T ts = (fabs(tq) < (T)1e-15) ? (T)1e-15 : tq;                   // beliefPropagation.py:122
+                            T xx = N::div(s1, ts);
+                            xx = fmin(fmax(xx, -CLIP_VAL), CLIP_VAL);                            // :125
+                            T rr = N::mul((T)2, N::atanh_(xx));                                  // :126
+                            if (sym) rr = N::mul(rr, alpha);                                     // decoding.py:171
+                            r[t] = rr;
+                        }
                         qo[t] = q;
                     }
-                    const float val = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), r[2]), prior[v]);    // :61-62
-                    const bool hd = val < 0.f;
+                    const T val = N::add(N::add(N::add(r[0], r[1]), r[2]), prior[v]);            // values = R_sum + prior
+                    const bool hd = val < (T)0;
                     hw |= (uint32_t)hd << b;
                     if (wr_llr) llr_out[v] = val;
                     if (hd) {
@@ -214,16 +252,21 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                     }
 #pragma unroll
                     for (int t = 0; t < 3; ++t) {
-                        float qn = __fsub_rn(val, r[t]);                                           // :63
-                        qn = bp_damp(damp, qn, omd, qo[t]);                                        // :65
-                        qn = fminf(fmaxf(qn, -clipv), clipv);                                      // :66
-                        *reinterpret_cast<float *>(my + e[t].x) = qn;
+                        T qn = N::sub(val, r[t]);                                                 // Q_new = values - R
+                        if (VAR == VAR_MIN_SUM || sym) {
+                            qn = bp_damp(damp, qn, omd, qo[t]);                                   // decoding.py:65 / :179
+                            qn = fmin(fmax(qn, -clipv), clipv);                                   // :66 / :181
+                            qn = bp_canon(qn);
+                        } else {
+                            qn = N::tanh_(N::mul(qn, (T)0.5));                                    // the slot holds tanh(Q/2)
+                        }
+                        *reinterpret_cast<T *>(myQ + e[t].x) = qn;
                     }
                 }
-                // the T lanes of the shot hold disjoint bits of this word
+                // the TL lanes of the shot hold disjoint bits of this word
 #pragma unroll
                 for (int o = G; o < 32; o <<= 1) hw |= __shfl_xor_sync(amask, hw, o);
-                if (j == 0) *reinterpret_cast<uint32_t *>(my + offHW + (uint32_t)wv * rowB) = hw;
+                if (j == 0) *reinterpret_cast<uint32_t *>(myH + offHW + (uint32_t)wv * (4u * S)) = hw;
             }
 
             // ================= syndrome of the hard decision ======================================
@@ -236,10 +279,10 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                 conv = conv && (a == synd[k]);
             }
 
-            __syncwarp(amask);          // hard-decision words written by sub-lane 0 are read by all T lanes
+            __syncwarp(amask);          // hard-decision words written by sub-lane 0 are read by all TL lanes
             if (conv || last) {
                 uint32_t *ho = P.hard + (size_t)shot * WN;
-                for (int w = j; w < WN; w += T) ho[w] = *reinterpret_cast<const uint32_t *>(my + offHW + (uint32_t)w * rowB);
+                for (int w = j; w < WN; w += TL) ho[w] = *reinterpret_cast<const uint32_t *>(myH + offHW + (uint32_t)w * (4u * S));
                 if (j == 0) {
                     P.conv[shot] = conv ? 1 : 0;
                     if (P.iters) P.iters[shot] = iter;

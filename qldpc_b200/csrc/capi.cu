@@ -250,12 +250,14 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     const bool wm_ok = (c->WM <= 5);
     G->tiled_T = 0;
     G->refill_min = 1;
-    if (cfg->staged == 0 && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM && c->tiled_ok) {
+    if (cfg->staged == 0 && c->tiled_ok) {
+        const bool f32ms = (cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM);   // both lane counts are built for it
         // T lanes per shot; NW warps with NW = 1 (mod T) keeps the check pass bank-conflict free
         int bestT = 0, bestNW = 0;
         for (int T : {4, 8}) {
-            if (cfg->lanes_per_shot && cfg->lanes_per_shot != T) continue;
-            const BPTiledLayout TL = bp_tiled_layout(g, T);
+            if (!f32ms && T != 8) continue;
+            if (f32ms && cfg->lanes_per_shot && cfg->lanes_per_shot != T) continue;
+            const BPTiledLayout TL = bp_tiled_layout(g, T, tsize, kernel_variant(cfg->variant));
             const int Gs = 32 / T;
             if (TL.tables + (size_t)Gs * TL.per_slot > (size_t)c->smem_optin) continue;
             long long smax = (long long)(((size_t)c->smem_optin - TL.tables) / TL.per_slot);
@@ -265,7 +267,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
             if (nw >= 1 && (nw > bestNW || bestT == 0)) { bestT = T; bestNW = (int)nw; }
         }
         if (bestT) {
-            const BPTiledLayout TL = bp_tiled_layout(g, bestT);
+            const BPTiledLayout TL = bp_tiled_layout(g, bestT, tsize, kernel_variant(cfg->variant));
             const int Gs = 32 / bestT;
             G->staged = false;
             G->tiled_T = bestT;
@@ -294,7 +296,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->threads = 128;
         G->shots_per_cta = 128;
         G->smem = 0;
-        G->grid = (int)std::max<long long>(1, std::min<long long>((B + 127) / 128, (long long)c->num_sms * 4));
+        G->grid = (int)std::max<long long>(1, std::min<long long>((B + 127) / 128, (long long)c->num_sms * 6));   // __launch_bounds__(128, 6)
         const size_t per_thread = (size_t)tsize * (c->E + 2 * (size_t)c->m) + 4 * (size_t)(c->WN + c->WM);
         G->gstate_bytes = per_thread * (size_t)G->grid * G->threads;
     }
@@ -351,23 +353,35 @@ static cudaError_t launch_bp_inst(const BPParams &P, const BPGeom &G, cudaStream
     return cudaGetLastError();
 }
 
-template <int T, int WMS>
+template <typename T, int VAR, int TL, int WMS>
 static cudaError_t launch_bp_tiled_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    auto kern = bp_tiled_kernel<T, WMS, 6>;
+    auto kern = bp_tiled_kernel<T, VAR, TL, WMS, 6>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
     if (e != cudaSuccess) return e;
     kern<<<G.grid, G.threads, G.smem, st>>>(P, c->d_vell0, c->d_vell1, G.refill_min);
     return cudaGetLastError();
 }
 
-static cudaError_t launch_bp_tiled(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+template <typename T, int VAR, int TL>
+static cudaError_t launch_bp_tiled_w(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-#define TILED_CASE(TT, WW) if (G.tiled_T == TT && P.g.WM == WW) return launch_bp_tiled_inst<TT, WW>(c, P, G, st)
-    TILED_CASE(4, 2); TILED_CASE(4, 3); TILED_CASE(4, 5);
-    TILED_CASE(8, 2); TILED_CASE(8, 3); TILED_CASE(8, 5);
-#undef TILED_CASE
-    return cudaErrorInvalidValue;
+    switch (P.g.WM) {
+    case 2: return launch_bp_tiled_inst<T, VAR, TL, 2>(c, P, G, st);
+    case 3: return launch_bp_tiled_inst<T, VAR, TL, 3>(c, P, G, st);
+    case 5: return launch_bp_tiled_inst<T, VAR, TL, 5>(c, P, G, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+static cudaError_t launch_bp_tiled(const qldpc_code *c, const BPParams &P, const BPGeom &G, int precision, int kv, cudaStream_t st)
+{
+    if (precision == 32 && kv == VAR_MIN_SUM)
+        return G.tiled_T == 4 ? launch_bp_tiled_w<float, VAR_MIN_SUM, 4>(c, P, G, st) : launch_bp_tiled_w<float, VAR_MIN_SUM, 8>(c, P, G, st);
+    if (G.tiled_T != 8) return cudaErrorInvalidValue;
+    if (precision == 32) return launch_bp_tiled_w<float, VAR_SUM_PRODUCT, 8>(c, P, G, st);
+    if (kv == VAR_MIN_SUM) return launch_bp_tiled_w<double, VAR_MIN_SUM, 8>(c, P, G, st);
+    return launch_bp_tiled_w<double, VAR_SUM_PRODUCT, 8>(c, P, G, st);
 }
 
 template <typename T, int VAR>
@@ -432,7 +446,7 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
     if (G.tiled_T)
-        e = launch_bp_tiled(c, P, G, st);
+        e = launch_bp_tiled(c, P, G, cfg->precision, kv, st);
     else if (cfg->precision == 64)
         e = (kv == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
     else

@@ -350,9 +350,19 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
             int best = 0x7fffffff;
             unsigned hasmask = 0;                                   // bit s: my s-th row has the bit
             int sidx = 0;
+            int cw[4], cs[4];                                      // word / shift of the first 4 checks of this column
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = (a0 + k < a1) ? (int)P.vtab[2 * (a0 + k) + 1] : -1;
+                cw[k] = c >> 5;
+                cs[k] = (c < 0) ? -1 : (c & 31);
+            }
             for (int r = tid; r < m; r += NT, ++sidx) {
                 uint32_t x = 0;
-                for (int a = a0; a < a1; ++a) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (cs[k] >= 0) x ^= T[(size_t)r * WM + cw[k]] >> cs[k];
+                for (int a = a0 + 4; a < a1; ++a) {
                     const int c = (int)P.vtab[2 * a + 1];
                     x ^= T[(size_t)r * WM + (c >> 5)] >> (c & 31);
                 }

@@ -209,6 +209,16 @@ def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
         got = code.bp_decode_batch(synd[:B], prior, **kw)
         for x, y in zip(got, ref):
             assert np.array_equal(x, y[:B])
+    # the other instantiations of the tiled kernel: float64 min-sum, sum-product (plain and damped) in both precisions
+    for variant, prec, al, dm, cl in (("min_sum", 64, 0.8, 0.7, 25.0), ("sum_product", 64, 1.0, 1.0, 20.0),
+                                      ("sum_product_sym", 64, 0.9, 0.8, 20.0), ("sum_product", 32, 1.0, 1.0, 20.0),
+                                      ("sum_product_sym", 32, 0.9, 0.8, 20.0)):
+        k2 = dict(variant=variant, max_iter=40, alpha=al, damping=dm, clip=cl, precision=prec)
+        assert code.geometry(code.config(**k2))["kernel"] == "tiled"
+        a = code.bp_decode_batch(synd[:1500], prior, staged=2, **k2)
+        b = code.bp_decode_batch(synd[:1500], prior, **k2)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), (stem, variant, prec)
     # non-uniform prior and default parameters (alpha = damping = 1)
     pr = rng.uniform(1.5, 4.0, n)
     a = code.bp_decode_batch(synd[:800], pr, "min_sum", 30, precision=32, staged=2)

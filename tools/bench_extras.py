@@ -91,68 +91,81 @@ def emit(config, **kw):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated config numbers, e.g. 4")
     args = ap.parse_args()
     q = 4 if args.quick else 1
+    only = set(args.only.split(",")) if args.only else None
+    global emit
+    _emit = emit
+    def emit(config, **kw):
+        if only is None or config.split(":")[0] in only:
+            _emit(config, **kw)
+    want = lambda k: only is None or k in only
     ms_kw = dict(variant="min_sum", alpha=0.8, damping=0.7, clip=25.0, precision=32)
 
-    # config 1: [[72,12,6]] p = 0.05, min-sum 50 iterations + OSD-0
-    H, Lx, d = load("[[72, 12, 6]]")
-    r = Runner(H, Lx, d)
-    emit("1: [[72,12,6]] p=0.05 min-sum BP50 + OSD-0, f32", **r.run(0.05, 8_000_000 // q, dict(max_iter=50, **ms_kw), 0))
-    emit("1: [[72,12,6]] p=0.05 min-sum defaults (alpha=1,damping=1,clip=20) BP50 + OSD-0, f32",
-         **r.run(0.05, 4_000_000 // q, dict(variant="min_sum", max_iter=50, precision=32), 0))
-
-    # config 2: [[144,12,12]] p-sweep, BP100 + OSD-7
-    H, Lx, d = load("[[144, 12, 12]]")
-    r = Runner(H, Lx, d)
-    for p in (0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.1):
-        emit(f"2: [[144,12,12]] p={p} min-sum BP100 + OSD-7, f32", p=p, **r.run(p, 8_000_000 // q, dict(max_iter=100, **ms_kw), 7))
-    emit("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f64 (thread-per-shot kernel)", p=0.05,
-         **r.run(0.05, 400_000 // q, dict(variant="sum_product", max_iter=100, precision=64), 7, reps=1))
-    emit("2: [[144,12,12]] p=0.05 min-sum BP100 + OSD-7, f64 parity mode (thread-per-shot kernel)", p=0.05,
-         **r.run(0.05, 1_000_000 // q, dict(variant="min_sum", max_iter=100, alpha=0.8, damping=0.7, clip=25.0, precision=64), 7, reps=1))
-
-    # config 3: [[288,12,18]] BP only
-    H, Lx, d = load("[[288, 12, 18]]")
-    r = Runner(H, Lx, d)
-    for p in (0.1, 0.06, 0.05, 0.04):
-        emit(f"3: [[288,12,18]] p={p} min-sum BP50, BP only, f32", p=p, **r.run(p, 4_000_000 // q, dict(max_iter=50, **ms_kw), -1))
-
-    # config 5: [[90,8,10]] / [[108,8,10]] p = 0.01, iteration budgets, min-sum vs sum-product
-    for name in ("[[90, 8, 10]]", "[[108, 8, 10]]"):
-        H, Lx, d = load(name)
+    if want('1'):  # config 1: [[72,12,6]] p = 0.05, min-sum 50 iterations + OSD-0
+        H, Lx, d = load("[[72, 12, 6]]")
         r = Runner(H, Lx, d)
-        for mi in (10, 50, 90):
-            emit(f"5: {name} p=0.01 min-sum BP{mi} + OSD-0, f32", **r.run(0.01, 8_000_000 // q, dict(max_iter=mi, **ms_kw), 0))
-        emit(f"5: {name} p=0.01 sum-product BP50 + OSD-0, f64", **r.run(0.01, 1_000_000 // q, dict(variant="sum_product", max_iter=50, precision=64), 0, reps=1))
+        emit("1: [[72,12,6]] p=0.05 min-sum BP50 + OSD-0, f32", **r.run(0.05, 8_000_000 // q, dict(max_iter=50, **ms_kw), 0))
+        emit("1: [[72,12,6]] p=0.05 min-sum defaults (alpha=1,damping=1,clip=20) BP50 + OSD-0, f32",
+             **r.run(0.05, 4_000_000 // q, dict(variant="min_sum", max_iter=50, precision=32), 0))
 
-    # config 4: space-time [[144,12,12]] x 12 rounds (864 x 2592), HBM-staged BP50 + OSD-0
-    H, Lx, d = load("[[144, 12, 12]]")
-    Hst = spaceTimeMatrix(H, 12)
-    r = Runner(Hst)
-    E = r.code.E
-    for p in (0.001, 0.005):
-        B = 300_000 // q
-        # syndromes of the phenomenological model WITHOUT the reference sampler's first-block quirk are not what the
-        # reference decodes; use its own sampler semantics, vectorised (spaceTime.py:20-43)
-        rng = np.random.default_rng(4)
-        m, n = H.shape
-        err = (rng.random((B, n)) < p).astype(np.int64)
-        s = (err @ H.T) % 2
-        hist = []
-        for _ in range(12):
-            s = (s + (rng.random((B, m)) < p)) % 2
-            hist.append(s)
-        blocks = [hist[-1]] + [(hist[i] + hist[i - 1]) % 2 for i in range(1, 12)]
-        synd = np.concatenate(blocks, axis=1).astype(np.uint8)
-        res = r.run(p, B, dict(max_iter=50, **ms_kw), 0, synd_override=synd, reps=1)
-        res_bp = r.run(p, B, dict(max_iter=50, **ms_kw), -1, synd_override=synd, reps=1)
-        bytes_per_iter = 12 * E
-        gbs = res_bp["shot_iterations_per_s"] * bytes_per_iter / 1e9
-        emit(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, HBM-staged", p=p, **res,
-             bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
-             roofline=dict(bound="hbm", algorithmic_bytes_per_shot_iteration=bytes_per_iter, achieved=gbs, peak=PEAKS.get("hbm_gbs", 6650.0),
-                           unit="GB/s", frac=gbs / PEAKS.get("hbm_gbs", 6650.0), note="BP kernel alone (bp_only run)"))
+
+    if want('2'):  # config 2: [[144,12,12]] p-sweep, BP100 + OSD-7
+        H, Lx, d = load("[[144, 12, 12]]")
+        r = Runner(H, Lx, d)
+        for p in (0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.1):
+            emit(f"2: [[144,12,12]] p={p} min-sum BP100 + OSD-7, f32", p=p, **r.run(p, 8_000_000 // q, dict(max_iter=100, **ms_kw), 7))
+        emit("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f64 (thread-per-shot kernel)", p=0.05,
+             **r.run(0.05, 400_000 // q, dict(variant="sum_product", max_iter=100, precision=64), 7, reps=1))
+        emit("2: [[144,12,12]] p=0.05 min-sum BP100 + OSD-7, f64 parity mode (thread-per-shot kernel)", p=0.05,
+             **r.run(0.05, 1_000_000 // q, dict(variant="min_sum", max_iter=100, alpha=0.8, damping=0.7, clip=25.0, precision=64), 7, reps=1))
+
+
+    if want('3'):  # config 3: [[288,12,18]] BP only
+        H, Lx, d = load("[[288, 12, 18]]")
+        r = Runner(H, Lx, d)
+        for p in (0.1, 0.06, 0.05, 0.04):
+            emit(f"3: [[288,12,18]] p={p} min-sum BP50, BP only, f32", p=p, **r.run(p, 4_000_000 // q, dict(max_iter=50, **ms_kw), -1))
+
+
+    if want('5'):  # config 5: [[90,8,10]] / [[108,8,10]] p = 0.01, iteration budgets, min-sum vs sum-product
+        for name in ("[[90, 8, 10]]", "[[108, 8, 10]]"):
+            H, Lx, d = load(name)
+            r = Runner(H, Lx, d)
+            for mi in (10, 50, 90):
+                emit(f"5: {name} p=0.01 min-sum BP{mi} + OSD-0, f32", **r.run(0.01, 8_000_000 // q, dict(max_iter=mi, **ms_kw), 0))
+            emit(f"5: {name} p=0.01 sum-product BP50 + OSD-0, f64", **r.run(0.01, 1_000_000 // q, dict(variant="sum_product", max_iter=50, precision=64), 0, reps=1))
+
+
+    if want('4'):  # config 4: space-time [[144,12,12]] x 12 rounds (864 x 2592), HBM-staged BP50 + OSD-0
+        H, Lx, d = load("[[144, 12, 12]]")
+        Hst = spaceTimeMatrix(H, 12)
+        r = Runner(Hst)
+        E = r.code.E
+        for p in (0.001, 0.005):
+            B = 300_000 // q
+            # syndromes of the phenomenological model WITHOUT the reference sampler's first-block quirk are not what the
+            # reference decodes; use its own sampler semantics, vectorised (spaceTime.py:20-43)
+            rng = np.random.default_rng(4)
+            m, n = H.shape
+            err = (rng.random((B, n)) < p).astype(np.int64)
+            s = (err @ H.T) % 2
+            hist = []
+            for _ in range(12):
+                s = (s + (rng.random((B, m)) < p)) % 2
+                hist.append(s)
+            blocks = [hist[-1]] + [(hist[i] + hist[i - 1]) % 2 for i in range(1, 12)]
+            synd = np.concatenate(blocks, axis=1).astype(np.uint8)
+            res = r.run(p, B, dict(max_iter=50, **ms_kw), 0, synd_override=synd, reps=1)
+            res_bp = r.run(p, B, dict(max_iter=50, **ms_kw), -1, synd_override=synd, reps=1)
+            bytes_per_iter = 12 * E
+            gbs = res_bp["shot_iterations_per_s"] * bytes_per_iter / 1e9
+            emit(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, HBM-staged", p=p, **res,
+                 bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
+                 roofline=dict(bound="hbm", algorithmic_bytes_per_shot_iteration=bytes_per_iter, achieved=gbs, peak=PEAKS.get("hbm_gbs", 6650.0),
+                               unit="GB/s", frac=gbs / PEAKS.get("hbm_gbs", 6650.0), note="BP kernel alone (bp_only run)"))
+
 
 
 if __name__ == "__main__":

@@ -275,6 +275,23 @@ def main():
     torch.cuda.synchronize()
     e2e_matches = bool(torch.equal(corr_u8_dev.cpu(), corr_h))
 
+    # ---------------- the other BP variants on the same workload (reported, not part of `value`) ----------------
+    variants = {}
+    if rank == 0:
+        Bv = min(B, 1_000_000)
+        for name, kw in (("min_sum_f64_bit_exact_vs_reference", dict(BP, precision=64)),
+                         ("sum_product_f64", dict(variant="sum_product", max_iter=BP["max_iter"], precision=64)),
+                         ("sum_product_f32", dict(variant="sum_product", max_iter=BP["max_iter"], precision=32))):
+            cv = Code.config(**kw)
+            run_v = lambda: _lib.check(L.qldpc_bposd_decode_dev(code.handle, ctypes.byref(cv), prior_p, Bv, synd.data_ptr(), OSD_ORDER,
+                                                                corr.data_ptr(), conv.data_ptr(), iters.data_ptr(), None, stream), name)
+            run_v()
+            torch.cuda.synchronize()
+            a, b_ = ev(), ev()
+            a.record(); run_v(); b_.record()
+            torch.cuda.synchronize()
+            variants[name] = {"shots_per_s": Bv / (a.elapsed_time(b_) * 1e-3), "shots": Bv, "kernel": code.geometry(cv)["kernel"]}
+
     if rank == 0:
         A = 15 * code.E + 2 * n + m                       # lane-ops per shot-iteration
         iters_exec = int(itot.item()) / world             # per rank, over the timed steps
@@ -315,6 +332,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": Be * m, "d2h_bytes_per_step": Be * (n + 1 + 4),
                         "shots_per_step": Be, "steps": e2e_steps, "api": "qldpc_bposd_decode_host (uint8 in pinned host memory)",
                         "matches_device_path": e2e_matches},
+                "other_variants_same_workload": variants,
                 "gpu_launches": launches, "clocks": clocks}
         if world == 1 and not args.no_cpu:
             synd_cpu = synd_h.numpy()

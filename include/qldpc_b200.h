@@ -95,6 +95,11 @@ void qldpc_code_destroy(qldpc_code *code);
 int qldpc_bp_geometry(qldpc_code *code, const qldpc_bp_config *cfg, int32_t *shots_per_cta,
                       int32_t *smem_bytes, int32_t *staged);
 
+/* Diagnostic: modelled shared-memory wavefronts per shot-iteration of the variable pass of the T-lanes-per-shot
+ * kernel (message rows x2 + summary rows), with variables in natural order (`before`) and in the bank-conflict
+ * optimised order the float32 kernel uses (`after`). */
+int qldpc_tiled_conflict_model(qldpc_code *code, int32_t lanes_per_shot, double *before, double *after);
+
 /* ---------------- host-pointer API (reference dtypes) ---------------- */
 
 /* Batched BP.  Stands in for performMinSum_Symmetric / performBeliefPropagationFast /

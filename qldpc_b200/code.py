@@ -104,6 +104,13 @@ class Code:
                     lanes_per_shot=(kind - 100 if kind >= 100 else 1),
                     kernel=('hbm_staged' if kind == 1 else 'tiled' if kind >= 100 else 'thread_per_shot'))
 
+    def tiled_conflict_model(self, lanes_per_shot=8):
+        """(before, after): modelled shared-memory wavefronts per shot-iteration of the tiled kernel's variable pass with
+        natural / optimised variable order."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.lib().qldpc_tiled_conflict_model(self._h, int(lanes_per_shot), ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     # ---- host-array API (reference dtypes) -------------------------------------------------------
     def bp_decode_batch(self, syndromes, prior, variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0,
                         precision=32, want_llr=True, staged=False, lanes_per_shot=0, refill_min=0):

@@ -43,9 +43,9 @@ __host__ __device__ inline BPTiledLayout bp_tiled_layout(const BPGraphDev &g, in
     const int nsum = (variant == VAR_MIN_SUM) ? 2 : 1;
     L.npad = (g.n + TL - 1) / TL * TL;
     size_t o = 0;
-    L.off_vt0 = o;     o += 8 * (size_t)L.npad * 3;
+    L.off_vt0 = o;     o += 32 * (size_t)L.npad;                // per position: {q0,q1,q2,v} {m0,m1,m2,prior bits}
     L.off_vt1 = g.two_tables ? o : L.off_vt0;
-    if (g.two_tables) o += 8 * (size_t)L.npad * 3;
+    if (g.two_tables) o += 32 * (size_t)L.npad;
     L.off_colmask = o; o += 4 * (size_t)L.npad * g.WM;
     o = (o + 7) & ~(size_t)7;
     L.off_prior = o;   o += (size_t)tsize * L.npad;
@@ -60,8 +60,11 @@ __host__ __device__ inline BPTiledLayout bp_tiled_layout(const BPGraphDev &g, in
 // per-check summary, moved with one vector access: {signed min1, min2} for min-sum, the signed product for sum-product
 template <typename T, int NS> struct alignas(NS * sizeof(T)) SummaryT { T v[NS]; };
 
-// vell tables (global, built by the host): entry (v, t), t < 3: c | (k << 16).  c = check, k = position of v inside
-// row c.  Every variable has exactly 3 edges (all BB codes).
+// vell tables (global, built by the host): 4 words per POSITION p (the variable processed by lane p % TL at step
+// p / TL): entries t < 3 are c | (k << 16) (c = check, k = position of the variable inside row c) in the order the
+// messages are added, word 3 is the variable index v.  Positions permute variables only inside a 32-variable word
+// (so hard-decision bits stay in their word); the permutation is chosen on the host to spread the rows touched by
+// the TL lanes of a step over distinct shared-memory banks.  Every variable has exactly 3 edges (all BB codes).
 template <typename T, int VAR, int TL, int WMS, int RW>
 __global__ void __launch_bounds__(576, 1)
 bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint32_t *__restrict__ vell1, int refill_min)
@@ -83,8 +86,8 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
 
     extern __shared__ __align__(16) unsigned char smem[];
     const BPTiledLayout L = bp_tiled_layout(g, TL, (int)TS, VAR);
-    uint2 *vt0 = reinterpret_cast<uint2 *>(smem + L.off_vt0);
-    uint2 *vt1 = reinterpret_cast<uint2 *>(smem + L.off_vt1);
+    uint4 *vt0 = reinterpret_cast<uint4 *>(smem + L.off_vt0);
+    uint4 *vt1 = reinterpret_cast<uint4 *>(smem + L.off_vt1);
     uint32_t *colmask = reinterpret_cast<uint32_t *>(smem + L.off_colmask);
     T *prior = reinterpret_cast<T *>(smem + L.off_prior);
     unsigned char *state = smem + L.off_state;
@@ -92,14 +95,26 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
     const uint32_t rowM = NS * TS * S;                          // bytes per summary row
     const uint32_t offM = (uint32_t)RW * m * rowQ, offHW = offM + (uint32_t)m * rowM;
 
-    for (int i = threadIdx.x; i < L.npad * 3; i += blockDim.x) {
-        const int v = i / 3;
-        auto mk = [&](uint32_t e) {
-            const uint32_t c = e & 0xffffu, k = e >> 16;
-            return make_uint2((k * m + c) * rowQ, offM + c * rowM);
+    for (int p = threadIdx.x; p < L.npad; p += blockDim.x) {
+        auto mk = [&](const uint32_t *ve, uint4 *vt) {
+            if (p >= n) {                                            // padding position: never visited by the passes
+                vt[2 * p] = make_uint4(0u, 0u, 0u, 0xffffffffu);
+                vt[2 * p + 1] = make_uint4(offM, offM, offM, 0u);
+                return;
+            }
+            uint32_t qq[3], mm[3];
+            for (int t = 0; t < 3; ++t) {
+                const uint32_t e = ve[4 * p + t], c = e & 0xffffu, k = e >> 16;
+                qq[t] = (k * m + c) * rowQ;
+                mm[t] = offM + c * rowM;
+            }
+            const uint32_t v = ve[4 * p + 3];
+            const uint32_t pb = (sizeof(T) == 4 && v < (uint32_t)n) ? __float_as_uint((float)reinterpret_cast<const T *>(P.prior)[v]) : 0u;
+            vt[2 * p] = make_uint4(qq[0], qq[1], qq[2], v);
+            vt[2 * p + 1] = make_uint4(mm[0], mm[1], mm[2], pb);
         };
-        vt0[i] = (v < n) ? mk(vell0[i]) : make_uint2(0u, offM);
-        if (g.two_tables) vt1[i] = (v < n) ? mk(vell1[i]) : make_uint2(0u, offM);
+        mk(vell0, vt0);
+        if (g.two_tables) mk(vell1, vt1);
     }
     for (int i = threadIdx.x; i < L.npad * WMS; i += blockDim.x) colmask[i] = (i < n * WMS) ? g.colmask[i] : 0u;
     for (int i = threadIdx.x; i < L.npad; i += blockDim.x) prior[i] = (i < n) ? reinterpret_cast<const T *>(P.prior)[i] : (T)0;
@@ -138,11 +153,14 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
 #pragma unroll
                     for (int w = 0; w < WMS; ++w) synd[w] = sp[w];
                     // Q = where(mask, prior, 0) (decoding.py:21 / beliefPropagation.py:107): the lanes split the variables
-                    for (int v = j; v < n; v += TL) {
-                        T pv = bp_canon(prior[v]);
+                    for (int p = j; p < n; p += TL) {
+                        const uint4 ea = vt1[2 * p];
+                        if (ea.w >= (uint32_t)n) continue;                          // padding position
+                        T pv = bp_canon(prior[ea.w]);
                         if (slot_is_tanh) pv = N::tanh_(N::mul(pv, (T)0.5));
-#pragma unroll
-                        for (int t = 0; t < 3; ++t) *reinterpret_cast<T *>(myQ + vt1[v * 3 + t].x) = pv;
+                        *reinterpret_cast<T *>(myQ + ea.x) = pv;
+                        *reinterpret_cast<T *>(myQ + ea.y) = pv;
+                        *reinterpret_cast<T *>(myQ + ea.z) = pv;
                     }
                     iter = 0;
                     active = true;
@@ -203,7 +221,7 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
             __syncwarp(amask);
 
             // ================= vertical step: lane j owns variables v = TL*i + j ==================
-            const uint2 *vt = (iter == 0) ? vt0 : vt1;
+            const uint4 *vt = (iter == 0) ? vt0 : vt1;
             const bool last = (iter == max_iter - 1);
             const bool wr_llr = (P.llr != nullptr) && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && last));
             T *llr_out = wr_llr ? reinterpret_cast<T *>(P.llr) + (size_t)shot * n : nullptr;
@@ -214,17 +232,16 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                 const int cnt = min(VPW, (n - 32 * wv - j + TL - 1) / TL);       // variables of this lane in word wv
 #pragma unroll 2
                 for (int ii = 0; ii < cnt; ++ii) {
-                    const int b = TL * ii + j;
-                    const int v = 32 * wv + b;
-                    const uint2 *ent = vt + v * 3;
-                    uint2 e[3];
+                    const int p = 32 * wv + TL * ii + j;                           // position
+                    const uint4 ea = vt[2 * p], eb = vt[2 * p + 1];
+                    const uint32_t eq[3] = {ea.x, ea.y, ea.z}, em[3] = {eb.x, eb.y, eb.z};
+                    const int v = (int)ea.w;                                          // variable at this position (same word)
+                    const int b = v & 31;
                     T qo[3], r[3];
 #pragma unroll
-                    for (int t = 0; t < 3; ++t) e[t] = ent[t];
-#pragma unroll
                     for (int t = 0; t < 3; ++t) {
-                        const T q = *reinterpret_cast<const T *>(myQ + e[t].x);
-                        const sum_t s12 = *reinterpret_cast<const sum_t *>(myM + e[t].y);
+                        const T q = *reinterpret_cast<const T *>(myQ + eq[t]);
+                        const sum_t s12 = *reinterpret_cast<const sum_t *>(myM + em[t]);
                         const T s1 = s12.v[0];
                         if (VAR == VAR_MIN_SUM) {
                             const T s2 = s12.v[NS - 1];
@@ -242,7 +259,8 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                         }
                         qo[t] = q;
                     }
-                    const T val = N::add(N::add(N::add(r[0], r[1]), r[2]), prior[v]);            // values = R_sum + prior
+                    const T pr = (sizeof(T) == 4) ? (T)__uint_as_float(eb.w) : prior[v];
+                    const T val = N::add(N::add(N::add(r[0], r[1]), r[2]), pr);                  // values = R_sum + prior
                     const bool hd = val < (T)0;
                     hw |= (uint32_t)hd << b;
                     if (wr_llr) llr_out[v] = val;
@@ -260,7 +278,7 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                         } else {
                             qn = N::tanh_(N::mul(qn, (T)0.5));                                    // the slot holds tanh(Q/2)
                         }
-                        *reinterpret_cast<T *>(myQ + e[t].x) = qn;
+                        *reinterpret_cast<T *>(myQ + eq[t]) = qn;
                     }
                 }
                 // the TL lanes of the shot hold disjoint bits of this word

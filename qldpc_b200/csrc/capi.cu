@@ -71,7 +71,10 @@ struct qldpc_code {
     int num_sms = 0, smem_optin = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_var_ptr = nullptr;
     uint32_t *d_vtab0 = nullptr, *d_vtab1 = nullptr, *d_colmask = nullptr, *d_Lrows = nullptr, *d_Hrows = nullptr;
-    uint32_t *d_vell0 = nullptr, *d_vell1 = nullptr;   // (check | k << 16) per (variable, t < 3): T-lanes-per-shot kernel
+    // T-lanes-per-shot kernel tables: 4 words per position {e0, e1, e2, v}, e = check | k << 16.  [0]: identity positions
+    // (float64: the reference's addition order is kept as is), [1]/[2]: positions optimised for TL = 4 / 8 (float32)
+    uint32_t *d_vell0[3] = {nullptr, nullptr, nullptr}, *d_vell1[3] = {nullptr, nullptr, nullptr};
+    double tiled_conflict_cost[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // modelled wavefronts per shot-iteration: before / after
     bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;
@@ -163,14 +166,104 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
     int min_col_w = n > 0 ? 1 << 30 : 0;
     for (int v = 0; v < n; ++v) min_col_w = std::min(min_col_w, var_ptr[v + 1] - var_ptr[v]);
     c->tiled_ok = (c->uniform_row_w == 6) && (c->max_col_w == 3) && (min_col_w == 3) && (m < 65536) && (c->WM == 2 || c->WM == 3 || c->WM == 5);
-    std::vector<uint32_t> vell0((size_t)n * 3, 0xffffffffu), vell1((size_t)n * 3, 0xffffffffu);
+    std::vector<uint32_t> vell0[3], vell1[3];
     if (c->tiled_ok) {
-        for (int v = 0; v < n; ++v)
-            for (int a = var_ptr[v], t = 0; a < var_ptr[v + 1]; ++a, ++t) {
-                const int e0 = var_edge0[a], e1 = var_edge1[a];
-                vell0[(size_t)v * 3 + t] = (uint32_t)edge_check[e0] | ((uint32_t)(e0 - row_ptr[edge_check[e0]]) << 16);
-                vell1[(size_t)v * 3 + t] = (uint32_t)edge_check[e1] | ((uint32_t)(e1 - row_ptr[edge_check[e1]]) << 16);
+        // entry of the t-th added edge of variable v in table `ve`
+        auto entry = [&](const int32_t *ve, int v, int t) {
+            const int e = ve[var_ptr[v] + t];
+            return (uint32_t)edge_check[e] | ((uint32_t)(e - row_ptr[edge_check[e]]) << 16);
+        };
+        // shared-memory wavefronts of one warp-wide access by TL lane groups to rows r[j] with `es`-byte elements
+        // (S = G mod 32 slots per row, G = 32/TL consecutive slots per group; 64-bit accesses go by half-warps)
+        auto wavefronts = [&](const int *r, int TL, int es) {
+            const int Gs = 32 / TL, wpe = es / 4;
+            int total = 0;
+            const int halves = (es == 8) ? 2 : 1;
+            for (int h = 0; h < halves; ++h) {
+                int cnt[32] = {0};
+                int mx = 0;
+                const int j0 = h * TL / halves, j1 = (h + 1) * TL / halves;
+                for (int jj = j0; jj < j1; ++jj)
+                    for (int gg = 0; gg < Gs; ++gg)
+                        for (int wv = 0; wv < wpe; ++wv) {
+                            const int bank = (((r[jj] * Gs + gg) * wpe) + wv) & 31;
+                            mx = std::max(mx, ++cnt[bank]);
+                        }
+                total += mx;
             }
+            return total;
+        };
+        for (int ti = 0; ti < 3; ++ti) {
+            const int TL = ti == 0 ? 8 : (ti == 1 ? 4 : 8);
+            std::vector<int> pos2var(n);
+            std::vector<uint8_t> sw0(n, 0), sw1(n, 0);
+            for (int v = 0; v < n; ++v) pos2var[v] = v;
+            // cost of the steps of one 32-variable word: message rows (load + store, 4-byte) and summary rows (8-byte)
+            auto step_cost = [&](const int32_t *ve, const std::vector<uint8_t> &sw, int p0, int cntp) {
+                double cost = 0;
+                for (int t = 0; t < 3; ++t) {
+                    int rq[8], rm[8];
+                    for (int jj = 0; jj < TL; ++jj) {
+                        if (jj < cntp) {
+                            const int v = pos2var[p0 + jj];
+                            const int tt = (t < 2 && sw[v]) ? 1 - t : t;
+                            const uint32_t e = entry(ve, v, tt);
+                            rq[jj] = (int)((e >> 16) * m + (e & 0xffffu));
+                            rm[jj] = (int)(e & 0xffffu);
+                        } else { rq[jj] = -1000 - jj * 977; rm[jj] = -1000 - jj * 977; }
+                    }
+                    cost += 2.0 * wavefronts(rq, TL, 4) + wavefronts(rm, TL, 8);
+                }
+                return cost;
+            };
+            auto total_cost = [&]() {
+                double cst = 0;
+                for (int p0 = 0; p0 < n; p0 += TL) cst += step_cost(var_edge1, sw1, p0, std::min(TL, n - p0));
+                return cst;
+            };
+            c->tiled_conflict_cost[ti][0] = total_cost();
+            if (ti > 0) {
+                // local search inside each 32-variable word: swap two positions / toggle the order of the two first-added
+                // edges of a variable ((x + y) + z == (y + x) + z, so float results do not change)
+                for (int w0 = 0; w0 < n; w0 += 32) {
+                    const int w1 = std::min(n, w0 + 32);
+                    auto word_cost = [&]() {
+                        double cst = 0;
+                        for (int p0 = w0; p0 < w1; p0 += TL) cst += step_cost(var_edge1, sw1, p0, std::min(TL, w1 - p0));
+                        return cst;
+                    };
+                    double best = word_cost();
+                    for (int pass = 0; pass < 8; ++pass) {
+                        bool improved = false;
+                        for (int a = w0; a < w1; ++a) {
+                            const int va = pos2var[a];
+                            sw1[va] ^= 1;
+                            double cst = word_cost();
+                            if (cst < best) { best = cst; improved = true; } else sw1[va] ^= 1;
+                            for (int b = a + 1; b < w1; ++b) {
+                                if (a / TL == b / TL) continue;
+                                std::swap(pos2var[a], pos2var[b]);
+                                cst = word_cost();
+                                if (cst < best) { best = cst; improved = true; } else std::swap(pos2var[a], pos2var[b]);
+                            }
+                        }
+                        if (!improved) break;
+                    }
+                }
+                sw0 = sw1;      // iteration-0 table: same positions, same swaps (only used with non-uniform priors)
+            }
+            c->tiled_conflict_cost[ti][1] = total_cost();
+            vell0[ti].assign((size_t)n * 4, 0u);
+            vell1[ti].assign((size_t)n * 4, 0u);
+            for (int p = 0; p < n; ++p) {
+                const int v = pos2var[p];
+                for (int t = 0; t < 3; ++t) {
+                    vell0[ti][(size_t)p * 4 + t] = entry(var_edge0, v, (t < 2 && sw0[v]) ? 1 - t : t);
+                    vell1[ti][(size_t)p * 4 + t] = entry(var_edge1, v, (t < 2 && sw1[v]) ? 1 - t : t);
+                }
+                vell0[ti][(size_t)p * 4 + 3] = vell1[ti][(size_t)p * 4 + 3] = (uint32_t)v;
+            }
+        }
     }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
     for (int r = 0; r < k; ++r)
@@ -202,8 +295,10 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
     CK(upload(&c->d_colmask, colmask));
     CK(upload(&c->d_Lrows, Lrows));
     CK(upload(&c->d_Hrows, Hrows));
-    CK(upload(&c->d_vell0, vell0));
-    CK(upload(&c->d_vell1, vell1));
+    for (int ti = 0; ti < 3; ++ti) {
+        CK(upload(&c->d_vell0[ti], vell0[ti]));
+        CK(upload(&c->d_vell1[ti], vell1[ti]));
+    }
     CK(c->ctrl.reserve(sizeof(Ctrl)));
     *out = c;
     return QLDPC_OK;
@@ -214,7 +309,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     if (!c) return;
     cudaFree(c->d_row_ptr); cudaFree(c->d_col_idx); cudaFree(c->d_var_ptr);
     cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
-    cudaFree(c->d_vell0); cudaFree(c->d_vell1);
+    for (int ti = 0; ti < 3; ++ti) { cudaFree(c->d_vell0[ti]); cudaFree(c->d_vell1[ti]); }
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
                       &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
@@ -315,6 +410,15 @@ extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int3
     return QLDPC_OK;
 }
 
+extern "C" int qldpc_tiled_conflict_model(qldpc_code *c, int32_t lanes_per_shot, double *before, double *after)
+{
+    if (!c || !c->tiled_ok) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_tiled_conflict_model: the tiled kernel does not apply to this code");
+    const int ti = lanes_per_shot == 4 ? 1 : 2;
+    if (before) *before = c->tiled_conflict_cost[ti][0];
+    if (after) *after = c->tiled_conflict_cost[ti][1];
+    return QLDPC_OK;
+}
+
 static int check_cfg(const qldpc_bp_config *cfg)
 {
     if (!cfg) return fail(QLDPC_ERR_ARG, "null BP config");
@@ -359,7 +463,8 @@ static cudaError_t launch_bp_tiled_inst(const qldpc_code *c, const BPParams &P, 
     auto kern = bp_tiled_kernel<T, VAR, TL, WMS, 6>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
     if (e != cudaSuccess) return e;
-    kern<<<G.grid, G.threads, G.smem, st>>>(P, c->d_vell0, c->d_vell1, G.refill_min);
+    const int ti = (sizeof(T) == 8) ? 0 : (TL == 4 ? 1 : 2);     // float64 keeps identity positions
+    kern<<<G.grid, G.threads, G.smem, st>>>(P, c->d_vell0[ti], c->d_vell1[ti], G.refill_min);
     return cudaGetLastError();
 }
 

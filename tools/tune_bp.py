@@ -31,6 +31,10 @@ st = torch.cuda.current_stream().cuda_stream
 _lib.check(L.qldpc_sample_dev(code.handle, args.p, 0, 0, 1, B, err.data_ptr(), synd.data_ptr(), st))
 prior = np.full(n, np.log((1 - args.p) / args.p))
 ref = None
+try:
+    print('conflict model (wavefronts per warp-iteration of the variable pass) T=4:', code.tiled_conflict_model(4), 'T=8:', code.tiled_conflict_model(8))
+except Exception as ex:
+    print('no conflict model:', ex)
 for spec in args.configs.split(","):
     staged, T, rmin = (int(x) for x in spec.split(":"))
     cfg = Code.config("min_sum", args.max_iter, 0.8, 0.7, 25.0, 32, staged, T, rmin)

@@ -104,7 +104,7 @@ def run_reference(args, rank):
     prior = np.full(n, np.log((1 - P_ERR) / P_ERR))
     rng = np.random.default_rng(SEED)
     vals, sample = [], 0
-    S = 40000
+    S = 2_000_000
     err = (rng.random((S, n)) < P_ERR).astype(np.uint8)
     synd = ((err.astype(np.int64) @ H.T) % 2).astype(np.uint8)
     for i in range(args.warmup + args.steps):

@@ -117,6 +117,29 @@ def test_sum_product_f64_vs_reference_golden(bp_golden, ci):
     np.testing.assert_allclose(llr[early], d[key + "_sym_llr"][early], rtol=1e-4)
 
 
+def test_sum_product_f32_accuracy_is_measured_not_assumed(bp_golden):
+    """float32 sum-product (fast variant): SURVEY.md H4 predicts it cannot meet 1e-4 relative everywhere (the check-node
+    clip 0.9999999 is not representable); it must still agree on hard decisions for early-converging shots and its LLR
+    error is printed, bounded loosely.  The float64 kernels are the ones held to the 1e-4 bar."""
+    d, meta = bp_golden
+    worst = 0.0
+    for case in meta["cases"]:
+        key = case["key"]
+        H, _ = load_code_file(case["code"], case["layout"])
+        synd = _synd(H, d[key + "_errors"])
+        prior = _prior(case["p"], H.shape[1])
+        code = _code(H, "sum_product")
+        hard, conv, llr, iters = code.bp_decode_batch(synd, prior, "sum_product", case["max_iter"], precision=32)
+        early = d[key + "_sp_conv"] & (d[key + "_sp_iter"] <= 10)
+        agree = (hard[early] == d[key + "_sp_hard"][early]).all(1).mean()
+        assert agree >= 0.9
+        same = early & conv & (iters == d[key + "_sp_iter"])
+        rel = np.abs(llr[same] - d[key + "_sp_llr"][same]) / np.maximum(1e-3, np.abs(d[key + "_sp_llr"][same]))
+        worst = max(worst, float(rel.max()))
+    print(f"\n[f32 sum-product] worst relative LLR error on shots converging at the reference's iteration: {worst:.2e}")
+    assert worst < 0.05
+
+
 def test_non_uniform_prior_and_loop_version(bp_golden):
     d, meta = bp_golden
     H, _ = load_code_file("[[72, 12, 6]]")

@@ -139,6 +139,10 @@ int qldpc_check_host(qldpc_code *code, int64_t B, const uint8_t *err, const uint
                      const uint8_t *synd, const uint8_t *conv, const int32_t *iters,
                      int32_t distance, uint8_t *flags, int32_t *weight, uint64_t *counters);
 
+/* syndromes of given errors, synd = err * H^T mod 2 (paperResults.py:65, beliefPropagationGPU.py:198):
+ * err [B][n] uint8 -> synd [B][m] uint8 */
+int qldpc_syndrome_host(qldpc_code *code, int64_t B, const uint8_t *err, uint8_t *synd);
+
 /* generate_errors_and_syndromes_batch (beliefPropagationGPU.py:181) on the device: Philox4x32-10
  * keyed by (seed, first_shot + i).  err [B][n] uint8, synd [B][m] uint8.  draws = 2 XORs two
  * independent draws (paperResults.py:61-63). */
@@ -176,6 +180,8 @@ int qldpc_osd_decode_dev(qldpc_code *code, const int32_t *idx, const uint32_t *c
 int qldpc_check_dev(qldpc_code *code, int64_t B, const uint32_t *err, const uint32_t *corr,
                     const uint32_t *synd, const uint8_t *conv, const int32_t *iters, int32_t distance,
                     uint8_t *flags, int32_t *weight, uint64_t *counters_dev, void *stream);
+
+int qldpc_syndrome_dev(qldpc_code *code, int64_t B, const uint32_t *err, uint32_t *synd, void *stream);
 
 int qldpc_sample_dev(qldpc_code *code, double p, uint64_t seed, uint64_t first_shot, int32_t draws,
                      int64_t B, uint32_t *err, uint32_t *synd, void *stream);

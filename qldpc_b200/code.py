@@ -195,6 +195,16 @@ class Code:
         return dict(logical=(flags & 1).astype(bool), valid=(flags & 2).astype(bool), degenerate=(flags & 4).astype(bool),
                     weight=weight, counters=dict(zip(_lib.COUNTER_NAMES, (int(x) for x in counters))))
 
+    def syndromes(self, errors):
+        """synd = errors @ H.T % 2 on the device.  errors (B, n) 0/1 -> int8 (B, m)."""
+        err = _bits(errors)
+        if err.ndim != 2 or err.shape[1] != self.n:
+            raise ValueError("errors must be (B, n)")
+        syn = np.zeros((err.shape[0], self.m), np.uint8)
+        if err.shape[0]:
+            _lib.check(_lib.lib().qldpc_syndrome_host(self._h, err.shape[0], _vp(err), _vp(syn)), "qldpc_syndrome_host")
+        return syn.view(np.int8)
+
     def sample(self, p, B, seed=0, first_shot=0, draws=1):
         """Device Philox sampler -> (errors int8 (B,n), syndromes int8 (B,m))."""
         err = np.zeros((B, self.n), np.uint8)

@@ -112,6 +112,22 @@ __device__ __forceinline__ float bp_damp(float d, float qn, float omd, float qo)
 __device__ __forceinline__ double bp_canon(double q) { return __dadd_rn(q, 0.0); }
 __device__ __forceinline__ float bp_canon(float q) { return q; }
 
+// Check-to-variable message of sum-product from the leave-one-out product x:  2 * atanh(clip(x, +-0.9999999))
+// (beliefPropagation.py:125-126).  0.9999999 is not a float32 number (it rounds to 1 - 2^-23, which would move the
+// saturation value from 16.81 to 16.64), so the float32 kernels clip x to the largest float below 1 and clamp the
+// result to the reference's saturation value 2 * atanh(0.9999999) instead.
+__device__ __forceinline__ double bp_sp_r(double x)
+{
+    x = fmin(fmax(x, -0.9999999), 0.9999999);
+    return __dmul_rn(2.0, atanh(x));
+}
+__device__ __forceinline__ float bp_sp_r(float x)
+{
+    x = fminf(fmaxf(x, -0x1.fffffep-1f), 0x1.fffffep-1f);
+    const float r = __fmul_rn(2.f, atanhf(x));
+    return fminf(fmaxf(r, -16.811242831518264f), 16.811242831518264f);
+}
+
 // Shared-memory footprint, shared with the host (capi.cu) so both agree on the carve-up.
 struct BPSmemLayout {
     size_t off_rowptr, off_varptr, off_vtab0, off_vtab1, off_colmask, off_prior, off_state;
@@ -214,7 +230,6 @@ bp_decode_kernel(const BPParams P)
     const T alpha = (T)P.alpha, damp = (T)P.damping, omd = (T)P.one_minus_damping, clipv = (T)P.clip;
     const int max_iter = P.max_iter;
     const bool slot_is_tanh = (VAR == VAR_SUM_PRODUCT) && !P.sym;
-    const T CLIP_VAL = (T)0.9999999;
     const int rw = g.uniform_row_w;
 
     constexpr int WREG = (WMS > 0) ? WMS : 1;
@@ -370,9 +385,7 @@ bp_decode_kernel(const BPParams P)
                             } else {
                                 T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
                                 const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;     // beliefPropagation.py:122
-                                T x = N::div(s1, ts);
-                                x = fmin(fmax(x, -CLIP_VAL), CLIP_VAL);              // :125
-                                rr = N::mul((T)2, N::atanh_(x));                     // :126
+                                rr = bp_sp_r(N::div(s1, ts));                        // :125-126
                                 if (dumping) rdump[ec.x] = rr;                       // R before scaling (decoding.py:169)
                                 if (P.sym) rr = N::mul(rr, alpha);                   // decoding.py:171
                             }
@@ -422,9 +435,7 @@ bp_decode_kernel(const BPParams P)
                         } else {
                             T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
                             const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;
-                            T x = N::div(s1, ts);
-                            x = fmin(fmax(x, -CLIP_VAL), CLIP_VAL);
-                            rr = N::mul((T)2, N::atanh_(x));
+                            rr = bp_sp_r(N::div(s1, ts));
                             if (dumping) rdump[ec.x] = rr;
                             if (P.sym) rr = N::mul(rr, alpha);
                         }

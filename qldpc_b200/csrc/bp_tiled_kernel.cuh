@@ -127,7 +127,6 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
     const int max_iter = P.max_iter;
     const bool sym = P.sym != 0;
     const bool slot_is_tanh = (VAR == VAR_SUM_PRODUCT) && !sym;
-    const T CLIP_VAL = (T)0.9999999;
 
     uint32_t synd[WMS], acc[WMS];
     long long shot = -1;
@@ -251,9 +250,7 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                         } else {
                             const T tq = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
                             const T ts = (fabs(tq) < (T)1e-15) ? (T)1e-15 : tq;                   // beliefPropagation.py:122
-                            T xx = N::div(s1, ts);
-                            xx = fmin(fmax(xx, -CLIP_VAL), CLIP_VAL);                            // :125
-                            T rr = N::mul((T)2, N::atanh_(xx));                                  // :126
+                            T rr = bp_sp_r(N::div(s1, ts));                                      // :125-126
                             if (sym) rr = N::mul(rr, alpha);                                     // decoding.py:171
                             r[t] = rr;
                         }

@@ -1044,6 +1044,36 @@ extern "C" int qldpc_check_host(qldpc_code *c, int64_t B, const uint8_t *err, co
     return QLDPC_OK;
 }
 
+extern "C" int qldpc_syndrome_dev(qldpc_code *c, int64_t B, const uint32_t *err, uint32_t *synd, void *stream)
+{
+    if (!c || !err || !synd) return fail(QLDPC_ERR_ARG, "qldpc_syndrome_dev: null argument");
+    if (B <= 0) return QLDPC_OK;
+    syndrome_kernel<<<grid_for(B * c->WM, 256, c->num_sms), 256, 0, (cudaStream_t)stream>>>(c->d_row_ptr, c->d_col_idx, c->m, c->WM, c->WN,
+                                                                                           B, err, synd);
+    CK(cudaGetLastError());
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_syndrome_host(qldpc_code *c, int64_t B, const uint8_t *err, uint8_t *synd)
+{
+    if (!c || !err || !synd) return fail(QLDPC_ERR_ARG, "qldpc_syndrome_host: null argument");
+    cudaStream_t st = 0;
+    const long long chunk = 1ll << 20;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        CK(cudaMemcpyAsync(c->ws_u8a.p, err + (size_t)o * c->n, (size_t)b * c->n, cudaMemcpyHostToDevice, st));
+        if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_err.as<uint32_t>(), b, c->n, st)) return rc;
+        if (int rc = qldpc_syndrome_dev(c, b, c->ws_err.as<uint32_t>(), c->ws_synd.as<uint32_t>(), st)) return rc;
+        if (int rc = qldpc_unpack_bits_dev(c->ws_synd.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->m, st)) return rc;
+        CK(cudaMemcpyAsync(synd + (size_t)o * c->m, c->ws_u8a.p, (size_t)b * c->m, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    return QLDPC_OK;
+}
+
 extern "C" int qldpc_sample_host(qldpc_code *c, double p, uint64_t seed, uint64_t first_shot, int32_t draws, int64_t B,
                                  uint8_t *err, uint8_t *synd)
 {

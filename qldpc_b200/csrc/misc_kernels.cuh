@@ -110,6 +110,31 @@ __global__ void sample_kernel(const SampleParams P)
     for (int k = 0; k < WM; ++k) P.synd[(size_t)t * WM + k] = sy[k];
 }
 
+// ---- syndromes of given errors: synd = err * H^T mod 2 (paperResults.py:65, beliefPropagationGPU.py:198) -------
+// One thread per (shot, 32-check word): parity of the packed error bits over the columns of each row (CSR of H).
+__global__ void syndrome_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int m, int WM, int WN,
+                                long long B, const uint32_t *__restrict__ err, uint32_t *__restrict__ synd)
+{
+    const long long total = B * WM;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long s = t / WM;
+        const int w = (int)(t - s * WM);
+        const uint32_t *e = err + (size_t)s * WN;
+        uint32_t out = 0;
+        const int hi = min(32, m - 32 * w);
+        for (int b = 0; b < hi; ++b) {
+            const int c = 32 * w + b;
+            uint32_t par = 0;
+            for (int a = row_ptr[c]; a < row_ptr[c + 1]; ++a) {
+                const int v = col_idx[a];
+                par ^= e[v >> 5] >> (v & 31);
+            }
+            out |= (par & 1u) << b;
+        }
+        synd[t] = out;
+    }
+}
+
 // ---- checks + counters ------------------------------------------------------------------------
 enum {
     CNT_SHOTS = 0,        // shots counted

@@ -39,6 +39,5 @@ def generate_errors_and_syndromes_batch(H, error_rate, batch_size, rng=None):
         seed = int(np.random.SeedSequence().generate_state(2, np.uint32).view(np.uint64)[0])
         return code.sample(error_rate, batch_size, seed=seed)
     num_checks, num_vars = Hd.shape
-    errors = (rng.random((batch_size, num_vars)) < error_rate).astype(np.int8)
-    syndromes = (errors.astype(np.int64) @ (Hd != 0).astype(np.int64).T) % 2
-    return errors, syndromes.astype(np.int8)
+    errors = (rng.random((batch_size, num_vars)) < error_rate).astype(np.int8)       # the reference's draws (:195)
+    return errors, cached_code(Hd, "sum_product").syndromes(errors)                  # err * H^T mod 2 on the device (:198)

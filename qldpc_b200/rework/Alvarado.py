@@ -16,7 +16,7 @@ def estimate_alpha_from_code(code, trials=5000, error_rate=0.05, maxIter=50, bin
     handle = cached_code(H, "min_sum")
     prior = np.full(n, np.log((1 - error_rate) / error_rate))
     errors = np.array([(np.random.random(n) < error_rate) for _ in range(trials)], dtype=np.uint8)
-    synd = ((errors.astype(np.int64) @ (H != 0).astype(np.int64).T) % 2).astype(np.uint8)
+    synd = handle.syndromes(errors)
     edge_rows, edge_cols = np.nonzero(H)
     true_0, true_1 = [], []
     step = 4096

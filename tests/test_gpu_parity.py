@@ -468,6 +468,23 @@ def _philox_numpy(sid, blk, stream, seed):
     return c
 
 
+def test_syndrome_kernel_and_all_kernels_smoke():
+    rng = np.random.default_rng(8)
+    for stem in ("steane", "[[90, 8, 10]]", "[[288, 12, 18]]"):
+        H, _ = load_code_file(stem)
+        code = _code(H, "min_sum")
+        err = (rng.random((1000, H.shape[1])) < 0.1).astype(np.uint8)
+        assert np.array_equal(code.syndromes(err).astype(np.uint8), _synd(H, err))
+    from qldpc_b200.spaceTime import spaceTimeMatrix
+    Hst = spaceTimeMatrix(load_code_file("[[72, 12, 6]]")[0], 4)
+    err = (rng.random((300, Hst.shape[1])) < 0.05).astype(np.uint8)
+    assert np.array_equal(_code(Hst, "min_sum").syndromes(err).astype(np.uint8), _synd(Hst, err))
+    import runpy
+    from conftest import ROOT
+    import os
+    runpy.run_path(os.path.join(ROOT, "tools", "sanitize_smoke.py"), run_name="__main__")    # every kernel, small batches
+
+
 def test_sampler_is_philox_keyed_by_global_shot_id():
     H, _ = load_code_file("[[144, 12, 12]]")
     code = _code(H, "min_sum")

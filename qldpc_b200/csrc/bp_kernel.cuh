@@ -69,7 +69,7 @@ struct BPParams {
     int32_t *fail_idx;          // compacted list of BP-failed shots (may be null)
     unsigned int *fail_count;
     unsigned long long *iter_total; // sum over shots of executed iterations (may be null)
-    void *gstate;               // STATE_SMEM = false: [(E + 2m) T + WN + WM words][total threads]
+    void *gstate;               // STATE_SMEM = false: [(2E + 2m) T + WN + WM words][total threads]
     void *r_dump;               // [B][E] T or null: check-to-variable messages of iteration `dump_iter` (CSR edge order),
     int dump_iter;              //   the alpha_estimation=True return of the reference (decoding.py:58-59,168-169)
 };
@@ -182,7 +182,10 @@ bp_decode_kernel(const BPParams P)
     const T *prior;
     // ---- state (stride S words between consecutive edges of one shot) ---------------------
     // (__restrict__: the arrays are disjoint, so loads of the next check may be hoisted above the summary stores)
-    T *__restrict__ Q, *__restrict__ M1, *__restrict__ M2;
+    // HBM-staged mode ping-pongs between two message arrays (Q is only read, QW only written during an iteration), so that
+    // the loads of the next variable can be issued before the stores of the current one retire: memory-level parallelism
+    T *Q, *QW;
+    T *__restrict__ M1, *__restrict__ M2;
     uint32_t *__restrict__ HW, *__restrict__ SY = nullptr;
     int S;
 
@@ -208,6 +211,7 @@ bp_decode_kernel(const BPParams P)
         S = blockDim.x;
         T *st = reinterpret_cast<T *>(smem + L.off_state);
         Q = st + threadIdx.x;
+        QW = Q;
         M1 = Q + (idx_t)E * S;
         M2 = M1 + (idx_t)m * S;
         HW = reinterpret_cast<uint32_t *>(st + (idx_t)(E + (VAR == VAR_MIN_SUM ? 2 : 1) * m) * S) + threadIdx.x;
@@ -221,9 +225,10 @@ bp_decode_kernel(const BPParams P)
         const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
         T *st = reinterpret_cast<T *>(P.gstate);
         Q = st + gt;
-        M1 = Q + (idx_t)E * S;
+        QW = Q + (idx_t)E * S;
+        M1 = QW + (idx_t)E * S;
         M2 = M1 + (idx_t)m * S;
-        HW = reinterpret_cast<uint32_t *>(st + (idx_t)(E + 2 * m) * S) + gt;
+        HW = reinterpret_cast<uint32_t *>(st + (idx_t)(2 * E + 2 * m) * S) + gt;
         SY = HW + (idx_t)WN * S;
     }
 
@@ -348,6 +353,12 @@ bp_decode_kernel(const BPParams P)
         // ================= vertical step ===================================================
         const uint2 *vt = (iter == 0) ? vtab0 : vtab1;
         const bool last = (iter == max_iter - 1);
+        // read side / write side of this iteration: distinct arrays (hence __restrict__) when staged in HBM; the same array
+        // in shared memory, where each edge is read before it is written, by the same thread
+        typedef typename std::conditional<STATE_SMEM, const T *, const T *__restrict__>::type qr_t;
+        typedef typename std::conditional<STATE_SMEM, T *, T *__restrict__>::type qw_t;
+        qr_t qr = Q;
+        qw_t qw = QW;
         const bool wr_llr = (P.llr != nullptr) && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && last));
         T *llr_out = wr_llr ? reinterpret_cast<T *>(P.llr) + (size_t)shot * n : nullptr;
         const bool dumping = (P.r_dump != nullptr) && (iter == P.dump_iter);
@@ -359,6 +370,7 @@ bp_decode_kernel(const BPParams P)
         for (int wv = 0; wv * 32 < n; ++wv) {
             uint32_t hw = 0;
             const int vend = min(32, n - 32 * wv);
+#pragma unroll 2
             for (int b = 0; b < vend; ++b) {
                 const int v = 32 * wv + b;
                 const int a0 = var_ptr[v];
@@ -372,7 +384,7 @@ bp_decode_kernel(const BPParams P)
                     for (int k = 0; k < 4; ++k) {
                         if (k0 + k < deg) {
                             const uint2 ec = vt[a0 + k0 + k];
-                            const T q = Q[(idx_t)ec.x * S];
+                            const T q = qr[(idx_t)ec.x * S];
                             const T s1 = M1[(idx_t)ec.y * S];
                             T rr;
                             if (VAR == VAR_MIN_SUM) {
@@ -416,14 +428,14 @@ bp_decode_kernel(const BPParams P)
                         } else if (slot_is_tanh) {
                             qn = N::tanh_(N::mul(qn, (T)0.5));
                         }
-                        Q[(idx_t)eo[k] * S] = qn;
+                        qw[(idx_t)eo[k] * S] = qn;
                     }
                 }
                 if (deg > 4) {
                     // generic tail (column weight > 4): recompute the message of each remaining edge
                     for (int k = 4; k < deg; ++k) {
                         const uint2 ec = vt[a0 + k];
-                        const T q = Q[(idx_t)ec.x * S];
+                        const T q = qr[(idx_t)ec.x * S];
                         const T s1 = M1[(idx_t)ec.y * S];
                         T rr;
                         if (VAR == VAR_MIN_SUM) {
@@ -447,7 +459,7 @@ bp_decode_kernel(const BPParams P)
                         } else if (slot_is_tanh) {
                             qn = N::tanh_(N::mul(qn, (T)0.5));
                         }
-                        Q[(idx_t)ec.x * S] = qn;
+                        qw[(idx_t)ec.x * S] = qn;
                     }
                 }
             }
@@ -489,6 +501,7 @@ bp_decode_kernel(const BPParams P)
             active = false;
         } else {
             ++iter;
+            if (!STATE_SMEM) { T *t_ = Q; Q = QW; QW = t_; }      // ping-pong
         }
         }  // if (active)
     }

@@ -128,6 +128,12 @@ __device__ __forceinline__ float bp_sp_r(float x)
     return fminf(fmaxf(r, -16.811242831518264f), 16.811242831518264f);
 }
 
+// Message-state accesses.  (Measured on B200: evict-first hints -- ld/st.global.cs -- on the HBM-staged state make the
+// kernel 10 % slower, because the per-check summaries written by the check pass are re-read from L2 by the variable
+// pass; default caching is kept.)
+template <bool SMEM, typename U> __device__ __forceinline__ U ld_state(const U *p) { return *p; }
+template <bool SMEM, typename U> __device__ __forceinline__ void st_state(U *p, U v) { *p = v; }
+
 // Shared-memory footprint, shared with the host (capi.cu) so both agree on the carve-up.
 struct BPSmemLayout {
     size_t off_rowptr, off_varptr, off_vtab0, off_vtab1, off_colmask, off_prior, off_state;
@@ -301,7 +307,7 @@ bp_decode_kernel(const BPParams P)
                         const T *q = Q + (idx_t)(6 * c) * S;
                         T x[6];
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) x[k] = q[(idx_t)k * S];
+                        for (int k = 0; k < 6; ++k) x[k] = ld_state<STATE_SMEM>(q + (idx_t)k * S);
 #pragma unroll
                         for (int k = 0; k < 6; ++k) {
                             sg ^= N::bits(x[k]);
@@ -316,7 +322,7 @@ bp_decode_kernel(const BPParams P)
                         const int e0 = row_ptr[c], deg = row_ptr[c + 1] - e0;
                         T x[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) x[k] = (k < deg) ? Q[(idx_t)(e0 + k) * S] : N::inf();
+                        for (int k = 0; k < 8; ++k) x[k] = (k < deg) ? ld_state<STATE_SMEM>(Q + (idx_t)(e0 + k) * S) : N::inf();
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             sg ^= N::bits(x[k]);
@@ -334,8 +340,8 @@ bp_decode_kernel(const BPParams P)
                             min2 = fmin(min2, t);
                         }
                     }
-                    M1[(idx_t)c * S] = N::from_bits(N::bits(min1) | (sg & N::SIGN)); // signed min1
-                    M2[(idx_t)c * S] = min2;
+                    st_state<STATE_SMEM>(M1 + (idx_t)c * S, N::from_bits(N::bits(min1) | (sg & N::SIGN))); // signed min1
+                    st_state<STATE_SMEM>(M2 + (idx_t)c * S, min2);
                 } else {
                     // beliefPropagation.py:114-118: row product of tanh(Q/2), ascending column order
                     T prod = (T)1;
@@ -375,36 +381,63 @@ bp_decode_kernel(const BPParams P)
                 const int v = 32 * wv + b;
                 const int a0 = var_ptr[v];
                 const int deg = var_ptr[v + 1] - a0;
-                T r[4], qo[4];
-                uint32_t eo[4];
+                // The first KB = 3 edges are handled branch-free: table entries and messages are loaded for a clamped edge
+                // index (a valid address even when deg < 3) and masked afterwards, so that all loads of a variable are in
+                // flight together -- essential when the state is staged in HBM.  Further edges go through the tail loop.
+                constexpr int KB = 3;
+                T r[KB], qo[KB];
+                uint32_t eo[KB];
                 T sum = (T)0;
-                // check-to-variable messages of v, in the reference's addition order
-                for (int k0 = 0; k0 < deg; k0 += 4) {
+                {
+                    uint2 ecs[KB];
+                    T qs[KB], s1s[KB], s2s[KB];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        if (k0 + k < deg) {
-                            const uint2 ec = vt[a0 + k0 + k];
-                            const T q = qr[(idx_t)ec.x * S];
-                            const T s1 = M1[(idx_t)ec.y * S];
-                            T rr;
-                            if (VAR == VAR_MIN_SUM) {
-                                const T s2 = M2[(idx_t)ec.y * S];
-                                const T a1 = fabs(s1);
-                                const T mag = (fabs(q) == a1) ? s2 : a1;             // decoding.py:51-53
-                                // R = alpha * syndrome_sign * r_signs * mag           (decoding.py:55)
-                                rr = N::from_bits(N::bits(N::mul(alpha, mag)) ^ ((N::bits(s1) ^ N::bits(q)) & N::SIGN));
-                                if (dumping) rdump[ec.x] = N::div(rr, alpha);        // R_new / alpha (decoding.py:59)
-                            } else {
-                                T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
-                                const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;     // beliefPropagation.py:122
-                                rr = bp_sp_r(N::div(s1, ts));                        // :125-126
-                                if (dumping) rdump[ec.x] = rr;                       // R before scaling (decoding.py:169)
-                                if (P.sym) rr = N::mul(rr, alpha);                   // decoding.py:171
-                            }
-                            sum = (k0 + k == 0) ? rr : N::add(sum, rr);
-                            if (k0 == 0) { r[k] = rr; qo[k] = q; eo[k] = ec.x; }
-                        }
+                    for (int k = 0; k < KB; ++k) ecs[k] = vt[min(a0 + min(k, max(deg - 1, 0)), E - 1)];
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) {
+                        qs[k] = ld_state<STATE_SMEM>(qr + (idx_t)ecs[k].x * S);
+                        s1s[k] = ld_state<STATE_SMEM>(M1 + (idx_t)ecs[k].y * S);
+                        s2s[k] = (VAR == VAR_MIN_SUM) ? ld_state<STATE_SMEM>(M2 + (idx_t)ecs[k].y * S) : (T)0;
                     }
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) {
+                        const T q = qs[k], s1 = s1s[k];
+                        T rr;
+                        if (VAR == VAR_MIN_SUM) {
+                            const T a1 = fabs(s1);
+                            const T mag = (fabs(q) == a1) ? s2s[k] : a1;                 // decoding.py:51-53
+                            // R = alpha * syndrome_sign * r_signs * mag                   (decoding.py:55)
+                            rr = N::from_bits(N::bits(N::mul(alpha, mag)) ^ ((N::bits(s1) ^ N::bits(q)) & N::SIGN));
+                            if (dumping && k < deg) rdump[ecs[k].x] = N::div(rr, alpha);  // R_new / alpha (decoding.py:59)
+                        } else {
+                            T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
+                            const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;             // beliefPropagation.py:122
+                            rr = bp_sp_r(N::div(s1, ts));                                // :125-126
+                            if (dumping && k < deg) rdump[ecs[k].x] = rr;                 // R before scaling (decoding.py:169)
+                            if (P.sym) rr = N::mul(rr, alpha);                           // decoding.py:171
+                        }
+                        if (k == 0) sum = (deg > 0) ? rr : (T)0;
+                        else if (k < deg) sum = N::add(sum, rr);
+                        r[k] = rr; qo[k] = q; eo[k] = ecs[k].x;
+                    }
+                }
+                for (int k = KB; k < deg; ++k) {                                       // column weight > 3: remaining messages
+                    const uint2 ec = vt[a0 + k];
+                    const T q = qr[(idx_t)ec.x * S];
+                    const T s1 = M1[(idx_t)ec.y * S];
+                    T rr;
+                    if (VAR == VAR_MIN_SUM) {
+                        const T s2 = M2[(idx_t)ec.y * S];
+                        const T a1 = fabs(s1);
+                        const T mag = (fabs(q) == a1) ? s2 : a1;
+                        rr = N::from_bits(N::bits(N::mul(alpha, mag)) ^ ((N::bits(s1) ^ N::bits(q)) & N::SIGN));
+                    } else {
+                        T t = slot_is_tanh ? q : N::tanh_(N::mul(q, (T)0.5));
+                        const T ts = (fabs(t) < (T)1e-15) ? (T)1e-15 : t;
+                        rr = bp_sp_r(N::div(s1, ts));
+                        if (P.sym) rr = N::mul(rr, alpha);
+                    }
+                    sum = N::add(sum, rr);
                 }
                 const T val = N::add(sum, prior[v]);                                 // values = R_sum + prior
                 const bool hd = val < (T)0;
@@ -418,7 +451,7 @@ bp_decode_kernel(const BPParams P)
                 }
                 // Q update: Q_new = values - R; damping against Q_old; clip  (decoding.py:63-66)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < KB; ++k) {
                     if (k < deg) {
                         T qn = N::sub(val, r[k]);
                         if (VAR == VAR_MIN_SUM || P.sym) {
@@ -428,12 +461,12 @@ bp_decode_kernel(const BPParams P)
                         } else if (slot_is_tanh) {
                             qn = N::tanh_(N::mul(qn, (T)0.5));
                         }
-                        qw[(idx_t)eo[k] * S] = qn;
+                        st_state<STATE_SMEM>(qw + (idx_t)eo[k] * S, qn);
                     }
                 }
-                if (deg > 4) {
-                    // generic tail (column weight > 4): recompute the message of each remaining edge
-                    for (int k = 4; k < deg; ++k) {
+                if (deg > KB) {
+                    // generic tail (column weight > 3): recompute the message of each remaining edge
+                    for (int k = KB; k < deg; ++k) {
                         const uint2 ec = vt[a0 + k];
                         const T q = qr[(idx_t)ec.x * S];
                         const T s1 = M1[(idx_t)ec.y * S];

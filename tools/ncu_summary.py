@@ -24,18 +24,20 @@ src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_ou
 rows = list(csv.reader(src.splitlines()))
 hdr, data = rows[1], rows[2:]
 isrc, ins, ismp, ithr = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Avg. Threads Executed")
-iwf, iwfi = hdr.index("L1 Wavefronts Shared"), hdr.index("L1 Wavefronts Shared Ideal")
+iwf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
+iwfi = hdr.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in hdr else None
 stall = [i for i, h in enumerate(hdr) if h.startswith("stall_") and "Not Issued" not in h]
 ti = sum(int(r[ins]) for r in data); ts = sum(int(r[ismp]) for r in data)
 print(f"\ntotal warp-instructions {ti}  samples {ts}")
 tot = {hdr[i]: sum(int(r[i]) for r in data) for i in stall}
 print("stall mix: " + ", ".join(f"{k[6:]} {100*v/ts:.1f}%" for k, v in sorted(tot.items(), key=lambda x: -x[1])[:8]))
-wf = sum(int(r[iwf]) for r in data); wfi = sum(int(r[iwfi]) for r in data)
-print(f"shared wavefronts {wf} ideal {wfi} (x{wf/max(1,wfi):.2f})")
+if iwf is not None:
+    wf = sum(int(r[iwf]) for r in data); wfi = sum(int(r[iwfi]) for r in data)
+    print(f"shared wavefronts {wf} ideal {wfi} (x{wf/max(1,wfi):.2f})")
 print(f"\ninstructions with >= {minpct}% of executed warp-instructions:")
 for idx, r in enumerate(data):
     n = int(r[ins])
     if n >= minpct / 100 * ti:
         top = sorted(((int(r[i]), hdr[i][6:]) for i in stall), reverse=True)[:2]
-        w = f"wf {r[iwf]}/{r[iwfi]}" if int(r[iwf]) else ""
+        w = f"wf {r[iwf]}/{r[iwfi]}" if (iwf is not None and int(r[iwf])) else ""
         print(f"{idx:5d} {r[isrc].strip()[:58]:58s} inst {100*n/ti:5.2f}% smp {100*int(r[ismp])/ts:5.2f}% thr {r[ithr]:>4s} {top[0][1]}:{top[0][0]} {top[1][1]}:{top[1][0]} {w}")

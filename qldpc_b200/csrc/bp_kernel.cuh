@@ -167,7 +167,7 @@ __host__ __device__ inline BPSmemLayout bp_smem_layout(const BPGraphDev &g, int 
 //          evaluated check by check after the variable pass.
 // ------------------------------------------------------------------------------------------
 template <typename T, int VAR, int WMS, bool STATE_SMEM>
-__global__ void __launch_bounds__(STATE_SMEM ? 256 : 128, STATE_SMEM ? 1 : 6)
+__global__ void __launch_bounds__(STATE_SMEM ? 256 : 128, STATE_SMEM ? 1 : 8)
 bp_decode_kernel(const BPParams P)
 {
     typedef Num<T> N;

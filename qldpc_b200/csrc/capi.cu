@@ -391,7 +391,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->threads = 128;
         G->shots_per_cta = 128;
         G->smem = 0;
-        G->grid = (int)std::max<long long>(1, std::min<long long>((B + 127) / 128, (long long)c->num_sms * 6));   // __launch_bounds__(128, 6)
+        G->grid = (int)std::max<long long>(1, std::min<long long>((B + 127) / 128, (long long)c->num_sms * 8));   // __launch_bounds__(128, 8)
         const size_t per_thread = (size_t)tsize * (2 * (size_t)c->E + 2 * (size_t)c->m) + 4 * (size_t)(c->WN + c->WM);
         G->gstate_bytes = per_thread * (size_t)G->grid * G->threads;
     }

@@ -699,7 +699,6 @@ extern "C" int qldpc_sample_dev(qldpc_code *c, double p, uint64_t seed, uint64_t
     if (!c || !err || !synd) return fail(QLDPC_ERR_ARG, "qldpc_sample_dev: null argument");
     if (!(p >= 0.0 && p < 1.0) || draws < 1 || draws > 2) return fail(QLDPC_ERR_ARG, "qldpc_sample_dev: need 0 <= p < 1 and draws in {1,2}");
     if (B <= 0) return QLDPC_OK;
-    if (c->WM > 5) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_sample_dev: more than 160 checks");
     SampleParams P;
     P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
     P.colmask = c->d_colmask;
@@ -714,7 +713,11 @@ extern "C" int qldpc_sample_dev(qldpc_code *c, double p, uint64_t seed, uint64_t
     case 2: launch_sample<2>(P, grid, st); break;
     case 3: launch_sample<3>(P, grid, st); break;
     case 4: launch_sample<4>(P, grid, st); break;
-    default: launch_sample<5>(P, grid, st); break;
+    case 5: launch_sample<5>(P, grid, st); break;
+    default:
+        launch_sample<0>(P, grid, st);                       // errors only ...
+        CK(cudaGetLastError());
+        return qldpc_syndrome_dev(c, B, err, synd, stream);  // ... syndromes from the CSR rows
     }
     CK(cudaGetLastError());
     return QLDPC_OK;
@@ -726,7 +729,6 @@ extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, co
 {
     if (!c || !err || !corr || !synd) return fail(QLDPC_ERR_ARG, "qldpc_check_dev: null argument");
     if (B <= 0) return QLDPC_OK;
-    if (c->WM > 5) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_check_dev: more than 160 checks");
     CheckParams P;
     P.m = c->m; P.n = c->n; P.k = c->k; P.WM = c->WM; P.WN = c->WN;
     P.colmask = c->d_colmask; P.Lrows = c->d_Lrows;
@@ -734,8 +736,17 @@ extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, co
     P.half_distance = distance / 2;
     P.counters = (unsigned long long *)counters_dev;
     P.flags = flags; P.weight = weight;
+    P.corr_synd = nullptr;
     const int grid = grid_for(B, 256, c->num_sms);
     cudaStream_t st = (cudaStream_t)stream;
+    if (c->WM > 5) {                                         // large H: syndrome of the correction from the CSR rows first
+        CK(c->ws_valid.reserve(4 * (size_t)B * c->WM));
+        if (int rc = qldpc_syndrome_dev(c, B, corr, c->ws_valid.as<uint32_t>(), stream)) return rc;
+        P.corr_synd = c->ws_valid.as<uint32_t>();
+        launch_check<0>(P, grid, st);
+        CK(cudaGetLastError());
+        return QLDPC_OK;
+    }
     switch (c->WM) {
     case 1: launch_check<1>(P, grid, st); break;
     case 2: launch_check<2>(P, grid, st); break;

@@ -70,6 +70,7 @@ struct SampleParams {
 };
 
 // One thread per shot.  Variable j uses word (j & 3) of Philox block (j >> 2) of stream `draw`.
+// WM == 0 (more than 160 checks): only the errors are produced here, the syndromes by syndrome_kernel.
 // The result depends only on (seed, global shot id), never on the launch shape or the rank.
 template <int WM>
 __global__ void sample_kernel(const SampleParams P)
@@ -78,9 +79,10 @@ __global__ void sample_kernel(const SampleParams P)
     if (t >= P.B) return;
     const unsigned long long sid = P.first_shot + (unsigned long long)t;
     const uint2 key = make_uint2((uint32_t)P.seed, (uint32_t)(P.seed >> 32));
-    uint32_t sy[WM];
+    constexpr int WR = WM > 0 ? WM : 1;
+    uint32_t sy[WR];
 #pragma unroll
-    for (int w = 0; w < WM; ++w) sy[w] = 0;
+    for (int w = 0; w < WR; ++w) sy[w] = 0;
     for (int w = 0; w < P.WN; ++w) {
         uint32_t bits = 0;
         const int hi = min(32, P.n - 32 * w);
@@ -97,17 +99,21 @@ __global__ void sample_kernel(const SampleParams P)
         }
         if (hi < 32) bits &= (1u << hi) - 1u;
         P.err[(size_t)t * P.WN + w] = bits;
-        uint32_t x = bits;
-        while (x) {
-            const int b = __ffs(x) - 1;
-            x &= x - 1;
-            const int v = 32 * w + b;
+        if (WM > 0) {
+            uint32_t x = bits;
+            while (x) {
+                const int b = __ffs(x) - 1;
+                x &= x - 1;
+                const int v = 32 * w + b;
 #pragma unroll
-            for (int k = 0; k < WM; ++k) sy[k] ^= P.colmask[v * WM + k];
+                for (int k = 0; k < WR; ++k) sy[k] ^= P.colmask[v * WR + k];
+            }
         }
     }
+    if (WM > 0) {
 #pragma unroll
-    for (int k = 0; k < WM; ++k) P.synd[(size_t)t * WM + k] = sy[k];
+        for (int k = 0; k < WR; ++k) P.synd[(size_t)t * WR + k] = sy[k];
+    }
 }
 
 // ---- syndromes of given errors: synd = err * H^T mod 2 (paperResults.py:65, beliefPropagationGPU.py:198) -------
@@ -167,6 +173,7 @@ struct CheckParams {
     unsigned long long *counters;// [CNT_NUM] (may be null)
     uint8_t *flags;              // [B] (may be null)
     int32_t *weight;             // [B] residual weight (may be null)
+    const uint32_t *corr_synd;   // [B][WM] syndrome of the correction, used by the WM == 0 instantiation (more than 160 checks)
 };
 
 template <int WM>
@@ -180,9 +187,10 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckParams P)
     for (int i = 0; i < 12; ++i) c[i] = 0;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < P.B; t += (long long)gridDim.x * blockDim.x) {
         const uint32_t *e = P.err + (size_t)t * P.WN, *x = P.corr + (size_t)t * P.WN;
-        uint32_t sy[WM];
+        constexpr int WR = WM > 0 ? WM : 1;
+        uint32_t sy[WR];
 #pragma unroll
-        for (int k = 0; k < WM; ++k) sy[k] = P.synd[(size_t)t * WM + k];
+        for (int k = 0; k < WR; ++k) sy[k] = (WM > 0) ? P.synd[(size_t)t * WR + k] : 0u;
         int wres = 0, werr = 0;
         bool differs = false;
         for (int w = 0; w < P.WN; ++w) {
@@ -190,18 +198,24 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckParams P)
             wres += __popc(ew ^ xw);
             werr += __popc(ew);
             differs |= (ew != xw);
-            uint32_t y = xw;                 // syndrome of the correction: XOR of the packed columns
-            while (y) {
-                const int b = __ffs(y) - 1;
-                y &= y - 1;
-                const int v = 32 * w + b;
+            if (WM > 0) {
+                uint32_t y = xw;             // syndrome of the correction: XOR of the packed columns
+                while (y) {
+                    const int b = __ffs(y) - 1;
+                    y &= y - 1;
+                    const int v = 32 * w + b;
 #pragma unroll
-                for (int k = 0; k < WM; ++k) sy[k] ^= P.colmask[v * WM + k];
+                    for (int k = 0; k < WR; ++k) sy[k] ^= P.colmask[v * WR + k];
+                }
             }
         }
         bool valid = true;
+        if (WM > 0) {
 #pragma unroll
-        for (int k = 0; k < WM; ++k) valid = valid && (sy[k] == 0);
+            for (int k = 0; k < WR; ++k) valid = valid && (sy[k] == 0);
+        } else {
+            for (int k = 0; k < P.WM; ++k) valid = valid && (P.corr_synd[(size_t)t * P.WM + k] == P.synd[(size_t)t * P.WM + k]);
+        }
         bool logical = false;
         for (int r = 0; r < P.k; ++r) {
             uint32_t par = 0;

@@ -630,3 +630,82 @@ def test_full_size_properties():
     code2 = _code(H2, "min_sum", d2["Lx"], int(d2["distance"]))
     c2 = code2.mc_sweep(0.04, 200_000, seed=5, variant="min_sum", max_iter=50, alpha=0.8, damping=0.7, clip=25.0, precision=32, osd_order=-1)
     assert c2["shots"] == 200_000 and c2["invalid"] == c2["bp_failed"]   # BP-only: exactly the failures are invalid
+
+
+# ----------------------------------------------------------------------------------------------
+# arbitrary sparse H (circuit-level-DEM-like input) and error behaviour
+# ----------------------------------------------------------------------------------------------
+def _random_sparse_h(rng, m, n, max_col_w):
+    H = np.zeros((m, n), np.uint8)
+    for v in range(n):
+        w = rng.integers(1, max_col_w + 1)
+        H[rng.choice(m, size=w, replace=False), v] = 1
+    return H
+
+
+@pytest.mark.parametrize("m,n,cw,staged", [(60, 200, 5, 0), (60, 200, 5, 1), (170, 400, 4, 0), (24, 40, 7, 0)])
+def test_arbitrary_sparse_h_nonuniform_priors_vs_oracle(m, n, cw, staged):
+    """A detector-error-model-shaped input as in studies/studyComplete.py:80-99: irregular sparse H (scipy.sparse accepted),
+    column weights up to 7, row weights well above 8, per-column priors from clipped probabilities (:88-89), an observables
+    matrix.  float64 min-sum / sum-product BP + OSD-0 must equal the oracle bit for bit / to tolerance."""
+    from scipy.sparse import csr_matrix
+    from qldpc_b200 import Code
+    rng = np.random.default_rng(m * 1000 + n)
+    H = _random_sparse_h(rng, m, n, cw)
+    probs = np.clip(rng.uniform(0.001, 0.08, n), 1e-15, 1 - 1e-15)
+    prior = np.log((1 - probs) / probs)
+    L = (rng.random((5, n)) < 0.1).astype(np.uint8)
+    B = 600
+    err = (rng.random((B, n)) < probs[None, :]).astype(np.uint8)
+    synd = _synd(H, err)
+    g = O.Graph(H)
+    code = Code(csr_matrix(H), L)
+    ref = O.decode_batch(g, synd, prior, O.MIN_SUM, 40, 0.8, 0.7, 25.0, osd_order=0, want_llr=True)
+    hard, conv, llr, iters = code.bp_decode_batch(synd, prior, "min_sum", 40, 0.8, 0.7, 25.0, precision=64, staged=staged)
+    assert np.array_equal(conv, ref["converged"]) and np.array_equal(iters, ref["iters"]) and np.array_equal(llr, ref["llr"])
+    corr, conv2, _ = code.bposd_decode_batch(synd, prior, "min_sum", 40, 0.8, 0.7, 25.0, precision=64, osd_order=0, staged=staged)
+    assert np.array_equal(corr, ref["corr"])
+    assert (~conv).sum() > 0
+    lg, va, wt = O.check_batch(g, L, err, corr, synd)
+    chk = code.check_batch(err, corr, synd, conv, iters)
+    if True:
+        assert np.array_equal(chk["logical"], lg) and np.array_equal(chk["valid"], va) and np.array_equal(chk["weight"], wt)
+    e2, s2 = code.sample(0.03, 500, seed=4)                     # device sampler on an arbitrary H (CSR syndromes when m > 160)
+    assert np.array_equal(s2.astype(np.uint8), _synd(H, e2.astype(np.uint8)))
+    cnt = code.mc_sweep(0.02, 2000, seed=1, variant="min_sum", max_iter=30, alpha=0.8, damping=0.7, clip=25.0, precision=32, osd_order=0)
+    assert cnt["shots"] == 2000 and cnt["invalid"] <= cnt["bp_failed"]
+    # sum-product on the same input: shots converging early agree to 1e-6
+    refsp = O.decode_batch(g, synd, prior, O.SUM_PRODUCT, 30, osd_order=-1, want_llr=True)
+    h2, c2, l2, i2 = code.bp_decode_batch(synd, prior, "sum_product", 30, precision=64, staged=staged)
+    early = refsp["converged"] & (refsp["iters"] <= 10)
+    assert early.sum() > B // 4
+    assert np.array_equal(c2[early], refsp["converged"][early]) and np.array_equal(i2[early], refsp["iters"][early])
+    np.testing.assert_allclose(l2[early], refsp["llr"][early], rtol=1e-6, atol=1e-9)
+
+
+def test_error_behaviour():
+    from qldpc_b200 import Code, QldpcError, _lib
+    import ctypes
+    H, _ = load_code_file("[[72, 12, 6]]")
+    code = _code(H, "min_sum")
+    prior = _prior(0.05, 72)
+    with pytest.raises(ValueError):
+        code.bp_decode_batch(np.zeros((4, 35), np.uint8), prior)                 # wrong number of checks
+    with pytest.raises(ValueError):
+        code.bp_decode_batch(np.zeros((4, 36), np.uint8), [1.0, 2.0])            # wrong prior length
+    with pytest.raises(ValueError):
+        code.osd_decode_batch(np.zeros((2, 36), np.uint8), np.zeros((2, 71)), np.zeros((2, 72), np.uint8))
+    with pytest.raises(KeyError):
+        code.bp_decode_batch(np.zeros((1, 36), np.uint8), prior, variant="nonsense")
+    with pytest.raises(QldpcError):
+        code.bp_decode_batch(np.zeros((1, 36), np.uint8), prior, max_iter=0)     # the C ABI validates its config
+    with pytest.raises(QldpcError):
+        code.bp_decode_batch(np.zeros((1, 36), np.uint8), prior, precision=16)
+    with pytest.raises(ValueError):
+        Code(np.zeros((3,)))                                                    # not a matrix
+    L = _lib.lib()
+    assert L.qldpc_code_create(0, 5, None, None, None, None, None, 0, None, ctypes.byref(ctypes.c_void_p())) != 0
+    assert b"bad argument" in L.qldpc_last_error()
+    # an all-zero prior (p = 0.5) and an all-ones syndrome are legal inputs
+    hard, conv, llr, it = code.bp_decode_batch(np.ones((3, 36), np.uint8), np.zeros(72), "min_sum", 5, precision=64)
+    assert hard.shape == (3, 72) and np.isfinite(llr).all()

@@ -631,7 +631,7 @@ static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_
     P.rank = c->rank;
     P.colmask = c->d_colmask;
     if (osd_use_block(c)) {
-        if (c->n > 65535) return fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65535 columns");
+        if (c->n > 65534 || c->m > 32767) return fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65534 columns or 32767 rows");
         if (P.rec_ordering) return fail(QLDPC_ERR_UNSUPPORTED, "OSD-w sweep (order > 0) is not available for check matrices with more than 160 rows");
         OSDBlockParams Q;
         Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank;

@@ -279,7 +279,8 @@ __host__ __device__ inline size_t osdb_smem_bytes(int m, int n)
 {
     const int WM = (m + 31) / 32, WN = (n + 31) / 32;
     size_t o = 4 * (size_t)m * WM;                              // T
-    o += 4 * (size_t)m * 2;                                     // pos, pcol
+    o += 2 * (size_t)m * 2;                                     // pos (int16), pcol (uint16)
+    o = (o + 3) & ~(size_t)3;
     o += 4 * (size_t)WM * 2;                                    // residual syndrome words, b words
     o += 4 * (size_t)WN;                                        // solution words
     o = (o + 7) & ~(size_t)7;
@@ -296,9 +297,9 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
     const int tid = threadIdx.x, NT = OSDB_THREADS, lane = tid & 31;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *T = reinterpret_cast<uint32_t *>(smem);                       // [m][WM]
-    int *pos = reinterpret_cast<int *>(T + (size_t)m * WM);                // [m]
-    int *pcol = pos + m;                                                    // [m]
-    uint32_t *bw = reinterpret_cast<uint32_t *>(pcol + m);                 // [WM] syndrome column, bit r = b[r]
+    int16_t *pos = reinterpret_cast<int16_t *>(T + (size_t)m * WM);       // [m]  (16-bit: two CTAs per SM fit for float keys)
+    uint16_t *pcol = reinterpret_cast<uint16_t *>(pos + m);                // [m]  0xFFFF: not a pivot row
+    uint32_t *bw = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(pcol + m) + 3) & ~(uintptr_t)3);   // [WM] syndrome column
     uint32_t *rsw = bw + WM;                                                // [WM] scratch
     uint32_t *solw = rsw + WM;                                              // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
             const int r = t / WM, w = t - r * WM;
             T[t] = (w == (r >> 5)) ? (1u << (r & 31)) : 0u;
         }
-        for (int r = tid; r < m; r += NT) { pos[r] = r; pcol[r] = -1; }
+        for (int r = tid; r < m; r += NT) { pos[r] = (int16_t)r; pcol[r] = 0xFFFFu; }
         __syncthreads();
         for (int w = tid; w < WM; w += NT) bw[w] = rsw[w];
         __syncthreads();
@@ -385,14 +386,14 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
             sidx = 0;
             for (int r = tid; r < m; r += NT, ++sidx) {
                 if (r == prow) continue;
-                if (pos[r] == row) pos[r] = pmin;                   // swap positions (OSD.py:56-58)
+                if (pos[r] == row) pos[r] = (int16_t)pmin;          // swap positions (OSD.py:56-58)
                 if ((hasmask >> sidx) & 1u) {                       // eliminate (OSD.py:64-68)
                     for (int w = 0; w < WM; ++w) T[(size_t)r * WM + w] ^= T[(size_t)prow * WM + w];
                     if (pb) atomicXor(&bw[r >> 5], 1u << (r & 31));
                 }
             }
             __syncthreads();
-            if (tid == 0) { pos[prow] = row; pcol[prow] = j; }
+            if (tid == 0) { pos[prow] = (int16_t)row; pcol[prow] = (uint16_t)j; }
             ++row;
         }
         __syncthreads();
@@ -401,7 +402,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
         int bad = 0;
         for (int r = tid; r < m; r += NT) {
             const uint32_t b = (bw[r >> 5] >> (r & 31)) & 1u;
-            if (pcol[r] >= 0) {
+            if (pcol[r] != 0xFFFFu) {
                 if (b) { const int v = ord[pcol[r]]; atomicXor(&solw[v >> 5], 1u << (v & 31)); }
             } else if (b) {
                 bad = 1;

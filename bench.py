@@ -311,7 +311,8 @@ def main():
         n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
         peak_laneops = n_sm * 128 * sm_max * 1e6
         achieved = iters_exec * A / bp_s
-        hbm_bytes_per_shot = 4 * WM + 4 * WN + 1 + 4   # packed syndrome in, packed correction + flag + iteration out
+        # packed syndrome in; packed correction + flag + iteration out; float32 posterior row for the BP failures (OSD input)
+        hbm_bytes_per_shot = 4 * WM + 4 * WN + 1 + 4 + 4 * n * cd["bp_failed"] / max(1, cd["shots"])
         kname = ("bp_tiled_kernel<T=%d,WM=%d,RW=6>" % (geom["lanes_per_shot"], WM)) if geom["kernel"] == "tiled" else "bp_decode_kernel<float,MIN_SUM>"
         roofline = {"bound": "alu", "kernel": kname,
                     "achieved": achieved / 1e12, "peak": peak_laneops / 1e12, "unit": "Tlane-op/s",
@@ -324,6 +325,13 @@ def main():
                             "achieved_gbs": hbm_bytes_per_shot * B * args.steps / bp_s / 1e9,
                             "peak_gbs": peaks.get("hbm_gbs"), "note": "on-chip path: HBM traffic is negligible by design"},
                     "traffic": None}
+        try:   # DRAM bytes per launch from the committed ncu capture of the same kernel (per shot x shots per launch)
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1e_bp_ncu.json")))
+            roofline["traffic"] = cap["dram_bytes_per_shot"] * min(B, CH)
+            roofline["ncu_capture"] = {k: cap[k] for k in ("source", "issue_slots_busy_pct", "alu_pipe_pct", "lsu_pipe_pct",
+                                                            "shared_wavefronts_pct_of_peak", "ipc_per_sm", "dram_bytes_per_shot")}
+        except Exception:
+            pass
         line = {"metric": METRIC, "value": value, "unit": "shots/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",

@@ -201,9 +201,8 @@ bp_tiled_kernel(const BPParams P, const uint32_t *__restrict__ vell0, const uint
                             min1 = fmin(min1, a);
                             min2 = fmin(min2, t);
                         }
-                        sv.v[0] = N::from_bits(N::bits(min1) | (sg & N::SIGN));
                         sv.v[NS - 1] = min2;
-                        if (NS == 2) sv.v[0] = N::from_bits(N::bits(min1) | (sg & N::SIGN));
+                        sv.v[0] = N::from_bits(N::bits(min1) | (sg & N::SIGN));           // signed min1 (written last: NS == 2 here)
                     } else {
                         // beliefPropagation.py:114-118: row product of tanh(Q/2), ascending column order
                         T prod = (T)1;

@@ -81,7 +81,7 @@ def paper_results(codes=CODES, physicalErrorRates=(0.05, 0.04, 0.03, 0.02, 0.01,
             out["BPs_fault"].append(c["bp_failed"] if bp_only else 0)     # paperResults.py leaves this counter at 0 (:74-75)
             out["BPs_miscorrected"].append(c["miscorrected"])
             out["incorrectable"].append(c["incorrectable"])
-            out["degeneracies"].append(c["degenerate"] - (0 if not bp_only else 0))
+            out["degeneracies"].append(c["degenerate"])
         results[name] = out
     return results
 

@@ -17,6 +17,8 @@
  *     (bit j of a row = bit (j & 31) of word (j >> 5)), and a cudaStream_t passed as void*; they
  *     only enqueue work.
  *   - shots are the leading axis of every batched array.
+ *   - a qldpc_code owns device workspaces and streams: use one handle per host thread / per stream at a time
+ *     (handles are cheap; the Tanner-graph tables are a few tens of KB).
  */
 #ifndef QLDPC_B200_H
 #define QLDPC_B200_H

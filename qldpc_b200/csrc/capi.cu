@@ -118,6 +118,9 @@ template <typename T> static cudaError_t upload(T **dst, const std::vector<T> &s
     return cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
+static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, const int32_t *var_ptr,
+                            const int32_t *var_edge0, const int32_t *var_edge1, int32_t k, const uint8_t *L, qldpc_code *c);
+
 extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx,
                                  const int32_t *var_ptr, const int32_t *var_edge0, const int32_t *var_edge1,
                                  int32_t k, const uint8_t *L, qldpc_code **out)
@@ -128,6 +131,21 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
     const int E = row_ptr[m];
     if (E <= 0 || var_ptr[n] != E) return fail(QLDPC_ERR_ARG, "qldpc_code_create: inconsistent CSR / variable pointers");
     qldpc_code *c = new qldpc_code();
+    const int rc = code_create_impl(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, k, L, c);
+    if (rc != QLDPC_OK) {               // release whatever was uploaded before the failure
+        const std::string msg = g_err;
+        qldpc_code_destroy(c);
+        g_err = msg;
+        return rc;
+    }
+    *out = c;
+    return QLDPC_OK;
+}
+
+static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, const int32_t *var_ptr,
+                            const int32_t *var_edge0, const int32_t *var_edge1, int32_t k, const uint8_t *L, qldpc_code *c)
+{
+    const int E = row_ptr[m];
     c->m = m; c->n = n; c->E = E; c->k = k;
     c->WM = (m + 31) / 32;
     c->WN = (n + 31) / 32;
@@ -142,7 +160,7 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
     for (int r = 0; r < m; ++r) {
         if (row_ptr[r + 1] - row_ptr[r] != rw) rw = 0;
         for (int e = row_ptr[r]; e < row_ptr[r + 1]; ++e) {
-            if (col_idx[e] < 0 || col_idx[e] >= n) { delete c; return fail(QLDPC_ERR_ARG, "qldpc_code_create: column index out of range"); }
+            if (col_idx[e] < 0 || col_idx[e] >= n) return fail(QLDPC_ERR_ARG, "qldpc_code_create: column index out of range");
             edge_check[e] = r;
         }
     }
@@ -152,10 +170,8 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
         c->max_col_w = std::max(c->max_col_w, var_ptr[v + 1] - var_ptr[v]);
         for (int a = var_ptr[v]; a < var_ptr[v + 1]; ++a) {
             const int e0 = var_edge0[a], e1 = var_edge1[a];
-            if (e0 < 0 || e0 >= E || e1 < 0 || e1 >= E || col_idx[e0] != v || col_idx[e1] != v) {
-                delete c;
+            if (e0 < 0 || e0 >= E || e1 < 0 || e1 >= E || col_idx[e0] != v || col_idx[e1] != v)
                 return fail(QLDPC_ERR_ARG, "qldpc_code_create: var_edge table does not match the CSR");
-            }
             vt0[2 * a] = e0; vt0[2 * a + 1] = edge_check[e0];
             vt1[2 * a] = e1; vt1[2 * a + 1] = edge_check[e1];
             if (e0 != e1) c->two_tables = 1;
@@ -300,7 +316,6 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
         CK(upload(&c->d_vell1[ti], vell1[ti]));
     }
     CK(c->ctrl.reserve(sizeof(Ctrl)));
-    *out = c;
     return QLDPC_OK;
 }
 
@@ -988,11 +1003,9 @@ extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg
     if (const char *e = getenv("QLDPC_HOST_CHUNK")) chunk = std::max<long long>(1024, atoll(e));
     chunk = std::min<long long>(chunk, CHUNK);
     if (int rc = set_prior(c, prior, 0)) return rc;
-    int rc_all = QLDPC_OK;
-    long long i = 0;
-    for (long long o = 0; o < B && rc_all == QLDPC_OK; o += chunk, ++i) {
-        const long long b = std::min<long long>(chunk, B - o);
-        qldpc_code::Slot &sl = c->slot[i % qldpc_code::NSLOT];
+    // enqueue every chunk; on any failure stop enqueuing, but always drain the streams before returning, so that no copy
+    // into the caller's buffers is still in flight
+    auto enqueue = [&](long long o, long long b, qldpc_code::Slot &sl) -> int {
         if (!sl.st) CK(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
         cudaStream_t st = sl.st;
         CK(sl.u8in.reserve((size_t)b * c->m));
@@ -1010,9 +1023,17 @@ extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg
         CK(cudaMemcpyAsync(corr + (size_t)o * c->n, sl.u8out.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
         if (iters) CK(cudaMemcpyAsync(iters + o, sl.iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
-    }
+        return QLDPC_OK;
+    };
+    int rc_all = QLDPC_OK;
+    long long i = 0;
+    for (long long o = 0; o < B && rc_all == QLDPC_OK; o += chunk, ++i)
+        rc_all = enqueue(o, std::min<long long>(chunk, B - o), c->slot[i % qldpc_code::NSLOT]);
+    const std::string msg = g_err;
     for (auto &sl : c->slot)
-        if (sl.st) CK(cudaStreamSynchronize(sl.st));
+        if (sl.st && cudaStreamSynchronize(sl.st) != cudaSuccess && rc_all == QLDPC_OK)
+            rc_all = fail(QLDPC_ERR_CUDA, "qldpc_bposd_decode_host: stream synchronisation failed");
+    if (rc_all != QLDPC_OK && !msg.empty()) g_err = msg;
     return rc_all;
 }
 

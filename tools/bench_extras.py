@@ -116,9 +116,9 @@ def main():
         r = Runner(H, Lx, d)
         for p in (0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.1):
             emit(f"2: [[144,12,12]] p={p} min-sum BP100 + OSD-7, f32", p=p, **r.run(p, 8_000_000 // q, dict(max_iter=100, **ms_kw), 7))
-        emit("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f64 (thread-per-shot kernel)", p=0.05,
+        emit("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f64", p=0.05,
              **r.run(0.05, 400_000 // q, dict(variant="sum_product", max_iter=100, precision=64), 7, reps=1))
-        emit("2: [[144,12,12]] p=0.05 min-sum BP100 + OSD-7, f64 parity mode (thread-per-shot kernel)", p=0.05,
+        emit("2: [[144,12,12]] p=0.05 min-sum BP100 + OSD-7, f64 (bit-exact parity mode)", p=0.05,
              **r.run(0.05, 1_000_000 // q, dict(variant="min_sum", max_iter=100, alpha=0.8, damping=0.7, clip=25.0, precision=64), 7, reps=1))
 
 

@@ -162,7 +162,7 @@ def main():
     prior_p = prior.ctypes.data_as(ctypes.c_void_p)
     geom = code.geometry(cfg)
     B = args.shots
-    CH = 1 << 22
+    CH = 1 << 24          # shots per BP launch (LLR hand-off buffer: 4n bytes per shot)
     i32 = torch.int32
     err = torch.empty((B, WN), dtype=i32, device=dev)
     synd = torch.empty((B, WM), dtype=i32, device=dev)
@@ -296,6 +296,26 @@ def main():
             a.record(); run_v(); b_.record()
             torch.cuda.synchronize()
             variants[name] = {"shots_per_s": Bv / (a.elapsed_time(b_) * 1e-3), "shots": Bv, "kernel": code.geometry(cv)["kernel"]}
+        # the p-sweep of BASELINE configs[1] (rework/main.py:30 list + 0.01), same decoder, device-sampled syndromes
+        sweep = {}
+        Bs = min(B, 2_000_000)
+        for pp in (0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.1):
+            _lib.check(L.qldpc_sample_dev(code.handle, pp, SEED + 1, 0, 1, Bs, err.data_ptr(), synd.data_ptr(), stream), "sample")
+            pr = np.full(n, np.log((1 - pp) / pp))
+            run_p = lambda: _lib.check(L.qldpc_bposd_decode_dev(code.handle, ctypes.byref(cfg), pr.ctypes.data_as(ctypes.c_void_p), Bs,
+                                                                synd.data_ptr(), OSD_ORDER, corr.data_ptr(), conv.data_ptr(), iters.data_ptr(),
+                                                                None, stream), "sweep")
+            run_p()
+            torch.cuda.synchronize()
+            a, b_ = ev(), ev()
+            a.record(); run_p(); b_.record()
+            torch.cuda.synchronize()
+            counters.zero_()
+            _lib.check(L.qldpc_check_dev(code.handle, Bs, err.data_ptr(), corr.data_ptr(), synd.data_ptr(), conv.data_ptr(), iters.data_ptr(),
+                                         distance, None, None, counters.data_ptr(), stream), "check")
+            cs = dict(zip(_lib.COUNTER_NAMES, counters.cpu().tolist()))
+            sweep[str(pp)] = {"shots_per_s": Bs / (a.elapsed_time(b_) * 1e-3), "ler": cs["logical"] / Bs,
+                              "bp_failure_rate": cs["bp_failed"] / Bs, "invalid": cs["invalid"]}
 
     if rank == 0:
         A = 15 * code.E + 2 * n + m                       # lane-ops per shot-iteration
@@ -345,7 +365,7 @@ def main():
                 "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": Be * m, "d2h_bytes_per_step": Be * (n + 1 + 4),
                         "shots_per_step": Be, "steps": e2e_steps, "api": "qldpc_bposd_decode_host (uint8 in pinned host memory)",
                         "matches_device_path": e2e_matches},
-                "other_variants_same_workload": variants,
+                "other_variants_same_workload": variants, "p_sweep_configs1": sweep,
                 "gpu_launches": launches, "clocks": clocks}
         if world == 1 and not args.no_cpu:
             synd_cpu = synd_h.numpy()

@@ -776,7 +776,7 @@ extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, co
 // ------------------------------------------------------------------------------------------------
 // fused BP -> OSD
 // ------------------------------------------------------------------------------------------------
-static const long long CHUNK = 1ll << 22;   // shots per internal launch (bounds the LLR workspace)
+static const long long CHUNK = 1ll << 24;   // shots per internal launch (bounds the LLR hand-off workspace: 4n bytes per shot)
 
 // BP, then OSD-0 on the compacted BP failures, for at most CHUNK shots, with explicit workspaces
 static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, long long b, const uint32_t *synd,

@@ -969,7 +969,14 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
             P.rec_sred = reinterpret_cast<uint8_t *>(r);
         }
         if (int rc = osd_launch(c, P, 1, b, st)) return rc;
-        if (want_rec) {
+        bool any_invalid = false;
+        if (want_rec) {     // the sweep is dead code whenever every OSD-0 solution satisfies its syndrome (OSD_enhanced.py:58-60)
+            std::vector<uint8_t> hv((size_t)b);
+            CK(cudaMemcpyAsync(hv.data(), c->ws_valid.p, (size_t)b, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            for (uint8_t x : hv) any_invalid |= (x == 0);
+        }
+        if (want_rec && any_invalid) {
             // OSD-w sweep on the shots whose OSD-0 solution misses the syndrome (OSD_enhanced.py:66-131)
             OSDWParams W;
             memset(&W, 0, sizeof(W));

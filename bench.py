@@ -274,6 +274,26 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = Be * e2e_steps * world / float(te.item())
+    # same call with bit-packed host rows (not a reference dtype; reported next to the headline e2e)
+    synd_hp = torch.empty((Be, WM), dtype=i32).pin_memory()
+    synd_hp.copy_(synd[:Be])
+    corr_hp = torch.empty((Be, WN), dtype=i32).pin_memory()
+    torch.cuda.synchronize()
+
+    def e2e_packed_step():
+        _lib.check(L.qldpc_bposd_decode_host_packed(code.handle, ctypes.byref(cfg), prior_p, Be, synd_hp.data_ptr(), OSD_ORDER,
+                                                    corr_hp.data_ptr(), conv_h.data_ptr(), iters_h.data_ptr()), "bposd_host_packed")
+    e2e_packed_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_packed_step()
+    torch.cuda.synchronize()
+    tp = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+    e2e_packed_value = Be * e2e_steps * world / float(tp.item())
+    e2e_packed_matches = bool(torch.equal(corr_hp, corr[:Be].cpu()))
     # the host-path corrections must equal the device-path ones (same shots)
     corr_u8_dev = torch.empty((Be, n), dtype=torch.uint8, device=dev)
     _lib.check(L.qldpc_unpack_bits_dev(corr.data_ptr(), corr_u8_dev.data_ptr(), Be, n, stream), "unpack")
@@ -364,7 +384,10 @@ def main():
                 "roofline": roofline,
                 "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": Be * m, "d2h_bytes_per_step": Be * (n + 1 + 4),
                         "shots_per_step": Be, "steps": e2e_steps, "api": "qldpc_bposd_decode_host (uint8 in pinned host memory)",
-                        "matches_device_path": e2e_matches},
+                        "matches_device_path": e2e_matches,
+                        "packed_host_rows": {"value": e2e_packed_value, "unit": "shots/s", "h2d_bytes_per_step": Be * 4 * WM,
+                                             "d2h_bytes_per_step": Be * (4 * WN + 1 + 4), "api": "qldpc_bposd_decode_host_packed",
+                                             "matches_device_path": e2e_packed_matches}},
                 "other_variants_same_workload": variants, "p_sweep_configs1": sweep,
                 "gpu_launches": launches, "clocks": clocks}
         if world == 1 and not args.no_cpu:

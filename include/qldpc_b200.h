@@ -134,6 +134,12 @@ int qldpc_bposd_decode_host(qldpc_code *code, const qldpc_bp_config *cfg, const 
                             const uint8_t *synd, int32_t osd_order, uint8_t *corr, uint8_t *conv,
                             int32_t *iters);
 
+/* Same call with bit-packed host rows (synd [B][words_m], corr [B][words_n] uint32): 37 instead of 221 bytes per
+ * [[144,12,12]] shot cross PCIe.  Not a reference dtype; for callers that keep syndromes packed. */
+int qldpc_bposd_decode_host_packed(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                   const uint32_t *synd, int32_t osd_order, uint32_t *corr, uint8_t *conv,
+                                   int32_t *iters);
+
 /* Per-shot checks of the drivers (paperResults.py:83-100, rework/main.py:90-112):
  * err/corr [B][n] uint8, synd [B][m] uint8 -> flags [B] uint8 (bit0 logical, bit1 valid,
  * bit2 degenerate), weight [B] int32 (residual weight), counters[QLDPC_NUM_COUNTERS] (any may be NULL). */

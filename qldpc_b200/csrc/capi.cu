@@ -998,10 +998,14 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
     return QLDPC_OK;
 }
 
-extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
-                                       const uint8_t *synd, int32_t osd_order, uint8_t *corr, uint8_t *conv, int32_t *iters)
+// packed = false: synd [B][m] / corr [B][n] uint8 (the reference's dtypes);  packed = true: bit-packed uint32 rows
+static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                  const void *synd_v, int32_t osd_order, void *corr_v, uint8_t *conv, int32_t *iters, bool packed)
 {
+    const uint8_t *synd = reinterpret_cast<const uint8_t *>(synd_v);
+    uint8_t *corr = reinterpret_cast<uint8_t *>(corr_v);
     if (!c || !synd || !corr || !conv) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_host: null argument");
+    const size_t in_row = packed ? 4 * (size_t)c->WM : (size_t)c->m, out_row = packed ? 4 * (size_t)c->WN : (size_t)c->n;
     if (int rc = check_cfg(cfg)) return rc;
     if (B <= 0) return QLDPC_OK;
     // Chunks rotate over NSLOT streams: copy-in / pack / BP / OSD / unpack / copy-out of chunk i overlap with the
@@ -1015,19 +1019,27 @@ extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg
     auto enqueue = [&](long long o, long long b, qldpc_code::Slot &sl) -> int {
         if (!sl.st) CK(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
         cudaStream_t st = sl.st;
-        CK(sl.u8in.reserve((size_t)b * c->m));
-        CK(sl.u8out.reserve((size_t)b * c->n));
         CK(sl.synd.reserve(4 * (size_t)b * c->WM));
         CK(sl.hard.reserve(4 * (size_t)b * c->WN));
         CK(sl.conv.reserve((size_t)b));
         CK(sl.iters.reserve(4 * (size_t)b));
-        CK(cudaMemcpyAsync(sl.u8in.p, synd + (size_t)o * c->m, (size_t)b * c->m, cudaMemcpyHostToDevice, st));
-        if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, st)) return rc;
+        if (packed) {
+            CK(cudaMemcpyAsync(sl.synd.p, synd + (size_t)o * in_row, (size_t)b * in_row, cudaMemcpyHostToDevice, st));
+        } else {
+            CK(sl.u8in.reserve((size_t)b * c->m));
+            CK(sl.u8out.reserve((size_t)b * c->n));
+            CK(cudaMemcpyAsync(sl.u8in.p, synd + (size_t)o * in_row, (size_t)b * in_row, cudaMemcpyHostToDevice, st));
+            if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, st)) return rc;
+        }
         if (int rc = bposd_chunk(c, cfg, prior, b, sl.synd.as<uint32_t>(), osd_order, sl.hard.as<uint32_t>(), sl.conv.as<uint8_t>(),
                                  sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, st))
             return rc;
-        if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, st)) return rc;
-        CK(cudaMemcpyAsync(corr + (size_t)o * c->n, sl.u8out.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
+        if (packed) {
+            CK(cudaMemcpyAsync(corr + (size_t)o * out_row, sl.hard.p, (size_t)b * out_row, cudaMemcpyDeviceToHost, st));
+        } else {
+            if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, st)) return rc;
+            CK(cudaMemcpyAsync(corr + (size_t)o * out_row, sl.u8out.p, (size_t)b * out_row, cudaMemcpyDeviceToHost, st));
+        }
         CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
         if (iters) CK(cudaMemcpyAsync(iters + o, sl.iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
         return QLDPC_OK;
@@ -1042,6 +1054,20 @@ extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg
             rc_all = fail(QLDPC_ERR_CUDA, "qldpc_bposd_decode_host: stream synchronisation failed");
     if (rc_all != QLDPC_OK && !msg.empty()) g_err = msg;
     return rc_all;
+}
+
+extern "C" int qldpc_bposd_decode_host(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                       const uint8_t *synd, int32_t osd_order, uint8_t *corr, uint8_t *conv, int32_t *iters)
+{
+    if (!c) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_host: null code");
+    return bposd_decode_host_impl(c, cfg, prior, B, synd, osd_order, corr, conv, iters, false);
+}
+
+extern "C" int qldpc_bposd_decode_host_packed(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
+                                              const uint32_t *synd, int32_t osd_order, uint32_t *corr, uint8_t *conv, int32_t *iters)
+{
+    if (!c) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_host_packed: null code");
+    return bposd_decode_host_impl(c, cfg, prior, B, synd, osd_order, corr, conv, iters, true);
 }
 
 extern "C" int qldpc_check_host(qldpc_code *c, int64_t B, const uint8_t *err, const uint8_t *corr, const uint8_t *synd,

@@ -165,6 +165,14 @@ int qldpc_mc_sweep(qldpc_code *code, const qldpc_bp_config *cfg, const double *p
                    uint64_t seed, uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order,
                    int32_t distance, uint64_t *counters);
 
+/* Posterior-LLR histograms without returning B*n floats (BP_per_Iteration.py:56,60 and rework/Alvarado.py:159-162 collect
+ * every posterior LLR on the host): device-sampled shots as in qldpc_mc_sweep, BP only, hist [3][nbins] uint64 ADDED into:
+ * row 0 = LLRs of variables whose true error bit is 0, row 1 = true bit 1, row 2 = all LLRs of BP-failed shots.  Uniform
+ * bins over [lo, hi), out-of-range values in the end bins.  bp_failed (may be NULL) is incremented by the BP failures. */
+int qldpc_bp_llr_histogram(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, double p, uint64_t seed,
+                           uint64_t first_shot, int64_t nshots, int32_t draws, double lo, double hi, int32_t nbins,
+                           uint64_t *hist, uint64_t *bp_failed);
+
 /* ---------------- device-pointer API (bit-packed, asynchronous) ---------------- */
 
 /* words per packed syndrome / error row */

@@ -228,6 +228,22 @@ class Code:
         return dict(zip(_lib.COUNTER_NAMES, (int(x) for x in counters)))
 
 
+    def llr_histograms(self, p, nshots, lo=-30.0, hi=30.0, nbins=120, prior=None, seed=0, first_shot=0, draws=1,
+                       variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0, precision=32):
+        """Posterior-LLR histograms computed on the device (no B*n floats returned).
+        -> dict(edges float64 (nbins+1,), true_0, true_1, bp_failed_shots uint64 (nbins,), n_bp_failed int)"""
+        cfg = self.config(variant, max_iter, alpha, damping, clip, precision)
+        pe = p if draws == 1 else 2 * p * (1 - p)
+        pr = self._prior(np.log((1 - pe) / pe) if prior is None else prior)
+        hist = np.zeros((3, int(nbins)), np.uint64)
+        nf = ctypes.c_uint64(0)
+        _lib.check(_lib.lib().qldpc_bp_llr_histogram(self._h, ctypes.byref(cfg), _vp(pr), float(p), int(seed), int(first_shot),
+                                                     int(nshots), int(draws), float(lo), float(hi), int(nbins), _vp(hist),
+                                                     ctypes.byref(nf)), "qldpc_bp_llr_histogram")
+        return dict(edges=np.linspace(lo, hi, int(nbins) + 1), true_0=hist[0], true_1=hist[1], bp_failed_shots=hist[2],
+                    n_bp_failed=int(nf.value))
+
+
 # ------------------------------------------------------------------------------------------------
 # codes/*.npz (SURVEY.md section 8 a11) and the handle cache used by the reference-named wrappers
 # ------------------------------------------------------------------------------------------------

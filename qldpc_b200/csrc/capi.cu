@@ -1163,6 +1163,51 @@ extern "C" int qldpc_sample_host(qldpc_code *c, double p, uint64_t seed, uint64_
     return QLDPC_OK;
 }
 
+// BP on device-sampled shots with the posterior LLRs histogrammed on the device instead of returned:
+// hist [3][nbins] uint64 (true bit 0 / true bit 1 / BP-failed shots), ADDED into the host array; counters as qldpc_mc_sweep.
+extern "C" int qldpc_bp_llr_histogram(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, double p, uint64_t seed,
+                                      uint64_t first_shot, int64_t nshots, int32_t draws, double lo, double hi, int32_t nbins,
+                                      uint64_t *hist, uint64_t *bp_failed)
+{
+    if (!c || !hist || nbins <= 0 || nbins > 4096 || !(hi > lo)) return fail(QLDPC_ERR_ARG, "qldpc_bp_llr_histogram: bad argument");
+    if (int rc = check_cfg(cfg)) return rc;
+    cudaStream_t st = 0;
+    const int tsize = cfg->precision == 64 ? 8 : 4;
+    CK(c->ws_cnt.reserve(8 * (size_t)3 * nbins + 16));
+    CK(cudaMemsetAsync(c->ws_cnt.p, 0, 8 * (size_t)3 * nbins + 16, st));
+    unsigned long long *d_hist = c->ws_cnt.as<unsigned long long>();
+    unsigned long long *d_fail = d_hist + 3 * nbins;
+    const long long chunk = 1ll << 20;
+    for (long long o = 0; o < nshots; o += chunk) {
+        const long long b = std::min<long long>(chunk, nshots - o);
+        CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+        CK(c->ws_hard.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        CK(c->ws_conv.reserve((size_t)b));
+        CK(c->ws_iters.reserve(4 * (size_t)b));
+        CK(c->ws_llr.reserve((size_t)b * c->n * tsize));
+        if (int rc = qldpc_sample_dev(c, p, seed, first_shot + (uint64_t)o, draws, b, c->ws_err.as<uint32_t>(), c->ws_synd.as<uint32_t>(), st))
+            return rc;
+        if (int rc = qldpc_bp_decode_dev(c, cfg, prior, b, c->ws_synd.as<uint32_t>(), c->ws_hard.as<uint32_t>(), c->ws_conv.as<uint8_t>(),
+                                         c->ws_iters.as<int32_t>(), c->ws_llr.p, QLDPC_LLR_ALL, nullptr, nullptr, nullptr, st))
+            return rc;
+        const int grid = grid_for(b * (long long)c->n, 256, c->num_sms);
+        const size_t smem = 4 * (size_t)3 * nbins;
+        if (tsize == 8)
+            llr_hist_kernel<double><<<grid, 256, smem, st>>>(c->ws_llr.as<double>(), c->ws_err.as<uint32_t>(), c->ws_conv.as<uint8_t>(), b,
+                                                             c->n, c->WN, lo, hi, nbins, d_hist, d_fail);
+        else
+            llr_hist_kernel<float><<<grid, 256, smem, st>>>(c->ws_llr.as<float>(), c->ws_err.as<uint32_t>(), c->ws_conv.as<uint8_t>(), b,
+                                                            c->n, c->WN, lo, hi, nbins, d_hist, d_fail);
+        CK(cudaGetLastError());
+    }
+    std::vector<uint64_t> h((size_t)3 * nbins + 1);
+    CK(cudaMemcpy(h.data(), d_hist, 8 * h.size(), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < (size_t)3 * nbins; ++i) hist[i] += h[i];
+    if (bp_failed) *bp_failed += h[(size_t)3 * nbins];
+    return QLDPC_OK;
+}
+
 extern "C" int qldpc_mc_sweep(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, double p, uint64_t seed,
                               uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order, int32_t distance,
                               uint64_t *counters)

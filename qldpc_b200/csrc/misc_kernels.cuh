@@ -141,6 +141,37 @@ __global__ void syndrome_kernel(const int32_t *__restrict__ row_ptr, const int32
     }
 }
 
+// ---- posterior-LLR histograms (BP_per_Iteration.py:56,60; rework/Alvarado.py:159-162) -----------------------------
+// hist[0]: LLRs of variables whose true error bit is 0, hist[1]: true bit 1, hist[2]: all LLRs of BP-failed shots.
+// Bins are uniform over [lo, hi); values outside go to the first / last bin.  Shared-memory privatised counters.
+template <typename T>
+__global__ void __launch_bounds__(256) llr_hist_kernel(const T *__restrict__ llr, const uint32_t *__restrict__ err, const uint8_t *__restrict__ conv,
+                                                       long long B, int n, int WN, double lo, double hi, int nbins, unsigned long long *hist,
+                                                       unsigned long long *n_failed)
+{
+    extern __shared__ unsigned int s_h[];                 // [3][nbins]
+    for (int i = threadIdx.x; i < 3 * nbins; i += blockDim.x) s_h[i] = 0;
+    __syncthreads();
+    const double scale = nbins / (hi - lo);
+    const long long total = B * (long long)n;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long s = t / n;
+        const int v = (int)(t - s * n);
+        const double x = (double)llr[t];
+        int bin = (int)floor((x - lo) * scale);
+        bin = max(0, min(nbins - 1, bin));
+        const int bit = err ? (int)((err[(size_t)s * WN + (v >> 5)] >> (v & 31)) & 1u) : 0;
+        atomicAdd(&s_h[bit * nbins + bin], 1u);
+        if (conv && !conv[s]) {
+            atomicAdd(&s_h[2 * nbins + bin], 1u);
+            if (v == 0) atomicAdd(n_failed, 1ull);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * nbins; i += blockDim.x)
+        if (s_h[i]) atomicAdd(&hist[i], (unsigned long long)s_h[i]);
+}
+
 // ---- checks + counters ------------------------------------------------------------------------
 enum {
     CNT_SHOTS = 0,        // shots counted

@@ -87,3 +87,21 @@ def test_bp_per_iteration_dict():
     ms = X.bp_per_iteration(codes=["[[108, 8, 10]]"], errorRate=0.01, iterations=(30,), trials=N, variant="min_sum", alpha=0.8,
                             damping=0.7, clip=25.0, precision=32)["[[108, 8, 10]]"]
     assert ms["logicalErrors"][0] < 0.01
+
+
+def test_device_llr_histograms_match_host_histograms():
+    """LLR histograms on the device == np.histogram of the LLRs the batched call returns."""
+    from qldpc_b200 import Code, graph
+    H, d = load_code_file("[[108, 8, 10]]")
+    code = Code(H, d["Lx"], (graph.SEQ, graph.SEQ), int(d["distance"]))
+    p, N, seed = 0.04, 30000, 5
+    kw = dict(variant="min_sum", max_iter=20, alpha=0.8, damping=0.7, clip=25.0, precision=32)
+    h = code.llr_histograms(p, N, lo=-30.0, hi=30.0, nbins=60, seed=seed, **kw)
+    err, synd = code.sample(p, N, seed=seed)
+    hard, conv, llr, iters = code.bp_decode_batch(synd, np.log((1 - p) / p), **kw)
+    edges = h["edges"]
+    clipped = np.clip(llr, edges[0], np.nextafter(edges[-1], -np.inf))
+    assert np.array_equal(h["true_0"], np.histogram(clipped[err == 0], bins=edges)[0])
+    assert np.array_equal(h["true_1"], np.histogram(clipped[err == 1], bins=edges)[0])
+    assert np.array_equal(h["bp_failed_shots"], np.histogram(clipped[~conv], bins=edges)[0])
+    assert h["n_bp_failed"] == int((~conv).sum()) and int(h["true_0"].sum() + h["true_1"].sum()) == N * 108

@@ -245,6 +245,11 @@ bp_decode_kernel(const BPParams P)
 
     constexpr int WREG = (WMS > 0) ? WMS : 1;
     uint32_t synd[WREG], acc[WREG];
+    // WMS == 0: running syndrome of the hard decision as a thread-private bit array (dynamically indexed, i.e. in local
+    // memory), toggled only for the rare variables decided as 1 -- instead of re-reading the hard-decision words check by check
+    constexpr int PARW = (WMS > 0) ? 1 : 64;
+    uint32_t par[PARW];
+    const bool use_par = (WMS == 0) && (WM <= PARW);
     long long shot = -1;
     int iter = 0;
     bool active = false, exhausted = false;
@@ -372,6 +377,8 @@ bp_decode_kernel(const BPParams P)
         if (WMS > 0) {
 #pragma unroll
             for (int k = 0; k < WREG; ++k) acc[k] = 0;
+        } else if (use_par) {
+            for (int w = 0; w < WM; ++w) par[w] = 0;
         }
         for (int wv = 0; wv * 32 < n; ++wv) {
             uint32_t hw = 0;
@@ -448,6 +455,11 @@ bp_decode_kernel(const BPParams P)
 #pragma unroll
                         for (int k = 0; k < WREG; ++k) acc[k] ^= colmask[v * WREG + k];
                     }
+                } else if (use_par && hd) {
+                    for (int a = a0; a < a0 + deg; ++a) {
+                        const uint32_t c = vt[a].y;
+                        par[c >> 5] ^= 1u << (c & 31);
+                    }
                 }
                 // Q update: Q_new = values - R; damping against Q_old; clip  (decoding.py:63-66)
 #pragma unroll
@@ -504,6 +516,8 @@ bp_decode_kernel(const BPParams P)
         if (WMS > 0) {
 #pragma unroll
             for (int k = 0; k < WREG; ++k) conv = conv && (acc[k] == synd[k]);
+        } else if (use_par) {
+            for (int w = 0; w < WM; ++w) conv = conv && (par[w] == SY[(idx_t)w * S]);
         } else {
             for (int w = 0; w * 32 < m && conv; ++w) {
                 uint32_t par = 0;

@@ -68,8 +68,9 @@ typedef struct {
     int32_t staged;     /* kernel choice.  0: auto -- float32 min-sum on a uniform-row-weight H runs the
                            T-lanes-per-shot shared-memory kernel, anything else the thread-per-shot kernel,
                            in shared memory when the per-shot state fits, else HBM-staged;
-                           1: force the HBM-staged kernel; 2: force the thread-per-shot kernel            */
-    int32_t lanes_per_shot; /* 0: auto | 4 | 8 (T-lanes-per-shot kernel)                             */
+                           1: force the HBM-staged kernel; 2: force the thread-per-shot kernel;
+                           3: force the warp-per-shot kernel (float32 min-sum on BB-shaped H)             */
+    int32_t lanes_per_shot; /* 0: auto | 4 | 8 (T-lanes-per-shot kernel) | 32 (warp-per-shot kernel)        */
     int32_t refill_min; /* 0: auto.  Idle shots per warp that trigger a refill from the shot cursor  */
     double alpha;       /* min-sum normalisation / sum-product scaling                               */
     double damping;     /* damping on Q                                                              */

@@ -82,7 +82,7 @@ class Code:
         cfg.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
         cfg.precision = int(precision)
         cfg.max_iter = int(max_iter)
-        cfg.staged = int(staged)          # 0 auto | 1 (True) HBM-staged | 2 thread-per-shot
+        cfg.staged = int(staged)          # 0 auto | 1 (True) HBM-staged | 2 thread-per-shot | 3 warp-per-shot
         cfg.lanes_per_shot = int(lanes_per_shot)
         cfg.refill_min = int(refill_min)
         cfg.alpha, cfg.damping, cfg.clip = float(alpha), float(damping), float(clip)
@@ -102,7 +102,7 @@ class Code:
         kind = c.value
         return dict(shots_per_cta=a.value, smem_bytes=b.value, staged=(kind == 1),
                     lanes_per_shot=(kind - 100 if kind >= 100 else 1),
-                    kernel=('hbm_staged' if kind == 1 else 'tiled' if kind >= 100 else 'thread_per_shot'))
+                    kernel=('hbm_staged' if kind == 1 else 'warp_per_shot' if kind == 132 else 'tiled' if kind >= 100 else 'thread_per_shot'))
 
     def tiled_conflict_model(self, lanes_per_shot=8):
         """(before, after): modelled shared-memory wavefronts per shot-iteration of the tiled kernel's variable pass with

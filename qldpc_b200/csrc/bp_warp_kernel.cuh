@@ -1,0 +1,209 @@
+// Min-sum BP for code-capacity check matrices (BB codes) on sm_100a: ONE WARP PER SHOT, the variable-to-check
+// messages live in REGISTERS of the lane that owns their check.
+//
+// Same arithmetic, in the same order, as bp_decode_kernel<float, VAR_MIN_SUM> / bp_tiled_kernel (reference
+// rework/decoding.py:5-75): results are bit-identical.  Different mapping, chosen after the ncu profile of the tiled
+// kernel (profiles/r1e: shared-memory wavefronts at 84 % of peak, issue slots 76 % busy):
+//   * lane l owns checks c = l + 32 i (i < CPL) and keeps their RW incoming messages Q[i][k] in registers, so the whole
+//     check pass (sign parity, min1/min2, the RW outgoing messages R) is lane-local: no loads, no index arithmetic;
+//   * R is published to a per-warp shared-memory buffer in the owner's own bank (conflict-free stores);
+//   * lane l also owns variables v = l + 32 i (i < VPL): it GATHERS its 3 incoming R (indices held in registers, loaded
+//     once per kernel), adds them in the reference's order, adds the prior, and publishes the posterior (conflict-free
+//     store); the hard-decision word i of the shot is simply __ballot_sync(posterior < 0);
+//   * each check-owner lane gathers the posteriors of its RW variables, updates Q in registers (damping against the Q it
+//     still holds, clip), and accumulates the parity of the hard decisions of its check from the sign bits it just read:
+//     the syndrome test of the hard decision is lane-local, followed by one __all_sync.
+// Per shot-iteration this needs ~45 shared-memory words per lane-row instead of ~150 wavefronts per shot in the tiled
+// kernel and about 30 % fewer instructions (no table reads, no address arithmetic, no divergence: a warp decodes exactly
+// one shot, retires it and fetches the next one from the global cursor).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "bp_kernel.cuh"
+
+namespace qldpc {
+
+constexpr int BPW_WARPS = 8;            // warps per CTA
+
+__device__ __forceinline__ float ldb(const float *base, uint32_t byte_off)
+{
+    return *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(base) + byte_off);
+}
+
+// per-warp shared memory: R buffer [CPL*RW][32] + one zero row [32] + posterior buffer [VPL][32]
+__host__ __device__ inline size_t bp_warp_smem_per_warp(int CPL, int VPL, int RW) { return 4 * (size_t)32 * (CPL * RW + 1 + VPL); }
+
+// min1 / min2 (smallest and second smallest, as values) of |q[0..RW)|: pairwise sort, then min1 = min of the pair
+// minima, min2 = min(median of the pair minima, min of the pair maxima).  13 FMNMX for RW = 6 instead of 18.
+template <int RW>
+__device__ __forceinline__ void bpw_two_smallest(const float (&q)[RW], float &min1, float &min2)
+{
+    if constexpr (RW == 6) {
+        const float a0 = fabsf(q[0]), a1 = fabsf(q[1]), a2 = fabsf(q[2]), a3 = fabsf(q[3]), a4 = fabsf(q[4]), a5 = fabsf(q[5]);
+        const float l0 = fminf(a0, a1), h0 = fmaxf(a0, a1);
+        const float l1 = fminf(a2, a3), h1 = fmaxf(a2, a3);
+        const float l2 = fminf(a4, a5), h2 = fmaxf(a4, a5);
+        const float lmin01 = fminf(l0, l1), lmax01 = fmaxf(l0, l1);
+        min1 = fminf(lmin01, l2);
+        const float lmed = fmaxf(lmin01, fminf(lmax01, l2));
+        min2 = fminf(lmed, fminf(fminf(h0, h1), h2));
+    } else {
+        min1 = CUDART_INF_F; min2 = CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            const float a = fabsf(q[k]);
+            const float t = fmaxf(min1, a);
+            min1 = fminf(min1, a);
+            min2 = fminf(min2, t);
+        }
+    }
+}
+
+// Tables (global, built by the host, natural labelling c = lane + 32 i, v = lane + 32 i):
+//   ridx  [VPL*3][32]  byte offset in the R buffer of the t-th ADDED message of variable (i, lane) in iterations >= 1
+//                      (the zero row for padding);  ridx0: the same for iteration 0 (read only when TWO: the
+//                      reference's NumPy reduction order differs between iteration 0 and the later ones, graph.py)
+//   vidx  [CPL*RW][32] byte offset in the posterior buffer of the variable of edge k of check (i, lane); 0 for padding
+template <int CPL, int VPL, int RW, bool TWO>
+__global__ void __launch_bounds__(BPW_WARPS * 32, (CPL * RW + VPL * 4 > 44) ? 1 : 2)
+bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const uint32_t *__restrict__ ridx0_tab,
+               const uint32_t *__restrict__ vidx_tab)
+{
+    constexpr int WMS = CPL;
+    const int m = P.g.m, n = P.g.n, WN = P.g.WN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *Rbuf = reinterpret_cast<float *>(smem + bp_warp_smem_per_warp(CPL, VPL, RW) * warp);
+    float *Vbuf = Rbuf + 32 * (CPL * RW + 1);
+    constexpr int ZERO_ROW = CPL * RW;
+
+    // ---- per-lane tables into registers (BYTE offsets into the R / posterior buffers) -------------
+    uint32_t ridx[VPL][3], vidx[CPL][RW];
+    float prior[VPL];
+    bool cvalid[CPL];
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+        const int v = lane + 32 * i;
+        prior[i] = (v < n) ? reinterpret_cast<const float *>(P.prior)[v] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) ridx[i][t] = ridx_tab[(i * 3 + t) * 32 + lane];
+    }
+#pragma unroll
+    for (int i = 0; i < CPL; ++i) {
+        cvalid[i] = (lane + 32 * i) < m;
+#pragma unroll
+        for (int k = 0; k < RW; ++k) vidx[i][k] = vidx_tab[(i * RW + k) * 32 + lane];
+    }
+    Rbuf[ZERO_ROW * 32 + lane] = 0.f;
+
+    const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
+    const int max_iter = P.max_iter;
+    unsigned long long iter_sum = 0;
+
+    while (true) {
+        // ---- next shot of this warp ----------------------------------------------------------------
+        unsigned long long s0 = 0;
+        if (lane == 0) s0 = atomicAdd(P.cursor, 1ull);
+        const long long shot = (long long)__shfl_sync(FULL, s0, 0);
+        if (shot >= P.B) break;
+        uint32_t sbit[CPL];                      // syndrome bit of each owned check, moved to the sign-bit position
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) {
+            const uint32_t w = P.synd[(size_t)shot * WMS + i];
+            sbit[i] = ((w >> lane) & 1u) << 31;
+        }
+        // Q = where(mask, prior, 0) (decoding.py:21): publish the priors, gather them along the edges
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) Vbuf[i * 32 + lane] = prior[i] + 0.f;
+        __syncwarp();
+        float Q[CPL][RW];
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+#pragma unroll
+            for (int k = 0; k < RW; ++k) Q[i][k] = ldb(Vbuf, vidx[i][k]);
+
+        int iter = 0;
+        bool conv = false;
+        for (;; ++iter) {
+            // ================= horizontal step (lane-local) ========================================
+            float R[CPL][RW];
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                uint32_t sg = sbit[i];
+#pragma unroll
+                for (int k = 0; k < RW; ++k) sg ^= __float_as_uint(Q[i][k]);
+                sg &= 0x80000000u;
+                float min1, min2;
+                bpw_two_smallest<RW>(Q[i], min1, min2);
+                const float am1 = __fmul_rn(alpha, min1), am2 = __fmul_rn(alpha, min2);                // :55 (alpha * magnitude)
+#pragma unroll
+                for (int k = 0; k < RW; ++k) {
+                    const float mag = (fabsf(Q[i][k]) == min1) ? am2 : am1;                          // decoding.py:51-53
+                    const float r = __uint_as_float(__float_as_uint(mag) ^ ((sg ^ __float_as_uint(Q[i][k])) & 0x80000000u));
+                    R[i][k] = r;           // (padding check slots produce garbage that no variable ever reads)
+                    Rbuf[(i * RW + k) * 32 + lane] = r;
+                }
+            }
+            __syncwarp();
+
+            // ================= vertical step: posteriors of the owned variables =====================
+            const bool last = (iter == max_iter - 1);
+            const bool wr_llr = (P.llr != nullptr) && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && last));
+            auto var_pass = [&](auto idx_of) {
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const float r0 = ldb(Rbuf, idx_of(i, 0)), r1 = ldb(Rbuf, idx_of(i, 1)), r2 = ldb(Rbuf, idx_of(i, 2));
+                    const float val = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);          // :61-62
+                    Vbuf[i * 32 + lane] = val;
+                    if (wr_llr && lane + 32 * i < n) reinterpret_cast<float *>(P.llr)[(size_t)shot * n + lane + 32 * i] = val;
+                }
+            };
+            if (TWO && iter == 0)
+                var_pass([&](int i, int t) { return __ldg(ridx0_tab + (i * 3 + t) * 32 + lane); });
+            else
+                var_pass([&](int i, int t) { return ridx[i][t]; });
+            __syncwarp();
+
+            // ================= Q update in registers + syndrome of the hard decision =================
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) {
+                uint32_t par = sbit[i];
+#pragma unroll
+                for (int k = 0; k < RW; ++k) {
+                    const float val = ldb(Vbuf, vidx[i][k]);
+                    par ^= __float_as_uint(val);            // sign bit == hard decision (a float sum is never -0.0 here)
+                    float qn = __fsub_rn(val, R[i][k]);                                           // :63
+                    qn = bp_damp(damp, qn, omd, Q[i][k]);                                         // :65
+                    qn = fminf(fmaxf(qn, -clipv), clipv);                                         // :66
+                    Q[i][k] = qn;
+                }
+                ok = ok && (!cvalid[i] || !(par & 0x80000000u));
+            }
+            conv = __all_sync(FULL, ok);
+            if (conv || last) break;
+        }
+
+        // ---- retire the shot: hard decision = sign of the posteriors still in the buffer ----------------
+        uint32_t myw = 0;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const uint32_t w = __ballot_sync(FULL, (lane + 32 * i < n) && (Vbuf[i * 32 + lane] < 0.f));
+            if (lane == i) myw = w;
+        }
+        if (lane < WN) P.hard[(size_t)shot * WN + lane] = myw;
+        if (lane == 0) {
+            P.conv[shot] = conv ? 1 : 0;
+            if (P.iters) P.iters[shot] = iter;
+            if (!conv && P.fail_idx) P.fail_idx[atomicAdd(P.fail_count, 1u)] = (int32_t)shot;
+            iter_sum += (unsigned long long)(iter + 1);
+        }
+    }
+    if (P.iter_total && lane == 0 && iter_sum) atomicAdd(P.iter_total, iter_sum);
+}
+
+}  // namespace qldpc

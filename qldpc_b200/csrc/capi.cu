@@ -13,6 +13,7 @@
 #include "../../include/qldpc_b200.h"
 #include "bp_kernel.cuh"
 #include "bp_tiled_kernel.cuh"
+#include "bp_warp_kernel.cuh"
 #include "misc_kernels.cuh"
 #include "osd_kernel.cuh"
 #include "osdw_kernel.cuh"
@@ -75,6 +76,8 @@ struct qldpc_code {
     // (float64: the reference's addition order is kept as is), [1]/[2]: positions optimised for TL = 4 / 8 (float32)
     uint32_t *d_vell0[3] = {nullptr, nullptr, nullptr}, *d_vell1[3] = {nullptr, nullptr, nullptr};
     double tiled_conflict_cost[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // modelled wavefronts per shot-iteration: before / after
+    uint32_t *d_wridx = nullptr, *d_wridx0 = nullptr, *d_wvidx = nullptr;              // warp-per-shot kernel: gather tables (byte offsets)
+    bool warp_ok = false;
     bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;
@@ -281,6 +284,35 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
             }
         }
     }
+    // warp-per-shot kernel (bp_warp_kernel.cuh): check c = lane + 32 i, variable v = lane + 32 i
+    std::vector<uint32_t> wridx, wridx0, wvidx;
+    c->warp_ok = c->tiled_ok && ((c->WM == 2 && (c->WN == 3 || c->WN == 4)) || (c->WM == 3 && c->WN == 5) || (c->WM == 5 && c->WN == 9));
+    if (c->warp_ok) {
+        const int RW = 6, CPL = c->WM, VPL = c->WN;
+        wridx.assign((size_t)VPL * 3 * 32, 0u);
+        wridx0.assign((size_t)VPL * 3 * 32, 0u);
+        wvidx.assign((size_t)CPL * RW * 32, 0u);
+        for (int i = 0; i < VPL; ++i)
+            for (int l = 0; l < 32; ++l) {
+                const int v = l + 32 * i;
+                for (int t = 0; t < 3; ++t) {
+                    for (int which = 0; which < 2; ++which) {
+                        uint32_t word = (uint32_t)(CPL * RW) * 32 + l;                   // the zero row
+                        if (v < n) {
+                            const int e = (which ? var_edge1 : var_edge0)[var_ptr[v] + t], cc = edge_check[e], kk = e - row_ptr[cc];
+                            word = (uint32_t)((cc / 32) * RW + kk) * 32 + (cc % 32);
+                        }
+                        (which ? wridx : wridx0)[(size_t)(i * 3 + t) * 32 + l] = 4u * word;
+                    }
+                }
+            }
+        for (int i = 0; i < CPL; ++i)
+            for (int l = 0; l < 32; ++l) {
+                const int cc = l + 32 * i;
+                for (int kk = 0; kk < RW; ++kk)
+                    wvidx[(size_t)(i * RW + kk) * 32 + l] = (cc < m) ? 4u * (uint32_t)col_idx[row_ptr[cc] + kk] : 0u;
+            }
+    }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
     for (int r = 0; r < k; ++r)
         for (int j = 0; j < n; ++j)
@@ -311,6 +343,9 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
     CK(upload(&c->d_colmask, colmask));
     CK(upload(&c->d_Lrows, Lrows));
     CK(upload(&c->d_Hrows, Hrows));
+    CK(upload(&c->d_wridx, wridx));
+    CK(upload(&c->d_wridx0, wridx0));
+    CK(upload(&c->d_wvidx, wvidx));
     for (int ti = 0; ti < 3; ++ti) {
         CK(upload(&c->d_vell0[ti], vell0[ti]));
         CK(upload(&c->d_vell1[ti], vell1[ti]));
@@ -325,6 +360,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     cudaFree(c->d_row_ptr); cudaFree(c->d_col_idx); cudaFree(c->d_var_ptr);
     cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
     for (int ti = 0; ti < 3; ++ti) { cudaFree(c->d_vell0[ti]); cudaFree(c->d_vell1[ti]); }
+    cudaFree(c->d_wridx); cudaFree(c->d_wridx0); cudaFree(c->d_wvidx);
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
                       &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
@@ -343,6 +379,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
 struct BPGeom {
     bool staged;
     int tiled_T;          // 0: thread-per-shot kernels; 4 / 8: lanes per shot of the tiled kernel
+    bool warp_kernel;     // warp-per-shot kernel (messages in registers)
     int shots_per_cta;
     int refill_min;
     int threads, grid;
@@ -360,6 +397,18 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     const bool wm_ok = (c->WM <= 5);
     G->tiled_T = 0;
     G->refill_min = 1;
+    G->warp_kernel = false;
+    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM &&
+        (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
+        G->staged = false;
+        G->warp_kernel = true;
+        G->threads = BPW_WARPS * 32;
+        G->shots_per_cta = BPW_WARPS;
+        G->smem = bp_warp_smem_per_warp(c->WM, c->WN, 6) * BPW_WARPS;
+        G->grid = 0;                 // filled at launch from the occupancy query
+        G->gstate_bytes = 0;
+        return QLDPC_OK;
+    }
     if (cfg->staged == 0 && c->tiled_ok) {
         const bool f32ms = (cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM);   // both lane counts are built for it
         // T lanes per shot; NW warps with NW = 1 (mod T) keeps the check pass bank-conflict free
@@ -421,7 +470,7 @@ extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int3
     bp_geometry(c, cfg, 1ll << 40, &G);
     if (shots_per_cta) *shots_per_cta = G.shots_per_cta;
     if (smem_bytes) *smem_bytes = (int32_t)G.smem;
-    if (staged) *staged = G.staged ? 1 : (G.tiled_T ? 100 + G.tiled_T : 0);
+    if (staged) *staged = G.staged ? 1 : (G.warp_kernel ? 132 : (G.tiled_T ? 100 + G.tiled_T : 0));
     return QLDPC_OK;
 }
 
@@ -492,6 +541,36 @@ static cudaError_t launch_bp_tiled_w(const qldpc_code *c, const BPParams &P, con
     case 5: return launch_bp_tiled_inst<T, VAR, TL, 5>(c, P, G, st);
     default: return cudaErrorInvalidValue;
     }
+}
+
+template <int CPL, int VPL, bool TWO>
+static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    auto kern = bp_warp_kernel<CPL, VPL, 6, TWO>;
+    if (G.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->d_wridx, c->d_wridx0, c->d_wvidx);
+    return cudaGetLastError();
+}
+
+template <int CPL, int VPL>
+static cudaError_t launch_bp_warp_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    return c->two_tables ? launch_bp_warp_inst2<CPL, VPL, true>(c, P, G, st) : launch_bp_warp_inst2<CPL, VPL, false>(c, P, G, st);
+}
+
+static cudaError_t launch_bp_warp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    if (c->WM == 2 && c->WN == 3) return launch_bp_warp_inst<2, 3>(c, P, G, st);
+    if (c->WM == 2 && c->WN == 4) return launch_bp_warp_inst<2, 4>(c, P, G, st);
+    if (c->WM == 3 && c->WN == 5) return launch_bp_warp_inst<3, 5>(c, P, G, st);
+    if (c->WM == 5 && c->WN == 9) return launch_bp_warp_inst<5, 9>(c, P, G, st);
+    return cudaErrorInvalidValue;
 }
 
 static cudaError_t launch_bp_tiled(const qldpc_code *c, const BPParams &P, const BPGeom &G, int precision, int kv, cudaStream_t st)
@@ -565,7 +644,9 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.dump_iter = -1;
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
-    if (G.tiled_T)
+    if (G.warp_kernel)
+        e = launch_bp_warp(c, P, G, st);
+    else if (G.tiled_T)
         e = launch_bp_tiled(c, P, G, cfg->precision, kv, st);
     else if (cfg->precision == 64)
         e = (kv == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
@@ -901,7 +982,7 @@ extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg,
         // same launch path as qldpc_bp_decode_dev, thread-per-shot kernel, with the dump enabled
         BPGeom G;
         qldpc_bp_config cf = *cfg;
-        if (cf.staged == 0) cf.staged = 2;
+        if (cf.staged == 0 || cf.staged == 3) cf.staged = 2;
         bp_geometry(c, &cf, b, &G);
         if (G.staged) CK(c->gstate.reserve(G.gstate_bytes));
         CK(c->ctrl.reserve(sizeof(Ctrl)));

@@ -264,7 +264,12 @@ def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
     prior = _prior(p, n)
     kw = dict(variant="min_sum", max_iter=60, alpha=0.8, damping=0.7, clip=25.0, precision=32)
     ref = code.bp_decode_batch(synd, prior, staged=2, **kw)
-    assert code.geometry(code.config(**kw))["kernel"] == "tiled"
+    assert code.geometry(code.config(**kw))["kernel"] in ("tiled", "warp_per_shot")
+    assert code.geometry(code.config(lanes_per_shot=8, **kw))["kernel"] == "tiled"
+    assert code.geometry(code.config(staged=3, **kw))["kernel"] == "warp_per_shot"
+    got = code.bp_decode_batch(synd, prior, staged=3, **kw)          # warp-per-shot kernel, messages in registers
+    for x, y in zip(got, ref):
+        assert np.array_equal(x, y), (stem, "warp_per_shot")
     for T in (4, 8):
         for rmin in (0, 1, 32 // T):
             got = code.bp_decode_batch(synd, prior, lanes_per_shot=T, refill_min=rmin, **kw)
@@ -287,9 +292,10 @@ def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
     # non-uniform prior and default parameters (alpha = damping = 1)
     pr = rng.uniform(1.5, 4.0, n)
     a = code.bp_decode_batch(synd[:800], pr, "min_sum", 30, precision=32, staged=2)
-    b = code.bp_decode_batch(synd[:800], pr, "min_sum", 30, precision=32)
-    for x, y in zip(a, b):
-        assert np.array_equal(x, y)
+    for kw2 in (dict(), dict(staged=3), dict(lanes_per_shot=8), dict(lanes_per_shot=4)):
+        b = code.bp_decode_batch(synd[:800], pr, "min_sum", 30, precision=32, **kw2)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), kw2
 
 
 def test_spacetime_bp_staged(spacetime_golden):

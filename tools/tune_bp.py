@@ -11,7 +11,7 @@ ap.add_argument("--code", default="[[144, 12, 12]]")
 ap.add_argument("--p", type=float, default=0.05)
 ap.add_argument("--shots", type=int, default=4_000_000)
 ap.add_argument("--max-iter", type=int, default=100)
-ap.add_argument("--configs", default="0:0:0,0:4:1,0:4:2,0:4:4,0:8:1,0:8:2,2:0:0")
+ap.add_argument("--configs", default="0:0:0,3:0:0,0:4:1,0:8:1,0:8:2,2:0:0")
 args = ap.parse_args()
 d = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "qldpc_b200", "data", "codes", args.code + ".npz"))
 H = d["Hx"]

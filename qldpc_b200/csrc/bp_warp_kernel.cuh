@@ -35,30 +35,13 @@ __device__ __forceinline__ float ldb(const float *base, uint32_t byte_off)
 // per-warp shared memory: R buffer [CPL*RW][32] + one zero row [32] + posterior buffer [VPL][32]
 __host__ __device__ inline size_t bp_warp_smem_per_warp(int CPL, int VPL, int RW) { return 4 * (size_t)32 * (CPL * RW + 1 + VPL); }
 
-// min1 / min2 (smallest and second smallest, as values) of |q[0..RW)|: pairwise sort, then min1 = min of the pair
-// minima, min2 = min(median of the pair minima, min of the pair maxima).  13 FMNMX for RW = 6 instead of 18.
-template <int RW>
-__device__ __forceinline__ void bpw_two_smallest(const float (&q)[RW], float &min1, float &min2)
+// FMNMX.XORSIGN: magnitude min(|a|, |b|), sign = sign(a) ^ sign(b).  A chain of these over a set of messages yields
+// the min-sum check output (product of the signs, minimum of the magnitudes) in ONE ALU-pipe instruction per message.
+__device__ __forceinline__ float bpw_xmin(float a, float b)
 {
-    if constexpr (RW == 6) {
-        const float a0 = fabsf(q[0]), a1 = fabsf(q[1]), a2 = fabsf(q[2]), a3 = fabsf(q[3]), a4 = fabsf(q[4]), a5 = fabsf(q[5]);
-        const float l0 = fminf(a0, a1), h0 = fmaxf(a0, a1);
-        const float l1 = fminf(a2, a3), h1 = fmaxf(a2, a3);
-        const float l2 = fminf(a4, a5), h2 = fmaxf(a4, a5);
-        const float lmin01 = fminf(l0, l1), lmax01 = fmaxf(l0, l1);
-        min1 = fminf(lmin01, l2);
-        const float lmed = fmaxf(lmin01, fminf(lmax01, l2));
-        min2 = fminf(lmed, fminf(fminf(h0, h1), h2));
-    } else {
-        min1 = CUDART_INF_F; min2 = CUDART_INF_F;
-#pragma unroll
-        for (int k = 0; k < RW; ++k) {
-            const float a = fabsf(q[k]);
-            const float t = fmaxf(min1, a);
-            min1 = fminf(min1, a);
-            min2 = fminf(min2, t);
-        }
-    }
+    float d;
+    asm("min.xorsign.abs.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
 }
 
 // Tables (global, built by the host, natural labelling c = lane + 32 i, v = lane + 32 i):
@@ -110,10 +93,13 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
         const long long shot = (long long)__shfl_sync(FULL, s0, 0);
         if (shot >= P.B) break;
         uint32_t sbit[CPL];                      // syndrome bit of each owned check, moved to the sign-bit position
+        float salpha[CPL], sone[CPL];            // (-1)^s * alpha, (-1)^s
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             const uint32_t w = P.synd[(size_t)shot * WMS + i];
             sbit[i] = ((w >> lane) & 1u) << 31;
+            salpha[i] = __uint_as_float(__float_as_uint(alpha) ^ sbit[i]);
+            sone[i] = __uint_as_float(0x3f800000u ^ sbit[i]);
         }
         // Q = where(mask, prior, 0) (decoding.py:21): publish the priors, gather them along the edges
         __syncwarp();
@@ -130,20 +116,23 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
         bool conv = false;
         for (;; ++iter) {
             // ================= horizontal step (lane-local) ========================================
+            // R[k] = alpha * (-1)^s * prod_{j != k} sign(Q[j]) * min_{j != k} |Q[j]| (decoding.py:41-55).  "All but k" is
+            // prefix (x) suffix of the xorsign-min; the minimum over the others IS min1, or min2 at the arg-min (ties
+            // included), so the values equal the reference's where(|Q| == min1, min2, min1) selection exactly.
             float R[CPL][RW];
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                uint32_t sg = sbit[i];
+                float pre[RW], suf[RW];
+                pre[1] = Q[i][0];
+                suf[RW - 2] = Q[i][RW - 1];
 #pragma unroll
-                for (int k = 0; k < RW; ++k) sg ^= __float_as_uint(Q[i][k]);
-                sg &= 0x80000000u;
-                float min1, min2;
-                bpw_two_smallest<RW>(Q[i], min1, min2);
-                const float am1 = __fmul_rn(alpha, min1), am2 = __fmul_rn(alpha, min2);                // :55 (alpha * magnitude)
+                for (int k = 2; k < RW; ++k) pre[k] = bpw_xmin(pre[k - 1], Q[i][k - 1]);
+#pragma unroll
+                for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_xmin(suf[k + 1], Q[i][k + 1]);
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
-                    const float mag = (fabsf(Q[i][k]) == min1) ? am2 : am1;                          // decoding.py:51-53
-                    const float r = __uint_as_float(__float_as_uint(mag) ^ ((sg ^ __float_as_uint(Q[i][k])) & 0x80000000u));
+                    const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
+                    const float r = __fmul_rn(o, salpha[i]);       // (+-alpha) * (+-magnitude): same rounding as alpha * magnitude
                     R[i][k] = r;           // (padding check slots produce garbage that no variable ever reads)
                     Rbuf[(i * RW + k) * 32 + lane] = r;
                 }
@@ -152,14 +141,12 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
 
             // ================= vertical step: posteriors of the owned variables =====================
             const bool last = (iter == max_iter - 1);
-            const bool wr_llr = (P.llr != nullptr) && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && last));
             auto var_pass = [&](auto idx_of) {
 #pragma unroll
                 for (int i = 0; i < VPL; ++i) {
                     const float r0 = ldb(Rbuf, idx_of(i, 0)), r1 = ldb(Rbuf, idx_of(i, 1)), r2 = ldb(Rbuf, idx_of(i, 2));
                     const float val = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);          // :61-62
                     Vbuf[i * 32 + lane] = val;
-                    if (wr_llr && lane + 32 * i < n) reinterpret_cast<float *>(P.llr)[(size_t)shot * n + lane + 32 * i] = val;
                 }
             };
             if (TWO && iter == 0)
@@ -169,20 +156,22 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
             __syncwarp();
 
             // ================= Q update in registers + syndrome of the hard decision =================
+            // The check is satisfied by the hard decisions iff (-1)^s * prod sign(posterior) > 0: the sign of a float
+            // product is the xor of the operand signs whatever the rounding (no overflow: |posterior| < 2^7).
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                uint32_t par = sbit[i];
+                float par = sone[i];
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
                     const float val = ldb(Vbuf, vidx[i][k]);
-                    par ^= __float_as_uint(val);            // sign bit == hard decision (a float sum is never -0.0 here)
+                    par = __fmul_rn(par, val);
                     float qn = __fsub_rn(val, R[i][k]);                                           // :63
                     qn = bp_damp(damp, qn, omd, Q[i][k]);                                         // :65
                     qn = fminf(fmaxf(qn, -clipv), clipv);                                         // :66
                     Q[i][k] = qn;
                 }
-                ok = ok && (!cvalid[i] || !(par & 0x80000000u));
+                ok = ok && (!cvalid[i] || (int)__float_as_uint(par) >= 0);
             }
             conv = __all_sync(FULL, ok);
             if (conv || last) break;
@@ -194,6 +183,8 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
         for (int i = 0; i < VPL; ++i) {
             const uint32_t w = __ballot_sync(FULL, (lane + 32 * i < n) && (Vbuf[i * 32 + lane] < 0.f));
             if (lane == i) myw = w;
+            if (P.llr != nullptr && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && !conv)) && lane + 32 * i < n)
+                reinterpret_cast<float *>(P.llr)[(size_t)shot * n + lane + 32 * i] = Vbuf[i * 32 + lane];
         }
         if (lane < WN) P.hard[(size_t)shot * WN + lane] = myw;
         if (lane == 0) {

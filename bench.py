@@ -161,6 +161,8 @@ def main():
     prior = np.full(n, np.log((1 - P_ERR) / P_ERR))
     prior_p = prior.ctypes.data_as(ctypes.c_void_p)
     geom = code.geometry(cfg)
+    if geom["kernel"] == "warp_per_shot":      # one-time set-up: bank-conflict search for the kernel's lane labelling
+        geom["warp_layout_gather_wavefronts"] = code.tune_warp_layout(int(os.environ.get("QLDPC_BENCH_TUNE_STEPS", 1_000_000)))
     B = args.shots
     CH = 1 << 24          # shots per BP launch (LLR hand-off buffer: 4n bytes per shot)
     i32 = torch.int32
@@ -353,7 +355,8 @@ def main():
         achieved = iters_exec * A / bp_s
         # packed syndrome in; packed correction + flag + iteration out; float32 posterior row for the BP failures (OSD input)
         hbm_bytes_per_shot = 4 * WM + 4 * WN + 1 + 4 + 4 * n * cd["bp_failed"] / max(1, cd["shots"])
-        kname = ("bp_tiled_kernel<T=%d,WM=%d,RW=6>" % (geom["lanes_per_shot"], WM)) if geom["kernel"] == "tiled" else "bp_decode_kernel<float,MIN_SUM>"
+        kname = {"tiled": "bp_tiled_kernel<T=%d,WM=%d,RW=6>" % (geom["lanes_per_shot"], WM),
+                 "warp_per_shot": "bp_warp_kernel<CPL=%d,VPL=%d,RW=6>" % (WM, WN)}.get(geom["kernel"], "bp_decode_kernel<float,MIN_SUM>")
         roofline = {"bound": "alu", "kernel": kname,
                     "achieved": achieved / 1e12, "peak": peak_laneops / 1e12, "unit": "Tlane-op/s",
                     "frac": achieved / peak_laneops,
@@ -366,7 +369,7 @@ def main():
                             "peak_gbs": peaks.get("hbm_gbs"), "note": "on-chip path: HBM traffic is negligible by design"},
                     "traffic": None}
         try:   # DRAM bytes per launch from the committed ncu capture of the same kernel (per shot x shots per launch)
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r1e_bp_ncu.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1h_bp_ncu.json" if geom["kernel"] == "warp_per_shot" else "r1e_bp_ncu.json")))
             roofline["traffic"] = cap["dram_bytes_per_shot"] * min(B, CH)
             roofline["ncu_capture"] = {k: cap[k] for k in ("source", "issue_slots_busy_pct", "alu_pipe_pct", "lsu_pipe_pct",
                                                             "shared_wavefronts_pct_of_peak", "ipc_per_sm", "dram_bytes_per_shot")}

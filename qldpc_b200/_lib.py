@@ -46,6 +46,7 @@ def lib():
         "qldpc_code_destroy": ([c_vp], None),
         "qldpc_bp_geometry": ([c_vp, P(BPConfig), P(c_i32), P(c_i32), P(c_i32)], ctypes.c_int),
         "qldpc_tiled_conflict_model": ([c_vp, c_i32, P(c_dbl), P(c_dbl)], ctypes.c_int),
+        "qldpc_warp_layout_tune": ([c_vp, c_i64, P(c_i32)], ctypes.c_int),
         "qldpc_words_m": ([c_vp], ctypes.c_int),
         "qldpc_words_n": ([c_vp], ctypes.c_int),
         "qldpc_bp_decode_host": ([c_vp, P(BPConfig), c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp], ctypes.c_int),
@@ -76,7 +77,7 @@ def lib():
 
 
 EXPORTED = ["qldpc_last_error", "qldpc_version", "qldpc_device_count", "qldpc_code_create", "qldpc_code_destroy",
-            "qldpc_bp_geometry", "qldpc_tiled_conflict_model", "qldpc_words_m", "qldpc_words_n", "qldpc_bp_decode_host", "qldpc_bp_messages_host", "qldpc_osd_decode_host",
+            "qldpc_bp_geometry", "qldpc_tiled_conflict_model", "qldpc_warp_layout_tune", "qldpc_words_m", "qldpc_words_n", "qldpc_bp_decode_host", "qldpc_bp_messages_host", "qldpc_osd_decode_host",
             "qldpc_bposd_decode_host", "qldpc_bposd_decode_host_packed", "qldpc_check_host", "qldpc_syndrome_host", "qldpc_syndrome_dev", "qldpc_sample_host", "qldpc_mc_sweep", "qldpc_bp_llr_histogram", "qldpc_bp_decode_dev",
             "qldpc_osd_decode_dev", "qldpc_check_dev", "qldpc_sample_dev", "qldpc_bposd_decode_dev",
             "qldpc_pack_bits_dev", "qldpc_unpack_bits_dev"]

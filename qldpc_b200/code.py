@@ -104,6 +104,14 @@ class Code:
                     lanes_per_shot=(kind - 100 if kind >= 100 else 1),
                     kernel=('hbm_staged' if kind == 1 else 'warp_per_shot' if kind == 132 else 'tiled' if kind >= 100 else 'thread_per_shot'))
 
+    def tune_warp_layout(self, steps=1_000_000):
+        """Bank-conflict search for the warp-per-shot kernel's labelling (one-time set-up, ~2.6 us per step; results
+        of the kernel are unchanged).  steps < 0: back to the natural labelling; 0: report only.
+        -> dict(natural, current, floor) modelled gather wavefronts per shot-iteration."""
+        cost = (ctypes.c_int32 * 3)()
+        _lib.check(_lib.lib().qldpc_warp_layout_tune(self._h, int(steps), cost))
+        return dict(natural=cost[0], current=cost[1], floor=cost[2])
+
     def tiled_conflict_model(self, lanes_per_shot=8):
         """(before, after): modelled shared-memory wavefronts per shot-iteration of the tiled kernel's variable pass with
         natural / optimised variable order."""

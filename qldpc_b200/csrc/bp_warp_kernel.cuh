@@ -44,18 +44,24 @@ __device__ __forceinline__ float bpw_xmin(float a, float b)
     return d;
 }
 
-// Tables (global, built by the host, natural labelling c = lane + 32 i, v = lane + 32 i):
-//   ridx  [VPL*3][32]  byte offset in the R buffer of the t-th ADDED message of variable (i, lane) in iterations >= 1
-//                      (the zero row for padding);  ridx0: the same for iteration 0 (read only when TWO: the
+// Tables (global, built by the host -- bp_warp_layout.h -- for a labelling "position = slot * 32 + lane" of the checks
+// and of the variables that it is free to choose):
+//   ridx  [VPL*3][32]  byte offset in the R buffer of the t-th ADDED message of the variable at (i, lane) in iterations
+//                      >= 1 (the zero row for padding);  ridx0: the same for iteration 0 (read only when TWO: the
 //                      reference's NumPy reduction order differs between iteration 0 and the later ones, graph.py)
-//   vidx  [CPL*RW][32] byte offset in the posterior buffer of the variable of edge k of check (i, lane); 0 for padding
+//   vidx  [CPL*RW][32] byte offset in the posterior buffer of the variable of edge slot k of the check at (i, lane)
+//   cinfo [CPL][32]    index of the check at (i, lane) in H, 0xffffffff for padding
+//   vorig [VPL][32]    index of the variable at (i, lane) in H, 0xffffffff for padding
+//   vpos  [VPL][32]    byte offset in the posterior buffer of variable 32 i + lane of H
+struct BPWarpTables {
+    const uint32_t *ridx, *ridx0, *vidx, *cinfo, *vorig, *vpos;
+};
+
 template <int CPL, int VPL, int RW, bool TWO>
 __global__ void __launch_bounds__(BPW_WARPS * 32, (CPL * RW + VPL * 4 > 44) ? 1 : 2)
-bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const uint32_t *__restrict__ ridx0_tab,
-               const uint32_t *__restrict__ vidx_tab)
+bp_warp_kernel(const BPParams P, const BPWarpTables W)
 {
-    constexpr int WMS = CPL;
-    const int m = P.g.m, n = P.g.n, WN = P.g.WN;
+    const int n = P.g.n, WN = P.g.WN, WM = P.g.WM;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -64,21 +70,20 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
     constexpr int ZERO_ROW = CPL * RW;
 
     // ---- per-lane tables into registers (BYTE offsets into the R / posterior buffers) -------------
-    uint32_t ridx[VPL][3], vidx[CPL][RW];
+    uint32_t ridx[VPL][3], vidx[CPL][RW], cinfo[CPL];
     float prior[VPL];
-    bool cvalid[CPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        prior[i] = (v < n) ? reinterpret_cast<const float *>(P.prior)[v] : 0.f;
+        const uint32_t v = W.vorig[i * 32 + lane];
+        prior[i] = (v != 0xffffffffu) ? reinterpret_cast<const float *>(P.prior)[v] + 0.f : 0.f;    // (+ 0: a -0.0 prior becomes +0.0)
 #pragma unroll
-        for (int t = 0; t < 3; ++t) ridx[i][t] = ridx_tab[(i * 3 + t) * 32 + lane];
+        for (int t = 0; t < 3; ++t) ridx[i][t] = W.ridx[(i * 3 + t) * 32 + lane];
     }
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
-        cvalid[i] = (lane + 32 * i) < m;
+        cinfo[i] = W.cinfo[i * 32 + lane];
 #pragma unroll
-        for (int k = 0; k < RW; ++k) vidx[i][k] = vidx_tab[(i * RW + k) * 32 + lane];
+        for (int k = 0; k < RW; ++k) vidx[i][k] = W.vidx[(i * RW + k) * 32 + lane];
     }
     Rbuf[ZERO_ROW * 32 + lane] = 0.f;
 
@@ -93,13 +98,12 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
         const long long shot = (long long)__shfl_sync(FULL, s0, 0);
         if (shot >= P.B) break;
         uint32_t sbit[CPL];                      // syndrome bit of each owned check, moved to the sign-bit position
-        float salpha[CPL], sone[CPL];            // (-1)^s * alpha, (-1)^s
+        float salpha[CPL];                       // (-1)^s * alpha
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-            const uint32_t w = P.synd[(size_t)shot * WMS + i];
-            sbit[i] = ((w >> lane) & 1u) << 31;
+            const uint32_t w = (cinfo[i] != 0xffffffffu) ? P.synd[(size_t)shot * WM + (cinfo[i] >> 5)] : 0u;
+            sbit[i] = ((w >> (cinfo[i] & 31u)) & 1u) << 31;
             salpha[i] = __uint_as_float(__float_as_uint(alpha) ^ sbit[i]);
-            sone[i] = __uint_as_float(0x3f800000u ^ sbit[i]);
         }
         // Q = where(mask, prior, 0) (decoding.py:21): publish the priors, gather them along the edges
         __syncwarp();
@@ -150,41 +154,45 @@ bp_warp_kernel(const BPParams P, const uint32_t *__restrict__ ridx_tab, const ui
                 }
             };
             if (TWO && iter == 0)
-                var_pass([&](int i, int t) { return __ldg(ridx0_tab + (i * 3 + t) * 32 + lane); });
+                var_pass([&](int i, int t) { return __ldg(W.ridx0 + (i * 3 + t) * 32 + lane); });
             else
                 var_pass([&](int i, int t) { return ridx[i][t]; });
             __syncwarp();
 
             // ================= Q update in registers + syndrome of the hard decision =================
-            // The check is satisfied by the hard decisions iff (-1)^s * prod sign(posterior) > 0: the sign of a float
-            // product is the xor of the operand signs whatever the rounding (no overflow: |posterior| < 2^7).
+            // The check is satisfied by the hard decisions iff the xor of the posterior sign bits equals its syndrome bit
+            // (3-input LOP3s: the ALU pipe has room since the check pass moved to FMNMX.XORSIGN).
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
-                float par = sone[i];
+                uint32_t par = sbit[i];
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
                     const float val = ldb(Vbuf, vidx[i][k]);
-                    par = __fmul_rn(par, val);
+                    par ^= __float_as_uint(val);            // sign bit == hard decision (a sum with a non-zero prior is never -0.0)
                     float qn = __fsub_rn(val, R[i][k]);                                           // :63
                     qn = bp_damp(damp, qn, omd, Q[i][k]);                                         // :65
                     qn = fminf(fmaxf(qn, -clipv), clipv);                                         // :66
                     Q[i][k] = qn;
                 }
-                ok = ok && (!cvalid[i] || (int)__float_as_uint(par) >= 0);
+                ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);
             }
             conv = __all_sync(FULL, ok);
             if (conv || last) break;
         }
 
-        // ---- retire the shot: hard decision = sign of the posteriors still in the buffer ----------------
+        // ---- retire the shot: hard decision = sign of the posteriors still in the buffer, in the order of H ----
         uint32_t myw = 0;
+        const bool wr_llr = P.llr != nullptr && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && !conv));
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
-            const uint32_t w = __ballot_sync(FULL, (lane + 32 * i < n) && (Vbuf[i * 32 + lane] < 0.f));
-            if (lane == i) myw = w;
-            if (P.llr != nullptr && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && !conv)) && lane + 32 * i < n)
-                reinterpret_cast<float *>(P.llr)[(size_t)shot * n + lane + 32 * i] = Vbuf[i * 32 + lane];
+            if (i < WN) {                          // (uniform) VPL >= WN: a labelling may use more slots than ceil(n / 32)
+                const bool valid = lane + 32 * i < n;
+                const float val = valid ? ldb(Vbuf, __ldg(W.vpos + i * 32 + lane)) : 0.f;
+                const uint32_t w = __ballot_sync(FULL, valid && (val < 0.f));
+                if (lane == i) myw = w;
+                if (wr_llr && valid) reinterpret_cast<float *>(P.llr)[(size_t)shot * n + lane + 32 * i] = val;
+            }
         }
         if (lane < WN) P.hard[(size_t)shot * WN + lane] = myw;
         if (lane == 0) {

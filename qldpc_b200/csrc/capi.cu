@@ -14,6 +14,7 @@
 #include "bp_kernel.cuh"
 #include "bp_tiled_kernel.cuh"
 #include "bp_warp_kernel.cuh"
+#include "bp_warp_layout.h"
 #include "misc_kernels.cuh"
 #include "osd_kernel.cuh"
 #include "osdw_kernel.cuh"
@@ -76,7 +77,10 @@ struct qldpc_code {
     // (float64: the reference's addition order is kept as is), [1]/[2]: positions optimised for TL = 4 / 8 (float32)
     uint32_t *d_vell0[3] = {nullptr, nullptr, nullptr}, *d_vell1[3] = {nullptr, nullptr, nullptr};
     double tiled_conflict_cost[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // modelled wavefronts per shot-iteration: before / after
-    uint32_t *d_wridx = nullptr, *d_wridx0 = nullptr, *d_wvidx = nullptr;              // warp-per-shot kernel: gather tables (byte offsets)
+    uint32_t *d_wtab = nullptr;                                    // warp-per-shot kernel: the six tables of BPWarpTables, back to back
+    BPWarpTables wtab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    WarpLayoutBuilder *wlayout = nullptr;                          // labelling of checks / variables / edge slots (host)
+    int warp_cost[3] = {0, 0, 0};                                  // gather wavefronts per shot-iteration: natural, current, floor
     bool warp_ok = false;
     bool tiled_ok = false;
     std::vector<double> prior_cache;
@@ -142,6 +146,21 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
         return rc;
     }
     *out = c;
+    return QLDPC_OK;
+}
+
+// (re)builds the device tables of the warp-per-shot kernel from c->wlayout; the device must be idle
+static int warp_tables_upload(qldpc_code *c)
+{
+    const WarpLayout L = c->wlayout->tables();
+    std::vector<uint32_t> all;
+    size_t off[6];
+    const std::vector<uint32_t> *parts[6] = {&L.ridx, &L.ridx0, &L.vidx, &L.cinfo, &L.vorig, &L.vpos};
+    for (int i = 0; i < 6; ++i) { off[i] = all.size(); all.insert(all.end(), parts[i]->begin(), parts[i]->end()); }
+    if (!c->d_wtab) CK(cudaMalloc(&c->d_wtab, all.size() * sizeof(uint32_t)));
+    CK(cudaMemcpy(c->d_wtab, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    c->wtab = BPWarpTables{c->d_wtab + off[0], c->d_wtab + off[1], c->d_wtab + off[2], c->d_wtab + off[3], c->d_wtab + off[4], c->d_wtab + off[5]};
+    c->warp_cost[0] = L.cost_natural; c->warp_cost[1] = L.cost; c->warp_cost[2] = L.floor;
     return QLDPC_OK;
 }
 
@@ -284,34 +303,12 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
             }
         }
     }
-    // warp-per-shot kernel (bp_warp_kernel.cuh): check c = lane + 32 i, variable v = lane + 32 i
-    std::vector<uint32_t> wridx, wridx0, wvidx;
+    // warp-per-shot kernel (bp_warp_kernel.cuh): labelling and gather tables (bp_warp_layout.h)
     c->warp_ok = c->tiled_ok && ((c->WM == 2 && (c->WN == 3 || c->WN == 4)) || (c->WM == 3 && c->WN == 5) || (c->WM == 5 && c->WN == 9));
     if (c->warp_ok) {
-        const int RW = 6, CPL = c->WM, VPL = c->WN;
-        wridx.assign((size_t)VPL * 3 * 32, 0u);
-        wridx0.assign((size_t)VPL * 3 * 32, 0u);
-        wvidx.assign((size_t)CPL * RW * 32, 0u);
-        for (int i = 0; i < VPL; ++i)
-            for (int l = 0; l < 32; ++l) {
-                const int v = l + 32 * i;
-                for (int t = 0; t < 3; ++t) {
-                    for (int which = 0; which < 2; ++which) {
-                        uint32_t word = (uint32_t)(CPL * RW) * 32 + l;                   // the zero row
-                        if (v < n) {
-                            const int e = (which ? var_edge1 : var_edge0)[var_ptr[v] + t], cc = edge_check[e], kk = e - row_ptr[cc];
-                            word = (uint32_t)((cc / 32) * RW + kk) * 32 + (cc % 32);
-                        }
-                        (which ? wridx : wridx0)[(size_t)(i * 3 + t) * 32 + l] = 4u * word;
-                    }
-                }
-            }
-        for (int i = 0; i < CPL; ++i)
-            for (int l = 0; l < 32; ++l) {
-                const int cc = l + 32 * i;
-                for (int kk = 0; kk < RW; ++kk)
-                    wvidx[(size_t)(i * RW + kk) * 32 + l] = (cc < m) ? 4u * (uint32_t)col_idx[row_ptr[cc] + kk] : 0u;
-            }
+        c->wlayout = new WarpLayoutBuilder(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 6);
+        if (const char *ev = getenv("QLDPC_WARP_TUNE_STEPS")) c->wlayout->anneal(atoll(ev));
+        if (int rc = warp_tables_upload(c)) return rc;
     }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
     for (int r = 0; r < k; ++r)
@@ -343,9 +340,6 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
     CK(upload(&c->d_colmask, colmask));
     CK(upload(&c->d_Lrows, Lrows));
     CK(upload(&c->d_Hrows, Hrows));
-    CK(upload(&c->d_wridx, wridx));
-    CK(upload(&c->d_wridx0, wridx0));
-    CK(upload(&c->d_wvidx, wvidx));
     for (int ti = 0; ti < 3; ++ti) {
         CK(upload(&c->d_vell0[ti], vell0[ti]));
         CK(upload(&c->d_vell1[ti], vell1[ti]));
@@ -360,7 +354,8 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     cudaFree(c->d_row_ptr); cudaFree(c->d_col_idx); cudaFree(c->d_var_ptr);
     cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
     for (int ti = 0; ti < 3; ++ti) { cudaFree(c->d_vell0[ti]); cudaFree(c->d_vell1[ti]); }
-    cudaFree(c->d_wridx); cudaFree(c->d_wridx0); cudaFree(c->d_wvidx);
+    cudaFree(c->d_wtab);
+    delete c->wlayout;
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
                       &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
@@ -474,6 +469,19 @@ extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int3
     return QLDPC_OK;
 }
 
+extern "C" int qldpc_warp_layout_tune(qldpc_code *c, int64_t steps, int32_t *cost)
+{
+    if (!c) return fail(QLDPC_ERR_ARG, "qldpc_warp_layout_tune: null code");
+    if (!c->warp_ok) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_warp_layout_tune: the warp-per-shot kernel does not apply to this code");
+    CK(cudaDeviceSynchronize());
+    if (steps < 0) c->wlayout->natural();
+    if (steps > 0) c->wlayout->anneal(steps);
+    if (steps != 0)
+        if (int rc = warp_tables_upload(c)) return rc;
+    if (cost) { cost[0] = c->warp_cost[0]; cost[1] = c->warp_cost[1]; cost[2] = c->warp_cost[2]; }
+    return QLDPC_OK;
+}
+
 extern "C" int qldpc_tiled_conflict_model(qldpc_code *c, int32_t lanes_per_shot, double *before, double *after)
 {
     if (!c || !c->tiled_ok) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_tiled_conflict_model: the tiled kernel does not apply to this code");
@@ -554,7 +562,7 @@ static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, 
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
     const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->d_wridx, c->d_wridx0, c->d_wvidx);
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
     return cudaGetLastError();
 }
 

@@ -161,8 +161,8 @@ def main():
     prior = np.full(n, np.log((1 - P_ERR) / P_ERR))
     prior_p = prior.ctypes.data_as(ctypes.c_void_p)
     geom = code.geometry(cfg)
-    if geom["kernel"] == "warp_per_shot":      # one-time set-up: bank-conflict search for the kernel's lane labelling
-        geom["warp_layout_gather_wavefronts"] = code.tune_warp_layout(int(os.environ.get("QLDPC_BENCH_TUNE_STEPS", 1_000_000)))
+    if geom["kernel"] == "warp_per_shot":      # modelled scatter + gather wavefronts per shot-iteration of the lane labelling
+        geom["warp_layout_wavefronts"] = code.tune_warp_layout(0)
     B = args.shots
     CH = 1 << 24          # shots per BP launch (LLR hand-off buffer: 4n bytes per shot)
     i32 = torch.int32

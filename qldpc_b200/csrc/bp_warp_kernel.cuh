@@ -4,18 +4,19 @@
 // Same arithmetic, in the same order, as bp_decode_kernel<float, VAR_MIN_SUM> / bp_tiled_kernel (reference
 // rework/decoding.py:5-75): results are bit-identical.  Different mapping, chosen after the ncu profile of the tiled
 // kernel (profiles/r1e: shared-memory wavefronts at 84 % of peak, issue slots 76 % busy):
-//   * lane l owns checks c = l + 32 i (i < CPL) and keeps their RW incoming messages Q[i][k] in registers, so the whole
-//     check pass (sign parity, min1/min2, the RW outgoing messages R) is lane-local: no loads, no index arithmetic;
-//   * R is published to a per-warp shared-memory buffer in the owner's own bank (conflict-free stores);
-//   * lane l also owns variables v = l + 32 i (i < VPL): it GATHERS its 3 incoming R (indices held in registers, loaded
-//     once per kernel), adds them in the reference's order, adds the prior, and publishes the posterior (conflict-free
-//     store); the hard-decision word i of the shot is simply __ballot_sync(posterior < 0);
+//   * a lane owns up to CPL checks and keeps their RW incoming messages Q[i][k] in registers, so the whole check pass
+//     is lane-local: a prefix/suffix chain of FMNMX.XORSIGN (min of magnitudes, xor of signs in one instruction) gives
+//     the RW outgoing messages R, which the lane SCATTERS into the columns of their destination variables
+//     (plane t = position of the message in the variable's addition order);
+//   * a lane also owns up to VPL variables: it reads its own column (three planes, conflict-free, no index), adds in
+//     the reference's order, adds the prior and publishes the posterior;
 //   * each check-owner lane gathers the posteriors of its RW variables, updates Q in registers (damping against the Q it
-//     still holds, clip), and accumulates the parity of the hard decisions of its check from the sign bits it just read:
-//     the syndrome test of the hard decision is lane-local, followed by one __all_sync.
-// Per shot-iteration this needs ~45 shared-memory words per lane-row instead of ~150 wavefronts per shot in the tiled
-// kernel and about 30 % fewer instructions (no table reads, no address arithmetic, no divergence: a warp decodes exactly
-// one shot, retires it and fetches the next one from the global cursor).
+//     still holds, clip) and xors the sign bits it just read: the syndrome test of the hard decision is lane-local,
+//     followed by one __all_sync.
+// Which lane owns what, and in which register slot an edge sits, is chosen by the host (bp_warp_layout.h) so that
+// scatter and gather are bank-conflict free: CPL*RW + 4*VPL + CPL*RW wavefronts per shot-iteration (56 for
+// [[144,12,12]]) and ~240 warp-instructions, against ~150 wavefronts per shot and ~560 instructions in the tiled kernel.
+// A warp decodes exactly one shot, retires it and fetches the next one from the global cursor: no divergence.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -32,8 +33,13 @@ __device__ __forceinline__ float ldb(const float *base, uint32_t byte_off)
     return *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(base) + byte_off);
 }
 
-// per-warp shared memory: R buffer [CPL*RW][32] + one zero row [32] + posterior buffer [VPL][32]
-__host__ __device__ inline size_t bp_warp_smem_per_warp(int CPL, int VPL, int RW) { return 4 * (size_t)32 * (CPL * RW + 1 + VPL); }
+// per-warp shared memory: message planes [3][VPL][32] + one dump row [32] (padding lanes) + posteriors [VPL][32]
+__host__ __device__ inline size_t bp_warp_smem_per_warp(int VPL) { return 4 * (size_t)32 * (4 * VPL + 1); }
+
+__device__ __forceinline__ void stb(float *base, uint32_t byte_off, float v)
+{
+    *reinterpret_cast<float *>(reinterpret_cast<unsigned char *>(base) + byte_off) = v;
+}
 
 // FMNMX.XORSIGN: magnitude min(|a|, |b|), sign = sign(a) ^ sign(b).  A chain of these over a set of messages yields
 // the min-sum check output (product of the signs, minimum of the magnitudes) in ONE ALU-pipe instruction per message.
@@ -46,15 +52,16 @@ __device__ __forceinline__ float bpw_xmin(float a, float b)
 
 // Tables (global, built by the host -- bp_warp_layout.h -- for a labelling "position = slot * 32 + lane" of the checks
 // and of the variables that it is free to choose):
-//   ridx  [VPL*3][32]  byte offset in the R buffer of the t-th ADDED message of the variable at (i, lane) in iterations
-//                      >= 1 (the zero row for padding);  ridx0: the same for iteration 0 (read only when TWO: the
-//                      reference's NumPy reduction order differs between iteration 0 and the later ones, graph.py)
+//   sidx  [CPL*RW][32] byte offset in the message planes where edge slot k of the check at (i, lane) delivers its
+//                      message in iterations >= 1 (plane t, column of the variable; the dump row for padding);
+//                      sidx0: the same for iteration 0 (read only when TWO: the reference's NumPy reduction order
+//                      differs between iteration 0 and the later ones, graph.py)
 //   vidx  [CPL*RW][32] byte offset in the posterior buffer of the variable of edge slot k of the check at (i, lane)
 //   cinfo [CPL][32]    index of the check at (i, lane) in H, 0xffffffff for padding
 //   vorig [VPL][32]    index of the variable at (i, lane) in H, 0xffffffff for padding
 //   vpos  [VPL][32]    byte offset in the posterior buffer of variable 32 i + lane of H
 struct BPWarpTables {
-    const uint32_t *ridx, *ridx0, *vidx, *cinfo, *vorig, *vpos;
+    const uint32_t *sidx, *sidx0, *vidx, *cinfo, *vorig, *vpos;
 };
 
 template <int CPL, int VPL, int RW, bool TWO>
@@ -65,27 +72,28 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem[];
-    float *Rbuf = reinterpret_cast<float *>(smem + bp_warp_smem_per_warp(CPL, VPL, RW) * warp);
-    float *Vbuf = Rbuf + 32 * (CPL * RW + 1);
-    constexpr int ZERO_ROW = CPL * RW;
+    float *Rbuf = reinterpret_cast<float *>(smem + bp_warp_smem_per_warp(VPL) * warp);     // [3][VPL][32] + dump row
+    float *Vbuf = Rbuf + 32 * (3 * VPL + 1);
 
     // ---- per-lane tables into registers (BYTE offsets into the R / posterior buffers) -------------
-    uint32_t ridx[VPL][3], vidx[CPL][RW], cinfo[CPL];
+    uint32_t sidx[CPL][RW], vidx[CPL][RW], cinfo[CPL];
     float prior[VPL];
 #pragma unroll
     for (int i = 0; i < VPL; ++i) {
         const uint32_t v = W.vorig[i * 32 + lane];
         prior[i] = (v != 0xffffffffu) ? reinterpret_cast<const float *>(P.prior)[v] + 0.f : 0.f;    // (+ 0: a -0.0 prior becomes +0.0)
-#pragma unroll
-        for (int t = 0; t < 3; ++t) ridx[i][t] = W.ridx[(i * 3 + t) * 32 + lane];
     }
 #pragma unroll
     for (int i = 0; i < CPL; ++i) {
         cinfo[i] = W.cinfo[i * 32 + lane];
 #pragma unroll
-        for (int k = 0; k < RW; ++k) vidx[i][k] = W.vidx[(i * RW + k) * 32 + lane];
+        for (int k = 0; k < RW; ++k) {
+            vidx[i][k] = W.vidx[(i * RW + k) * 32 + lane];
+            sidx[i][k] = W.sidx[(i * RW + k) * 32 + lane];
+        }
     }
-    Rbuf[ZERO_ROW * 32 + lane] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3 * VPL + 1; ++r) Rbuf[r * 32 + lane] = 0.f;      // columns of padding positions stay zero for ever
 
     const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
     const int max_iter = P.max_iter;
@@ -137,26 +145,20 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
                 for (int k = 0; k < RW; ++k) {
                     const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
                     const float r = __fmul_rn(o, salpha[i]);       // (+-alpha) * (+-magnitude): same rounding as alpha * magnitude
-                    R[i][k] = r;           // (padding check slots produce garbage that no variable ever reads)
-                    Rbuf[(i * RW + k) * 32 + lane] = r;
+                    R[i][k] = r;
+                    if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + (i * RW + k) * 32 + lane), r);
+                    else stb(Rbuf, sidx[i][k], r);       // (padding lanes write garbage into the dump row)
                 }
             }
             __syncwarp();
 
             // ================= vertical step: posteriors of the owned variables =====================
             const bool last = (iter == max_iter - 1);
-            auto var_pass = [&](auto idx_of) {
 #pragma unroll
-                for (int i = 0; i < VPL; ++i) {
-                    const float r0 = ldb(Rbuf, idx_of(i, 0)), r1 = ldb(Rbuf, idx_of(i, 1)), r2 = ldb(Rbuf, idx_of(i, 2));
-                    const float val = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);          // :61-62
-                    Vbuf[i * 32 + lane] = val;
-                }
-            };
-            if (TWO && iter == 0)
-                var_pass([&](int i, int t) { return __ldg(W.ridx0 + (i * 3 + t) * 32 + lane); });
-            else
-                var_pass([&](int i, int t) { return ridx[i][t]; });
+            for (int i = 0; i < VPL; ++i) {
+                const float r0 = Rbuf[(0 * VPL + i) * 32 + lane], r1 = Rbuf[(1 * VPL + i) * 32 + lane], r2 = Rbuf[(2 * VPL + i) * 32 + lane];
+                Vbuf[i * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);        // :61-62
+            }
             __syncwarp();
 
             // ================= Q update in registers + syndrome of the hard decision =================

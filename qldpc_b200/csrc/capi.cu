@@ -155,7 +155,7 @@ static int warp_tables_upload(qldpc_code *c)
     const WarpLayout L = c->wlayout->tables();
     std::vector<uint32_t> all;
     size_t off[6];
-    const std::vector<uint32_t> *parts[6] = {&L.ridx, &L.ridx0, &L.vidx, &L.cinfo, &L.vorig, &L.vpos};
+    const std::vector<uint32_t> *parts[6] = {&L.sidx, &L.sidx0, &L.vidx, &L.cinfo, &L.vorig, &L.vpos};
     for (int i = 0; i < 6; ++i) { off[i] = all.size(); all.insert(all.end(), parts[i]->begin(), parts[i]->end()); }
     if (!c->d_wtab) CK(cudaMalloc(&c->d_wtab, all.size() * sizeof(uint32_t)));
     CK(cudaMemcpy(c->d_wtab, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
@@ -307,7 +307,7 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
     c->warp_ok = c->tiled_ok && ((c->WM == 2 && (c->WN == 3 || c->WN == 4)) || (c->WM == 3 && c->WN == 5) || (c->WM == 5 && c->WN == 9));
     if (c->warp_ok) {
         c->wlayout = new WarpLayoutBuilder(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 6);
-        if (const char *ev = getenv("QLDPC_WARP_TUNE_STEPS")) c->wlayout->anneal(atoll(ev));
+        if (!getenv("QLDPC_WARP_NATURAL_LAYOUT")) c->wlayout->construct();
         if (int rc = warp_tables_upload(c)) return rc;
     }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
@@ -399,7 +399,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->warp_kernel = true;
         G->threads = BPW_WARPS * 32;
         G->shots_per_cta = BPW_WARPS;
-        G->smem = bp_warp_smem_per_warp(c->WM, c->WN, 6) * BPW_WARPS;
+        G->smem = bp_warp_smem_per_warp(c->WN) * BPW_WARPS;
         G->grid = 0;                 // filled at launch from the occupancy query
         G->gstate_bytes = 0;
         return QLDPC_OK;
@@ -475,7 +475,7 @@ extern "C" int qldpc_warp_layout_tune(qldpc_code *c, int64_t steps, int32_t *cos
     if (!c->warp_ok) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_warp_layout_tune: the warp-per-shot kernel does not apply to this code");
     CK(cudaDeviceSynchronize());
     if (steps < 0) c->wlayout->natural();
-    if (steps > 0) c->wlayout->anneal(steps);
+    if (steps > 0) c->wlayout->construct(steps);
     if (steps != 0)
         if (int rc = warp_tables_upload(c)) return rc;
     if (cost) { cost[0] = c->warp_cost[0]; cost[1] = c->warp_cost[1]; cost[2] = c->warp_cost[2]; }

@@ -1,8 +1,9 @@
-"""Summarise an .ncu-rep (raw page + source page) into text: python tools/ncu_summary.py file.ncu-rep [min_pct]"""
+"""Summarise an .ncu-rep (raw page + source page) into text: python tools/ncu_summary.py file.ncu-rep [min_pct] [kernel-regex]"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 minpct = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+ksel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+raw = subprocess.run(["ncu", "-i", rep] + ksel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
 keys = ["Kernel Name", "gpu__time_duration.sum", "launch__registers_per_thread", "launch__block_size", "launch__grid_size",
@@ -20,9 +21,15 @@ for k in keys:
     if k in hdr:
         i = hdr.index(k)
         print(f"{k:85s} {vals[i][:60]:>22s} {units[i]}")
-src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+src = subprocess.run(["ncu", "-i", rep] + ksel + ["--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
-hdr, data = rows[1], rows[2:]
+hdr = rows[1]
+data = []
+for r in rows[2:]:
+    if r == hdr or (r and r[0] == 'Kernel Name'):
+        break              # a second view / kernel follows
+    if len(r) == len(hdr):
+        data.append(r)
 isrc, ins, ismp, ithr = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.index("Avg. Threads Executed")
 iwf = hdr.index("L1 Wavefronts Shared") if "L1 Wavefronts Shared" in hdr else None
 iwfi = hdr.index("L1 Wavefronts Shared Ideal") if "L1 Wavefronts Shared Ideal" in hdr else None

@@ -99,18 +99,26 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
     const int max_iter = P.max_iter;
     unsigned long long iter_sum = 0;
 
-    while (true) {
-        // ---- next shot of this warp ----------------------------------------------------------------
-        unsigned long long s0 = 0;
-        if (lane == 0) s0 = atomicAdd(P.cursor, 1ull);
-        const long long shot = (long long)__shfl_sync(FULL, s0, 0);
-        if (shot >= P.B) break;
+    // The shot index (global cursor) and the syndrome words of the NEXT shot are fetched while the current one is being
+    // decoded, so that neither the atomic nor the load latency is exposed between two shots.
+    auto load_synd = [&](long long sh, uint32_t (&w)[CPL]) {
+#pragma unroll
+        for (int i = 0; i < CPL; ++i) w[i] = (sh < P.B && cinfo[i] != 0xffffffffu) ? P.synd[(size_t)sh * WM + (cinfo[i] >> 5)] : 0u;
+    };
+    unsigned long long s0 = 0;
+    if (lane == 0) s0 = atomicAdd(P.cursor, 1ull);
+    long long shot = (long long)__shfl_sync(FULL, s0, 0);
+    uint32_t sw[CPL];
+    load_synd(shot, sw);
+
+    while (shot < P.B) {
+        if (lane == 0) s0 = atomicAdd(P.cursor, 1ull);       // consumed after iteration 0
+        long long next_shot = 0;
         uint32_t sbit[CPL];                      // syndrome bit of each owned check, moved to the sign-bit position
         float salpha[CPL];                       // (-1)^s * alpha
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
-            const uint32_t w = (cinfo[i] != 0xffffffffu) ? P.synd[(size_t)shot * WM + (cinfo[i] >> 5)] : 0u;
-            sbit[i] = ((w >> (cinfo[i] & 31u)) & 1u) << 31;
+            sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
             salpha[i] = __uint_as_float(__float_as_uint(alpha) ^ sbit[i]);
         }
         // Q = where(mask, prior, 0) (decoding.py:21): publish the priors, gather them along the edges
@@ -180,6 +188,10 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
                 ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);
             }
             conv = __all_sync(FULL, ok);
+            if (iter == 0) {
+                next_shot = (long long)__shfl_sync(FULL, s0, 0);
+                load_synd(next_shot, sw);
+            }
             if (conv || last) break;
         }
 
@@ -203,6 +215,7 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
             if (!conv && P.fail_idx) P.fail_idx[atomicAdd(P.fail_count, 1u)] = (int32_t)shot;
             iter_sum += (unsigned long long)(iter + 1);
         }
+        shot = next_shot;
     }
     if (P.iter_total && lane == 0 && iter_sum) atomicAdd(P.iter_total, iter_sum);
 }

@@ -694,9 +694,43 @@ static cudaError_t launch_osd_inst(const qldpc_code *c, const OSDParams &P, long
     return cudaGetLastError();
 }
 
+template <typename K, int WM, int NS>
+static cudaError_t launch_osd_fast_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
+{
+    auto kern = osd0_fast_kernel<K, WM, NS>;
+    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_WARPS * 32, smem);
+    long long grid = (long long)c->num_sms * std::max(1, occ);
+    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, (count_hint + OSD_WARPS - 1) / OSD_WARPS));
+    kern<<<(int)grid, OSD_WARPS * 32, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+// column-major kernel: the shapes of the reference's codes (m <= 160, n <= 288); cudaErrorNotSupported otherwise
+template <typename K>
+static cudaError_t launch_osd_fast(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
+{
+    const int NS = (P.n + 31) / 32;
+    if (P.WM == 2 && NS == 3) return launch_osd_fast_inst<K, 2, 3>(c, P, count_hint, st);
+    if (P.WM == 2 && NS == 4) return launch_osd_fast_inst<K, 2, 4>(c, P, count_hint, st);
+    if (P.WM == 3 && NS == 5) return launch_osd_fast_inst<K, 3, 5>(c, P, count_hint, st);
+    if (P.WM == 5 && NS == 9) return launch_osd_fast_inst<K, 5, 9>(c, P, count_hint, st);
+    return cudaErrorNotSupported;
+}
+
 template <typename K>
 static cudaError_t launch_osd_k(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
 {
+    static const bool force_rowmajor = getenv("QLDPC_OSD_FORCE_ROWMAJOR") != nullptr;    // test hook
+    if (!P.rec_ordering && !force_rowmajor) {
+        const cudaError_t e = launch_osd_fast<K>(c, P, count_hint, st);
+        if (e != cudaErrorNotSupported) return e;
+    }
     switch (P.WM) {
     case 1: return launch_osd_inst<K, 1>(c, P, count_hint, st);
     case 2: return launch_osd_inst<K, 2>(c, P, count_hint, st);

@@ -74,12 +74,140 @@ __host__ __device__ inline size_t osd_smem_per_warp(int n)
     return (o + 15) & ~(size_t)15;
 }
 
+// Row-major elimination of one shot by one warp, given its ordering `ord` (shared memory): residual syndrome,
+// gf2_elimination with the reference's pivot-row rule, solution, validity flag, optional elimination record.
+template <typename K, int WM>
+__device__ __forceinline__ void osd0_rowmajor_shot(const OSDParams &P, long long it, long long shot, const uint32_t *cmask,
+                                                   const uint16_t *ord, uint32_t *solw, int lane)
+{
+    const int m = P.m, n = P.n, WN = P.WN;
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t *hard = P.hard + (size_t)shot * WN;
+            // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------
+            uint32_t rs[WM];
+    #pragma unroll
+            for (int w = 0; w < WM; ++w) rs[w] = 0;
+            for (int v = lane; v < n; v += 32) {
+                if ((hard[v >> 5] >> (v & 31)) & 1u) {
+    #pragma unroll
+                    for (int w = 0; w < WM; ++w) rs[w] ^= cmask[v * WM + w];
+                }
+            }
+    #pragma unroll
+            for (int w = 0; w < WM; ++w) rs[w] = __reduce_xor_sync(FULL, rs[w]) ^ P.synd[(size_t)shot * WM + w];
+
+            // ---- T = I, b = residual, positions = row index ------------------------------------
+            uint32_t T[WM][WM];
+            uint32_t bbit[WM];
+            int pos[WM], pcol[WM];
+    #pragma unroll
+            for (int i = 0; i < WM; ++i) {
+    #pragma unroll
+                for (int w = 0; w < WM; ++w) T[i][w] = (w == i) ? (1u << lane) : 0u;
+                const int r = lane + 32 * i;
+                bbit[i] = (rs[i] >> lane) & 1u;
+                pos[i] = (r < m) ? r : 0x7fffffff;
+                pcol[i] = -1;
+            }
+
+            // ---- gf2_elimination (OSD.py:31-72) -------------------------------------------------
+            int row = 0;
+            const int rank = P.rank;
+            for (int j = 0; j < n && row < rank; ++j) {     // `row >= m` (:43); past `rank` pivots no column can pivot
+                const int col = ord[j];
+                uint32_t cm[WM];
+    #pragma unroll
+                for (int w = 0; w < WM; ++w) cm[w] = cmask[col * WM + w];
+                uint32_t has[WM];
+                int best = 0x7fffffff;
+    #pragma unroll
+                for (int i = 0; i < WM; ++i) {
+                    uint32_t x = 0;
+    #pragma unroll
+                    for (int w = 0; w < WM; ++w) x ^= T[i][w] & cm[w];
+                    has[i] = __popc(x) & 1u;
+                    if (has[i] && pos[i] >= row && pos[i] < best) best = pos[i];   // first row >= current (:47-50)
+                }
+                const int pmin = __reduce_min_sync(FULL, best);
+                if (pmin == 0x7fffffff) continue;                                    // no pivot in this column (:52-53)
+                // the owner of the pivot row broadcasts it
+                uint32_t prow[WM];
+                uint32_t pb = 0;
+                bool mine = false;
+    #pragma unroll
+                for (int w = 0; w < WM; ++w) prow[w] = 0;
+    #pragma unroll
+                for (int i = 0; i < WM; ++i) {
+                    if (pos[i] == pmin) {
+                        mine = true;
+                        pb = bbit[i];
+    #pragma unroll
+                        for (int w = 0; w < WM; ++w) prow[w] = T[i][w];
+                    }
+                }
+                const int owner = __ffs(__ballot_sync(FULL, mine)) - 1;
+                pb = __shfl_sync(FULL, pb, owner);
+    #pragma unroll
+                for (int w = 0; w < WM; ++w) prow[w] = __shfl_sync(FULL, prow[w], owner);
+                // swap the pivot row up (:56-58) == exchange positions; then eliminate all other rows (:64-68)
+    #pragma unroll
+                for (int i = 0; i < WM; ++i) {
+                    if (pos[i] == pmin) {
+                        pos[i] = row;
+                        pcol[i] = j;
+                    } else {
+                        if (pos[i] == row) pos[i] = pmin;
+                        if (has[i]) {
+    #pragma unroll
+                            for (int w = 0; w < WM; ++w) T[i][w] ^= prow[w];
+                            bbit[i] ^= pb;
+                        }
+                    }
+                }
+                ++row;
+            }
+
+            // ---- e_permuted[pivot col] = s_reduced[pivot row]; unpermute; xor hard (OSD.py:16-26) ----
+            // validity: every non-pivot row must end with b == 0
+            bool bad = false;
+    #pragma unroll
+            for (int i = 0; i < WM; ++i) bad = bad || (pcol[i] < 0 && bbit[i] && (lane + 32 * i) < m);
+            const bool any_bad = __any_sync(FULL, bad);
+            for (int w = lane; w < WN; w += 32) solw[w] = hard[w];
+            __syncwarp();
+    #pragma unroll
+            for (int i = 0; i < WM; ++i) {
+                if (pcol[i] >= 0 && bbit[i]) {
+                    const int v = ord[pcol[i]];
+                    atomicXor(&solw[v >> 5], 1u << (v & 31));
+                }
+            }
+            __syncwarp();
+            for (int w = lane; w < WN; w += 32) P.out[(size_t)shot * WN + w] = solw[w];
+            if (lane == 0 && P.valid) P.valid[shot] = any_bad ? 0 : 1;
+
+            // ---- elimination record for the OSD-w sweep -----------------------------------------
+            if (P.rec_ordering) {
+                for (int j = lane; j < n; j += 32) P.rec_ordering[(size_t)it * n + j] = ord[j];
+                for (int r = lane; r < m; r += 32) P.rec_pivcol[(size_t)it * m + r] = -1;
+                __syncwarp();
+    #pragma unroll
+                for (int i = 0; i < WM; ++i) {
+                    if (lane + 32 * i < m) {
+                        P.rec_pivcol[(size_t)it * m + pos[i]] = pcol[i];
+                        P.rec_sred[(size_t)it * m + pos[i]] = (uint8_t)bbit[i];
+                    }
+                }
+                if (lane == 0) P.rec_npiv[it] = row;
+            }
+}
+
 template <typename K, int WM>
 __global__ void __launch_bounds__(OSD_WARPS * 32)
 osd0_kernel(const OSDParams P)
 {
     typedef typename KeyBits<K>::type kbits;
-    const int m = P.m, n = P.n, WN = P.WN;
+    const int n = P.n;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *cmask = reinterpret_cast<uint32_t *>(smem);
@@ -92,12 +220,10 @@ osd0_kernel(const OSDParams P)
 
     const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
     const long long nwarps = (long long)gridDim.x * OSD_WARPS;
-    const unsigned FULL = 0xffffffffu;
 
     for (long long it = (long long)blockIdx.x * OSD_WARPS + warp; it < count; it += nwarps) {
         const long long shot = P.idx ? (long long)P.idx[it] : it;
         const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
-        const uint32_t *hard = P.hard + (size_t)shot * WN;
 
         // ---- ordering = argsort(|llr|), stable (OSD.py:10-11) ------------------------------
         for (int j = lane; j < n; j += 32) keys[j] = KeyBits<K>::get(llr[j]);
@@ -125,123 +251,194 @@ osd0_kernel(const OSDParams P)
         }
         __syncwarp();
 
-        // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------
-        uint32_t rs[WM];
+        osd0_rowmajor_shot<K, WM>(P, it, shot, cmask, ord, solw, lane);
+        __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// OSD-0, column-major: the production kernel when no elimination record is requested (BP+OSD pipelines).
+//
+// The OSD-0 solution does not depend on WHICH row pivots a column: the pivot columns are the greedy set of linearly
+// independent columns in |LLR| order (independent of the row choices), and the error supported on them that reproduces
+// the syndrome is unique.  The reference's "first row at or below the current one" rule (OSD.py:47-58) therefore only
+// matters for the elimination record of the OSD-w sweep, which osd0_kernel above still produces.
+//
+// That freedom allows the cheap formulation: lane l keeps the REDUCED columns at sorted positions 32 s + l (s < NS) in
+// registers as WM-word bit vectors, the syndrome column and the set of used pivot rows are warp-uniform registers.
+// Per column (broadcast from its owner with WM shuffles): free rows = column & ~used; none -> dependent column, next;
+// else the lowest free row p pivots, and every later column c with bit p set becomes c ^ (column - bit p) -- one
+// predicated 3-word XOR per register slot, on all 32 lanes at once.  About 45 warp-instructions per pivot and 10 per
+// dependent column instead of ~55 + 70 per column in the row-major kernel, and no REDUX / pivot-row search.
+// The rank of the stable argsort is counted block by block: keys before a lane's own 32-block compare with <=, keys
+// after it with <, only the diagonal block needs the tie rule per lane (2 instructions per compare instead of 6).
+// ------------------------------------------------------------------------------------------------
+template <typename K, int WM, int NS>
+__global__ void __launch_bounds__(OSD_WARPS * 32)
+osd0_fast_kernel(const OSDParams P)
+{
+    typedef typename KeyBits<K>::type kbits;
+    const int m = P.m, n = P.n, WN = P.WN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *cmask = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < n * WM; i += blockDim.x) cmask[i] = P.colmask[i];
+    __syncthreads();
+    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * warp;
+    kbits *keys = reinterpret_cast<kbits *>(base);
+    uint16_t *ord = reinterpret_cast<uint16_t *>(base + sizeof(kbits) * (size_t)n);
+    uint32_t *solw = reinterpret_cast<uint32_t *>(base + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
+
+    const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
+    const long long nwarps = (long long)gridDim.x * OSD_WARPS;
+    const unsigned FULL = 0xffffffffu;
+    const int rank = P.rank;
+
+    for (long long it = (long long)blockIdx.x * OSD_WARPS + warp; it < count; it += nwarps) {
+        const long long shot = P.idx ? (long long)P.idx[it] : it;
+        const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
+        const uint32_t *hard = P.hard + (size_t)shot * WN;
+
+        // ---- ordering = argsort(|llr|), stable (OSD.py:10-11): rank by counting --------------
+        kbits ki[NS];
+        int cnt[NS];
 #pragma unroll
-        for (int w = 0; w < WM; ++w) rs[w] = 0;
+        for (int t = 0; t < NS; ++t) {
+            const int i = 32 * t + lane;
+            ki[t] = (i < n) ? KeyBits<K>::get(llr[i]) : ~(kbits)0;        // padding sorts last
+            if (i < n) keys[i] = ki[t];
+            cnt[t] = 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int jb = 0; jb < NS; ++jb) {                                    // keys 32 jb .. 32 jb + 31
+            kbits thr[NS];
+#pragma unroll
+            for (int t = 0; t < NS; ++t) thr[t] = (jb < t) ? ki[t] + (kbits)1 : ki[t];     // j < i: count key_j <= key_i
+            const int jend = min(32, n - 32 * jb);
+#pragma unroll 4
+            for (int jl = 0; jl < jend; ++jl) {
+                const kbits kj = keys[32 * jb + jl];
+#pragma unroll
+                for (int t = 0; t < NS; ++t) {
+                    if (t == jb) cnt[t] += (kj < ki[t]) || (kj == ki[t] && jl < lane);
+                    else cnt[t] += (kj < thr[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NS; ++t) if (32 * t + lane < n) ord[cnt[t]] = (uint16_t)(32 * t + lane);
+        __syncwarp();
+
+        // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------
+        uint32_t b[WM];
+#pragma unroll
+        for (int w = 0; w < WM; ++w) b[w] = 0;
         for (int v = lane; v < n; v += 32) {
             if ((hard[v >> 5] >> (v & 31)) & 1u) {
 #pragma unroll
-                for (int w = 0; w < WM; ++w) rs[w] ^= cmask[v * WM + w];
+                for (int w = 0; w < WM; ++w) b[w] ^= cmask[v * WM + w];
             }
         }
 #pragma unroll
-        for (int w = 0; w < WM; ++w) rs[w] = __reduce_xor_sync(FULL, rs[w]) ^ P.synd[(size_t)shot * WM + w];
+        for (int w = 0; w < WM; ++w) b[w] = __reduce_xor_sync(FULL, b[w]) ^ P.synd[(size_t)shot * WM + w];
 
-        // ---- T = I, b = residual, positions = row index ------------------------------------
-        uint32_t T[WM][WM];
-        uint32_t bbit[WM];
-        int pos[WM], pcol[WM];
+        // ---- the columns in sorted order, WM words each -------------------------------------
+        uint32_t c[NS][WM];
+        int prow[NS];
 #pragma unroll
-        for (int i = 0; i < WM; ++i) {
+        for (int s = 0; s < NS; ++s) {
+            const int j = 32 * s + lane;
+            const int col = (j < n) ? ord[j] : 0;
 #pragma unroll
-            for (int w = 0; w < WM; ++w) T[i][w] = (w == i) ? (1u << lane) : 0u;
-            const int r = lane + 32 * i;
-            bbit[i] = (rs[i] >> lane) & 1u;
-            pos[i] = (r < m) ? r : 0x7fffffff;
-            pcol[i] = -1;
+            for (int w = 0; w < WM; ++w) c[s][w] = (j < n) ? cmask[col * WM + w] : 0u;
+            prow[s] = -1;
         }
 
-        // ---- gf2_elimination (OSD.py:31-72) -------------------------------------------------
-        int row = 0;
-        const int rank = P.rank;
-        for (int j = 0; j < n && row < rank; ++j) {     // `row >= m` (:43); past `rank` pivots no column can pivot
-            const int col = ord[j];
-            uint32_t cm[WM];
+        // ---- elimination ----------------------------------------------------------------------
+        uint32_t used[WM];
 #pragma unroll
-            for (int w = 0; w < WM; ++w) cm[w] = cmask[col * WM + w];
-            uint32_t has[WM];
-            int best = 0x7fffffff;
+        for (int w = 0; w < WM; ++w) used[w] = 0;
+        int npiv = 0;
 #pragma unroll
-            for (int i = 0; i < WM; ++i) {
-                uint32_t x = 0;
+        for (int s = 0; s < NS; ++s) {
+            const int lend = min(32, n - 32 * s);
+            for (int l = 0; l < lend && npiv < rank; ++l) {
+                uint32_t col[WM], any = 0;
 #pragma unroll
-                for (int w = 0; w < WM; ++w) x ^= T[i][w] & cm[w];
-                has[i] = __popc(x) & 1u;
-                if (has[i] && pos[i] >= row && pos[i] < best) best = pos[i];   // first row >= current (:47-50)
-            }
-            const int pmin = __reduce_min_sync(FULL, best);
-            if (pmin == 0x7fffffff) continue;                                    // no pivot in this column (:52-53)
-            // the owner of the pivot row broadcasts it
-            uint32_t prow[WM];
-            uint32_t pb = 0;
-            bool mine = false;
-#pragma unroll
-            for (int w = 0; w < WM; ++w) prow[w] = 0;
-#pragma unroll
-            for (int i = 0; i < WM; ++i) {
-                if (pos[i] == pmin) {
-                    mine = true;
-                    pb = bbit[i];
-#pragma unroll
-                    for (int w = 0; w < WM; ++w) prow[w] = T[i][w];
+                for (int w = 0; w < WM; ++w) {
+                    col[w] = __shfl_sync(FULL, c[s][w], l);
+                    any |= col[w] & ~used[w];
                 }
-            }
-            const int owner = __ffs(__ballot_sync(FULL, mine)) - 1;
-            pb = __shfl_sync(FULL, pb, owner);
+                if (any == 0) continue;                                      // dependent column (OSD.py:52-53)
+                int pw = 0;
+                uint32_t fw = col[0] & ~used[0];
 #pragma unroll
-            for (int w = 0; w < WM; ++w) prow[w] = __shfl_sync(FULL, prow[w], owner);
-            // swap the pivot row up (:56-58) == exchange positions; then eliminate all other rows (:64-68)
+                for (int w = WM - 1; w >= 1; --w) {
+                    bool lower = false;                                      // is some lower word non-empty?
 #pragma unroll
-            for (int i = 0; i < WM; ++i) {
-                if (pos[i] == pmin) {
-                    pos[i] = row;
-                    pcol[i] = j;
-                } else {
-                    if (pos[i] == row) pos[i] = pmin;
-                    if (has[i]) {
+                    for (int x = 0; x < w; ++x) lower = lower || ((col[x] & ~used[x]) != 0);
+                    if (!lower && (col[w] & ~used[w]) != 0) { pw = w; fw = col[w] & ~used[w]; }
+                }
+                const uint32_t pbit = fw & (0u - fw);                        // lowest free row of the column
+                if (lane == l) prow[s] = 32 * pw + __ffs(pbit) - 1;
+                ++npiv;
+                // pw is warp-uniform: one specialised copy of the update per word
 #pragma unroll
-                        for (int w = 0; w < WM; ++w) T[i][w] ^= prow[w];
-                        bbit[i] ^= pb;
+                for (int w0 = 0; w0 < WM; ++w0) {
+                    if (pw == w0) {
+                        used[w0] |= pbit;
+                        col[w0] &= ~pbit;                                    // the pivot row itself is not touched
+                        if (b[w0] & pbit) {
+#pragma unroll
+                            for (int w = 0; w < WM; ++w) b[w] ^= col[w];
+                        }
+#pragma unroll
+                        for (int s2 = s; s2 < NS; ++s2) {                    // (earlier positions are finished)
+                            if (c[s2][w0] & pbit) {
+#pragma unroll
+                                for (int w = 0; w < WM; ++w) c[s2][w] ^= col[w];
+                            }
+                        }
                     }
                 }
             }
-            ++row;
         }
 
-        // ---- e_permuted[pivot col] = s_reduced[pivot row]; unpermute; xor hard (OSD.py:16-26) ----
-        // validity: every non-pivot row must end with b == 0
+        // ---- e[pivot column] = reduced syndrome at its pivot row; xor hard (OSD.py:16-26) -----
+        // validity: every row that pivots no column must end with b == 0
         bool bad = false;
 #pragma unroll
-        for (int i = 0; i < WM; ++i) bad = bad || (pcol[i] < 0 && bbit[i] && (lane + 32 * i) < m);
-        const bool any_bad = __any_sync(FULL, bad);
+        for (int w = 0; w < WM; ++w) {
+            const int rows = m - 32 * w;                                     // rows of H in this word
+            const uint32_t live = rows >= 32 ? 0xffffffffu : (rows > 0 ? ((1u << rows) - 1u) : 0u);
+            bad = bad || ((b[w] & ~used[w] & live) != 0);
+        }
+        if (bad) {
+            // Inconsistent syndrome (never the case for s = e H^T): the reference's output then depends on its pivot-row
+            // choices, so this shot is redone with the row-major rule.
+            osd0_rowmajor_shot<K, WM>(P, it, shot, cmask, ord, solw, lane);
+            __syncwarp();
+            continue;
+        }
         for (int w = lane; w < WN; w += 32) solw[w] = hard[w];
         __syncwarp();
 #pragma unroll
-        for (int i = 0; i < WM; ++i) {
-            if (pcol[i] >= 0 && bbit[i]) {
-                const int v = ord[pcol[i]];
-                atomicXor(&solw[v >> 5], 1u << (v & 31));
+        for (int s = 0; s < NS; ++s) {
+            if (prow[s] >= 0) {
+                uint32_t bw = b[0];
+#pragma unroll
+                for (int w = 1; w < WM; ++w) if ((prow[s] >> 5) == w) bw = b[w];
+                if ((bw >> (prow[s] & 31)) & 1u) {
+                    const int v = ord[32 * s + lane];
+                    atomicXor(&solw[v >> 5], 1u << (v & 31));
+                }
             }
         }
         __syncwarp();
         for (int w = lane; w < WN; w += 32) P.out[(size_t)shot * WN + w] = solw[w];
-        if (lane == 0 && P.valid) P.valid[shot] = any_bad ? 0 : 1;
-
-        // ---- elimination record for the OSD-w sweep -----------------------------------------
-        if (P.rec_ordering) {
-            for (int j = lane; j < n; j += 32) P.rec_ordering[(size_t)it * n + j] = ord[j];
-            for (int r = lane; r < m; r += 32) P.rec_pivcol[(size_t)it * m + r] = -1;
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < WM; ++i) {
-                if (lane + 32 * i < m) {
-                    P.rec_pivcol[(size_t)it * m + pos[i]] = pcol[i];
-                    P.rec_sred[(size_t)it * m + pos[i]] = (uint8_t)bbit[i];
-                }
-            }
-            if (lane == 0) P.rec_npiv[it] = row;
-        }
+        if (lane == 0 && P.valid) P.valid[shot] = 1;
         __syncwarp();
     }
 }

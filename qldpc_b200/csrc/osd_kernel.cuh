@@ -50,6 +50,21 @@ struct OSDParams {
     int32_t *rec_npiv;            // [count]
 };
 
+// cnt -= (a < b), as a subtract-with-borrow pair (2 instructions; the compiler's own lowering of `cnt += (a < b)` is
+// add / compare / predicated move)
+__device__ __forceinline__ void osd_count_lt(int &cnt, uint32_t a, uint32_t b)
+{
+    uint32_t lo;
+    asm("{sub.cc.u32 %1, %2, %3;\n\tsubc.u32 %0, %0, 0;}" : "+r"(cnt), "=r"(lo) : "r"(a), "r"(b));
+}
+__device__ __forceinline__ void osd_count_lt(int &cnt, unsigned long long a, unsigned long long b)
+{
+    uint32_t lo, hi;
+    asm("{sub.cc.u32 %1, %3, %5;\n\tsubc.cc.u32 %2, %4, %6;\n\tsubc.u32 %0, %0, 0;}"
+        : "+r"(cnt), "=r"(lo), "=r"(hi)
+        : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
+}
+
 template <typename K> struct KeyBits;
 template <> struct KeyBits<float> {
     typedef uint32_t type;
@@ -322,13 +337,13 @@ osd0_fast_kernel(const OSDParams P)
                 const kbits kj = keys[32 * jb + jl];
 #pragma unroll
                 for (int t = 0; t < NS; ++t) {
-                    if (t == jb) cnt[t] += (kj < ki[t]) || (kj == ki[t] && jl < lane);
-                    else cnt[t] += (kj < thr[t]);
+                    if (t == jb) osd_count_lt(cnt[t], kj, ki[t] + (kbits)(jl < lane));     // diagonal block: tie rule per lane
+                    else osd_count_lt(cnt[t], kj, thr[t]);
                 }
             }
         }
 #pragma unroll
-        for (int t = 0; t < NS; ++t) if (32 * t + lane < n) ord[cnt[t]] = (uint16_t)(32 * t + lane);
+        for (int t = 0; t < NS; ++t) if (32 * t + lane < n) ord[-cnt[t]] = (uint16_t)(32 * t + lane);      // (cnt counts down)
         __syncwarp();
 
         // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------

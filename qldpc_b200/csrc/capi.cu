@@ -87,14 +87,17 @@ struct qldpc_code {
     DevBuf prior32, prior64, ctrl, gstate;
     DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
         ws_weight, ws_cnt, ws_llr_in, ws_rec;
-    // pipeline slots of the host-pointer decode call: each has its own stream, control block and workspaces so
-    // that the H2D copy / decode / D2H copy of consecutive chunks overlap
+    // Three-stage pipeline of the host-pointer decode call: a copy-in stream, a compute stream and a copy-out stream,
+    // chained per chunk by events; chunk buffers rotate over NSLOT slots.  Kernels of different chunks never share the
+    // GPU (each runs at full speed), the copies of the neighbouring chunks run under them.
     struct Slot {
-        cudaStream_t st = nullptr;
         DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail;
+        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
+        bool used = false;
     };
-    static constexpr int NSLOT = 3;
+    static constexpr int NSLOT = 4;
     Slot slot[NSLOT];
+    cudaStream_t st_in = nullptr, st_comp = nullptr, st_out = nullptr;
     BPGraphDev graph() const
     {
         BPGraphDev g;
@@ -363,8 +366,11 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     for (auto &sl : c->slot) {
         DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail};
         for (DevBuf *b : sb) b->release();
-        if (sl.st) cudaStreamDestroy(sl.st);
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_comp, sl.ev_out})
+            if (e) cudaEventDestroy(e);
     }
+    for (cudaStream_t st : {c->st_in, c->st_comp, c->st_out})
+        if (st) cudaStreamDestroy(st);
     delete c;
 }
 
@@ -1131,40 +1137,70 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
     const size_t in_row = packed ? 4 * (size_t)c->WM : (size_t)c->m, out_row = packed ? 4 * (size_t)c->WN : (size_t)c->n;
     if (int rc = check_cfg(cfg)) return rc;
     if (B <= 0) return QLDPC_OK;
-    // Chunks rotate over NSLOT streams: copy-in / pack / BP / OSD / unpack / copy-out of chunk i overlap with the
-    // copies of chunks i-1 and i+1 (true overlap needs pinned host buffers; pageable ones still work).
+    // Copy-in / (pack, BP, OSD, unpack) / copy-out of consecutive chunks run on three streams chained by events (true
+    // overlap needs pinned host buffers; pageable ones still work).
     long long chunk = 1ll << 20;
     if (const char *e = getenv("QLDPC_HOST_CHUNK")) chunk = std::max<long long>(1024, atoll(e));
     chunk = std::min<long long>(chunk, CHUNK);
     if (int rc = set_prior(c, prior, 0)) return rc;
     // enqueue every chunk; on any failure stop enqueuing, but always drain the streams before returning, so that no copy
     // into the caller's buffers is still in flight
+    // QLDPC_TRACE=1: per-chunk timeline (ms since the first enqueue) on stderr -- diagnostic for the overlap of copies and kernels
+    const bool trace = getenv("QLDPC_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    auto mark = [&](cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        tev.push_back(e);
+    };
+    if (!c->st_in) {
+        CK(cudaStreamCreateWithFlags(&c->st_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->st_comp, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
+    }
+    for (auto &sl : c->slot) sl.used = false;
     auto enqueue = [&](long long o, long long b, qldpc_code::Slot &sl) -> int {
-        if (!sl.st) CK(cudaStreamCreateWithFlags(&sl.st, cudaStreamNonBlocking));
-        cudaStream_t st = sl.st;
+        if (!sl.ev_in) {
+            CK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+        }
         CK(sl.synd.reserve(4 * (size_t)b * c->WM));
         CK(sl.hard.reserve(4 * (size_t)b * c->WN));
         CK(sl.conv.reserve((size_t)b));
         CK(sl.iters.reserve(4 * (size_t)b));
-        if (packed) {
-            CK(cudaMemcpyAsync(sl.synd.p, synd + (size_t)o * in_row, (size_t)b * in_row, cudaMemcpyHostToDevice, st));
-        } else {
+        if (!packed) {
             CK(sl.u8in.reserve((size_t)b * c->m));
             CK(sl.u8out.reserve((size_t)b * c->n));
-            CK(cudaMemcpyAsync(sl.u8in.p, synd + (size_t)o * in_row, (size_t)b * in_row, cudaMemcpyHostToDevice, st));
-            if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, st)) return rc;
         }
+        // ---- copy in (the slot's input buffer is free once the previous chunk that used it has been computed; waiting
+        //      for its copy-out as well keeps one rule for all buffers of the slot)
+        if (sl.used) CK(cudaStreamWaitEvent(c->st_in, sl.ev_out, 0));
+        mark(c->st_in);
+        CK(cudaMemcpyAsync(packed ? sl.synd.p : sl.u8in.p, synd + (size_t)o * in_row, (size_t)b * in_row, cudaMemcpyHostToDevice, c->st_in));
+        CK(cudaEventRecord(sl.ev_in, c->st_in));
+        mark(c->st_in);
+        // ---- compute
+        CK(cudaStreamWaitEvent(c->st_comp, sl.ev_in, 0));
+        if (!packed)
+            if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, c->st_comp)) return rc;
         if (int rc = bposd_chunk(c, cfg, prior, b, sl.synd.as<uint32_t>(), osd_order, sl.hard.as<uint32_t>(), sl.conv.as<uint8_t>(),
-                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, st))
+                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, c->st_comp))
             return rc;
-        if (packed) {
-            CK(cudaMemcpyAsync(corr + (size_t)o * out_row, sl.hard.p, (size_t)b * out_row, cudaMemcpyDeviceToHost, st));
-        } else {
-            if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, st)) return rc;
-            CK(cudaMemcpyAsync(corr + (size_t)o * out_row, sl.u8out.p, (size_t)b * out_row, cudaMemcpyDeviceToHost, st));
-        }
-        CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, st));
-        if (iters) CK(cudaMemcpyAsync(iters + o, sl.iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, st));
+        if (!packed)
+            if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, c->st_comp)) return rc;
+        CK(cudaEventRecord(sl.ev_comp, c->st_comp));
+        mark(c->st_comp);
+        // ---- copy out
+        CK(cudaStreamWaitEvent(c->st_out, sl.ev_comp, 0));
+        CK(cudaMemcpyAsync(corr + (size_t)o * out_row, packed ? sl.hard.p : sl.u8out.p, (size_t)b * out_row, cudaMemcpyDeviceToHost, c->st_out));
+        CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, c->st_out));
+        if (iters) CK(cudaMemcpyAsync(iters + o, sl.iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, c->st_out));
+        CK(cudaEventRecord(sl.ev_out, c->st_out));
+        mark(c->st_out);
+        sl.used = true;
         return QLDPC_OK;
     };
     int rc_all = QLDPC_OK;
@@ -1172,9 +1208,17 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
     for (long long o = 0; o < B && rc_all == QLDPC_OK; o += chunk, ++i)
         rc_all = enqueue(o, std::min<long long>(chunk, B - o), c->slot[i % qldpc_code::NSLOT]);
     const std::string msg = g_err;
-    for (auto &sl : c->slot)
-        if (sl.st && cudaStreamSynchronize(sl.st) != cudaSuccess && rc_all == QLDPC_OK)
+    for (cudaStream_t st : {c->st_in, c->st_comp, c->st_out})
+        if (st && cudaStreamSynchronize(st) != cudaSuccess && rc_all == QLDPC_OK)
             rc_all = fail(QLDPC_ERR_CUDA, "qldpc_bposd_decode_host: stream synchronisation failed");
+    if (trace) {
+        for (size_t q = 0; q + 3 < tev.size(); q += 4) {
+            float t[4];
+            for (int x = 0; x < 4; ++x) cudaEventElapsedTime(&t[x], tev[0], tev[q + x]);
+            fprintf(stderr, "[qldpc trace] chunk %zu: h2d %.2f - %.2f  compute done %.2f  d2h done %.2f ms\n", q / 4, t[0], t[1], t[2], t[3]);
+        }
+        for (cudaEvent_t e : tev) cudaEventDestroy(e);
+    }
     if (rc_all != QLDPC_OK && !msg.empty()) g_err = msg;
     return rc_all;
 }

@@ -378,24 +378,29 @@ osd0_fast_kernel(const OSDParams P)
         int npiv = 0;
 #pragma unroll
         for (int s = 0; s < NS; ++s) {
-            const int lend = min(32, n - 32 * s);
-            for (int l = 0; l < lend && npiv < rank; ++l) {
-                uint32_t col[WM], any = 0;
+            // A column without a free row can never get one back (it is only updated through a free row it holds), so
+            // the next column to pivot is the first lane of the slot, past the last pivot, that still has a free row:
+            // one ballot per PIVOT; dependent columns cost nothing.
+            unsigned todo = FULL;
+            while (npiv < rank) {
+                uint32_t freebits = 0;
+#pragma unroll
+                for (int w = 0; w < WM; ++w) freebits |= c[s][w] & ~used[w];
+                const unsigned live = __ballot_sync(FULL, freebits != 0) & todo;
+                if (live == 0) break;
+                const int l = __ffs(live) - 1;
+                todo &= ~((2u << l) - 1u);
+                uint32_t col[WM], fr[WM];
 #pragma unroll
                 for (int w = 0; w < WM; ++w) {
                     col[w] = __shfl_sync(FULL, c[s][w], l);
-                    any |= col[w] & ~used[w];
+                    fr[w] = col[w] & ~used[w];
                 }
-                if (any == 0) continue;                                      // dependent column (OSD.py:52-53)
-                int pw = 0;
-                uint32_t fw = col[0] & ~used[0];
+                int pw = WM - 1;
+                uint32_t fw = fr[WM - 1];
 #pragma unroll
-                for (int w = WM - 1; w >= 1; --w) {
-                    bool lower = false;                                      // is some lower word non-empty?
-#pragma unroll
-                    for (int x = 0; x < w; ++x) lower = lower || ((col[x] & ~used[x]) != 0);
-                    if (!lower && (col[w] & ~used[w]) != 0) { pw = w; fw = col[w] & ~used[w]; }
-                }
+                for (int w = WM - 2; w >= 0; --w)
+                    if (fr[w] != 0) { pw = w; fw = fr[w]; }                  // first word with a free row
                 const uint32_t pbit = fw & (0u - fw);                        // lowest free row of the column
                 if (lane == l) prow[s] = 32 * pw + __ffs(pbit) - 1;
                 ++npiv;

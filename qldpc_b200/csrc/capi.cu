@@ -829,7 +829,11 @@ extern "C" int qldpc_unpack_bits_dev(const uint32_t *in, uint8_t *out, int64_t B
 {
     if (B <= 0) return QLDPC_OK;
     const int W = (nbits + 31) / 32;
-    unpack_bits_kernel<<<grid_for(B * (long long)nbits, 256, 148), 256, 0, (cudaStream_t)stream>>>(in, out, B, nbits, W);
+    if (nbits % 16 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        unpack_bits16_kernel<<<grid_for(B * (long long)(nbits / 16), 256, 148), 256, 0, (cudaStream_t)stream>>>(
+            in, reinterpret_cast<uint4 *>(out), B, nbits, W);
+    else
+        unpack_bits_kernel<<<grid_for(B * (long long)nbits, 256, 148), 256, 0, (cudaStream_t)stream>>>(in, out, B, nbits, W);
     CK(cudaGetLastError());
     return QLDPC_OK;
 }

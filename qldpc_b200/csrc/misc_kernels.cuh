@@ -36,6 +36,25 @@ __global__ void unpack_bits_kernel(const uint32_t *__restrict__ in, uint8_t *__r
     }
 }
 
+// nbits % 16 == 0: one thread expands 16 bits into 16 bytes (one 128-bit store; the 16 bits never straddle a word)
+__global__ void unpack_bits16_kernel(const uint32_t *__restrict__ in, uint4 *__restrict__ out, long long B, int nbits, int W)
+{
+    const int per_row = nbits >> 4;
+    const long long total = B * (long long)per_row;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long s = t / per_row;
+        const int j = (int)(t - s * per_row) << 4;
+        const uint32_t bits = (in[(size_t)s * W + (j >> 5)] >> (j & 31)) & 0xffffu;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t nib = (bits >> (4 * q)) & 0xfu;
+            w[q] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        out[t] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
+
 template <typename TI, typename TO>
 __global__ void cast_kernel(const TI *__restrict__ in, TO *__restrict__ out, long long N)
 {

@@ -85,13 +85,14 @@ struct qldpc_code {
     bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;
+    DevBuf ws_redo;
     DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
         ws_weight, ws_cnt, ws_llr_in, ws_rec;
     // Three-stage pipeline of the host-pointer decode call: a copy-in stream, a compute stream and a copy-out stream,
     // chained per chunk by events; chunk buffers rotate over NSLOT slots.  Kernels of different chunks never share the
     // GPU (each runs at full speed), the copies of the neighbouring chunks run under them.
     struct Slot {
-        DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail;
+        DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail, redo;
         cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
         bool used = false;
     };
@@ -360,11 +361,11 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     cudaFree(c->d_wtab);
     delete c->wlayout;
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
-                      &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags,
+                      &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags, &c->ws_redo,
                       &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
-        DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail};
+        DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail, &sl.redo};
         for (DevBuf *b : sb) b->release();
         for (cudaEvent_t e : {sl.ev_in, sl.ev_comp, sl.ev_out})
             if (e) cudaEventDestroy(e);
@@ -763,13 +764,29 @@ static cudaError_t launch_osd_block(const qldpc_code *c, const OSDBlockParams &P
     return cudaGetLastError();
 }
 
+template <typename K>
+static cudaError_t launch_osd_block_fast(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
+{
+    auto kern = osd0_block_fast_kernel<K>;
+    const size_t smem = osdbf_smem_bytes<K>(P.m, P.n);
+    if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSDB_THREADS, smem);
+    long long grid = (long long)c->num_sms * std::max(1, occ);
+    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, count_hint));
+    kern<<<(int)grid, OSDB_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 static bool osd_use_block(const qldpc_code *c)
 {
     static const bool force = getenv("QLDPC_OSD_FORCE_BLOCK") != nullptr;    // test hook
     return force || c->WM > 5 || c->n > 65535;
 }
 
-static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st)
+static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st, DevBuf *redo = nullptr)
 {
     P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
     P.rank = c->rank;
@@ -782,6 +799,24 @@ static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_
         Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1;
         Q.idx = P.idx; Q.count_dev = P.count_dev; Q.count_host = P.count_host;
         Q.synd = P.synd; Q.llr = P.llr; Q.hard = P.hard; Q.out = P.out; Q.valid = P.valid;
+        Q.redo_idx = nullptr; Q.redo_count = nullptr;
+        static const bool force_rowmajor = getenv("QLDPC_OSD_FORCE_ROWMAJOR") != nullptr;    // test hook
+        const long long cap = P.count_dev ? P.cap : P.count_host;
+        if (!force_rowmajor && cap > 0 && redo) {
+            // column-major kernel; the shots it flags as inconsistent are redone by the row-major one
+            CK(redo->reserve(sizeof(int32_t) * (size_t)cap + 16));
+            Q.redo_count = redo->as<unsigned int>();
+            Q.redo_idx = redo->as<int32_t>() + 4;
+            CK(cudaMemsetAsync(Q.redo_count, 0, sizeof(unsigned int), st));
+            cudaError_t e = llr_f64 ? launch_osd_block_fast<double>(c, Q, count_hint, st) : launch_osd_block_fast<float>(c, Q, count_hint, st);
+            if (e != cudaSuccess)
+                return fail(e == cudaErrorInvalidValue ? QLDPC_ERR_UNSUPPORTED : QLDPC_ERR_CUDA,
+                            std::string("osd0_block_fast_kernel launch (check matrix too large for shared memory?): ") + cudaGetErrorString(e));
+            Q.idx = Q.redo_idx; Q.count_dev = Q.redo_count; Q.count_host = 0;
+            e = llr_f64 ? launch_osd_block<double>(c, Q, -1, st) : launch_osd_block<float>(c, Q, -1, st);
+            if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osd0_block_kernel (redo) launch: ") + cudaGetErrorString(e));
+            return QLDPC_OK;
+        }
         cudaError_t e = llr_f64 ? launch_osd_block<double>(c, Q, count_hint, st) : launch_osd_block<float>(c, Q, count_hint, st);
         if (e != cudaSuccess)
             return fail(e == cudaErrorInvalidValue ? QLDPC_ERR_UNSUPPORTED : QLDPC_ERR_CUDA,
@@ -805,7 +840,8 @@ extern "C" int qldpc_osd_decode_dev(qldpc_code *c, const int32_t *idx, const uin
     P.count_dev = count_dev;
     P.count_host = count_host;
     P.synd = synd; P.llr = llr; P.hard = hard; P.out = out; P.valid = valid;
-    return osd_launch(c, P, llr_f64, count_dev ? -1 : count_host, (cudaStream_t)stream);
+    P.cap = count_dev ? count_host : 0;          // with a device-side count, count_host (if > 0) bounds it
+    return osd_launch(c, P, llr_f64, count_dev ? -1 : count_host, (cudaStream_t)stream, &c->ws_redo);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -914,7 +950,7 @@ static const long long CHUNK = 1ll << 24;   // shots per internal launch (bounds
 // BP, then OSD-0 on the compacted BP failures, for at most CHUNK shots, with explicit workspaces
 static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, long long b, const uint32_t *synd,
                        int32_t osd_order, uint32_t *corr, uint8_t *conv, int32_t *iters, uint64_t *iter_total,
-                       DevBuf *ctrl, DevBuf *gstate, DevBuf *llr_buf, DevBuf *fail_buf, cudaStream_t st)
+                       DevBuf *ctrl, DevBuf *gstate, DevBuf *llr_buf, DevBuf *fail_buf, DevBuf *redo_buf, cudaStream_t st)
 {
     const int tsize = cfg->precision == 64 ? 8 : 4;
     void *llr = nullptr;
@@ -940,7 +976,8 @@ static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *
         P.out = corr;
         // OSD-w == OSD-0 whenever the OSD-0 solution satisfies the syndrome (OSD_enhanced.py:58-60),
         // which is always the case for syndromes of the form e * H^T.
-        rc = osd_launch(c, P, tsize == 8, -1, st);
+        P.cap = b;
+        rc = osd_launch(c, P, tsize == 8, -1, st, redo_buf);
         if (rc) return rc;
     }
     return QLDPC_OK;
@@ -956,7 +993,7 @@ extern "C" int qldpc_bposd_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg,
     for (long long o = 0; o < B; o += CHUNK) {
         const long long b = std::min<long long>(CHUNK, B - o);
         if (int rc = bposd_chunk(c, cfg, prior_host, b, synd + (size_t)o * c->WM, osd_order, corr + (size_t)o * c->WN, conv + o,
-                                 iters ? iters + o : nullptr, iter_total, &c->ctrl, &c->gstate, &c->ws_llr, &c->ws_fail, st))
+                                 iters ? iters + o : nullptr, iter_total, &c->ctrl, &c->gstate, &c->ws_llr, &c->ws_fail, &c->ws_redo, st))
             return rc;
     }
     return QLDPC_OK;
@@ -1101,7 +1138,7 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
             P.rec_npiv = reinterpret_cast<int32_t *>(r);                 r += 4 * (size_t)b;
             P.rec_sred = reinterpret_cast<uint8_t *>(r);
         }
-        if (int rc = osd_launch(c, P, 1, b, st)) return rc;
+        if (int rc = osd_launch(c, P, 1, b, st, &c->ws_redo)) return rc;
         bool any_invalid = false;
         if (want_rec) {     // the sweep is dead code whenever every OSD-0 solution satisfies its syndrome (OSD_enhanced.py:58-60)
             std::vector<uint8_t> hv((size_t)b);
@@ -1191,7 +1228,7 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         if (!packed)
             if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, c->st_comp)) return rc;
         if (int rc = bposd_chunk(c, cfg, prior, b, sl.synd.as<uint32_t>(), osd_order, sl.hard.as<uint32_t>(), sl.conv.as<uint8_t>(),
-                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, c->st_comp))
+                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, &sl.redo, c->st_comp))
             return rc;
         if (!packed)
             if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, c->st_comp)) return rc;

@@ -38,6 +38,7 @@ struct OSDParams {
     const int32_t *idx;           // [count] shot ids to process (null: identity)
     const unsigned int *count_dev;// number of entries in idx (device) ...
     long long count_host;         // ... or given by the host when count_dev == null
+    long long cap;                // upper bound of the count when it lives on the device (0: unknown)
     const uint32_t *synd;         // [B][WM]
     const void *llr;              // [B][n] float or double
     const uint32_t *hard;         // [B][WN]  BP hard decision
@@ -54,14 +55,12 @@ struct OSDParams {
 // add / compare / predicated move)
 __device__ __forceinline__ void osd_count_lt(int &cnt, uint32_t a, uint32_t b)
 {
-    uint32_t lo;
-    asm("{sub.cc.u32 %1, %2, %3;\n\tsubc.u32 %0, %0, 0;}" : "+r"(cnt), "=r"(lo) : "r"(a), "r"(b));
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %2;\n\tsubc.u32 %0, %0, 0;\n\t}" : "+r"(cnt) : "r"(a), "r"(b));
 }
 __device__ __forceinline__ void osd_count_lt(int &cnt, unsigned long long a, unsigned long long b)
 {
-    uint32_t lo, hi;
-    asm("{sub.cc.u32 %1, %3, %5;\n\tsubc.cc.u32 %2, %4, %6;\n\tsubc.u32 %0, %0, 0;}"
-        : "+r"(cnt), "=r"(lo), "=r"(hi)
+    asm("{\n\t.reg .u32 t;\n\tsub.cc.u32 t, %1, %3;\n\tsubc.cc.u32 t, %2, %4;\n\tsubc.u32 %0, %0, 0;\n\t}"
+        : "+r"(cnt)
         : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
 }
 
@@ -487,6 +486,10 @@ struct OSDBlockParams {
     const uint32_t *hard;         // [B][WN]
     uint32_t *out;                // [B][WN]
     uint8_t *valid;               // [B]
+    // osd0_block_fast_kernel only: shots whose syndrome turns out inconsistent are appended here and redone by
+    // osd0_block_kernel (the reference's output then depends on its pivot-row rule)
+    int32_t *redo_idx;            // [capacity >= count]
+    unsigned int *redo_count;
 };
 
 constexpr int OSDB_THREADS = 256;
@@ -628,6 +631,162 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
         bad = __syncthreads_or(bad);
         for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
         if (tid == 0 && P.valid) P.valid[shot] = bad ? 0 : 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// OSD-0 for large check matrices, column-major transform: the production block kernel.
+//
+// Same observation as osd0_fast_kernel: the OSD-0 solution does not depend on which row pivots a column, and a column
+// with no free row never gets one back.  The transform is stored by COLUMNS (TC[c] = column c of T, an m-bit vector of
+// WM words): the reduced column j = T h_j is the XOR of the <= few TC columns of the checks of variable ordering[j] --
+// ONE warp evaluates it (a word per lane) and finds its lowest free row; a row operation "rows S ^= row p" becomes
+// "every TC column with bit p set ^= S".  The 8 warps of the CTA test 8 consecutive candidate columns at once; the
+// first one with a free row pivots, the dependent ones before it are skipped for good, the ones after it are re-tested.
+// Block-wide synchronisation happens per PIVOT (3 barriers), not per column, and dependent columns (2/3 of a
+// space-time matrix) cost one warp-pass each.  Inconsistent syndromes are handed to osd0_block_kernel (redo list).
+// ------------------------------------------------------------------------------------------------
+template <typename K>
+__host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
+{
+    const int WM = (m + 31) / 32, WN = (n + 31) / 32;
+    size_t o = 4 * (size_t)m * WM;                              // TC
+    o += 2 * (size_t)m * 2;                                     // pivot rows / pivot columns (uint16)
+    o = (o + 3) & ~(size_t)3;
+    o += 4 * (size_t)WM * 3;                                    // used, b, S
+    o += 4 * (size_t)WM * (OSDB_THREADS / 32);                  // per-warp candidate columns
+    o += 4 * (size_t)WN;                                        // solution words
+    o = (o + 7) & ~(size_t)7;
+    o += sizeof(typename KeyBits<K>::type) * (size_t)n;         // keys
+    o += 2 * (size_t)n;                                         // ordering (uint16)
+    return o + 64;
+}
+
+template <typename K>
+__global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSDBlockParams P)
+{
+    typedef typename KeyBits<K>::type kbits;
+    constexpr int NW = OSDB_THREADS / 32;
+    const int m = P.m, n = P.n, WM = P.WM, WN = P.WN;
+    const int tid = threadIdx.x, NT = OSDB_THREADS, lane = tid & 31, warp = tid >> 5;
+    const unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *TC = reinterpret_cast<uint32_t *>(smem);                      // [m][WM]  column c of T
+    uint16_t *prow = reinterpret_cast<uint16_t *>(TC + (size_t)m * WM);    // [m] pivot row of the k-th pivot
+    uint16_t *pcolj = prow + m;                                            // [m] sorted position of the k-th pivot column
+    uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(pcolj + m) + 3) & ~(uintptr_t)3);   // [WM]
+    uint32_t *bw = used + WM;                                               // [WM] syndrome column
+    uint32_t *Sv = bw + WM;                                                 // [WM] pivot column without the pivot row
+    uint32_t *cand = Sv + WM;                                               // [NW][WM]
+    uint32_t *solw = cand + (size_t)NW * WM;                                // [WN]
+    kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
+    uint16_t *ord = reinterpret_cast<uint16_t *>(keys + n);
+    __shared__ int s_free[NW], s_p;
+
+    const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
+    for (long long it = blockIdx.x; it < count; it += gridDim.x) {
+        const long long shot = P.idx ? (long long)P.idx[it] : it;
+        const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
+        const uint32_t *hard = P.hard + (size_t)shot * WN;
+        __syncthreads();
+        // ---- stable ascending order of |llr| by rank counting ---------------------------------
+        for (int j = tid; j < n; j += NT) keys[j] = KeyBits<K>::get(llr[j]);
+        for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; }
+        for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
+        __syncthreads();
+        for (int i = tid; i < n; i += NT) {
+            const kbits ki = keys[i];
+            int cnt = 0;
+            int j = 0;
+#pragma unroll 4
+            for (; j < i; ++j) osd_count_lt(cnt, keys[j], ki + (kbits)1);        // j < i: key_j <= key_i
+#pragma unroll 4
+            for (; j < n; ++j) osd_count_lt(cnt, keys[j], ki);
+            ord[-cnt] = (uint16_t)i;
+        }
+        // ---- residual syndrome s ^ H*hard; T = I ------------------------------------------------
+        for (int v = tid; v < n; v += NT)
+            if ((hard[v >> 5] >> (v & 31)) & 1u)
+                for (int a = P.var_ptr[v]; a < P.var_ptr[v + 1]; ++a) {
+                    const int c = (int)P.vtab[2 * a + 1];
+                    atomicXor(&bw[c >> 5], 1u << (c & 31));
+                }
+        for (int t = tid; t < m * WM; t += NT) {
+            const int c = t / WM, w = t - c * WM;
+            TC[t] = (w == (c >> 5)) ? (1u << (c & 31)) : 0u;
+        }
+        __syncthreads();
+
+        // ---- elimination -----------------------------------------------------------------------
+        int j = 0, npiv = 0;
+        const int rank = P.rank;
+        while (j < n && npiv < rank) {
+            // warp w: reduced column of sorted position j + w, its free rows, the lowest of them
+            const int jj = j + warp;
+            int myfree = -1;                                        // lowest free row of my candidate, -1: dependent
+            if (jj < n) {
+                const int col = ord[jj];
+                const int a0 = P.var_ptr[col], a1 = P.var_ptr[col + 1];
+                for (int w0 = 0; w0 < WM; w0 += 32) {
+                    const int w = w0 + lane;
+                    uint32_t x = 0;
+                    if (w < WM)
+                        for (int a = a0; a < a1; ++a) x ^= TC[(size_t)P.vtab[2 * a + 1] * WM + w];
+                    if (w < WM) cand[(size_t)warp * WM + w] = x;
+                    const uint32_t fr = (w < WM) ? (x & ~used[w]) : 0u;
+                    const unsigned bal = __ballot_sync(FULL, fr != 0);
+                    if (bal != 0 && myfree < 0) {
+                        const int src = __ffs(bal) - 1;
+                        const uint32_t f = __shfl_sync(FULL, fr, src);
+                        myfree = 32 * (w0 + src) + __ffs(f) - 1;
+                    }
+                }
+            }
+            if (lane == 0) s_free[warp] = myfree;
+            __syncthreads();
+            int first = -1;
+#pragma unroll
+            for (int w = NW - 1; w >= 0; --w) if (s_free[w] >= 0) first = w;
+            if (first < 0) { j += NW; __syncthreads(); continue; }                 // NW dependent columns
+            const int p = s_free[first];
+            const uint32_t pbit = 1u << (p & 31);
+            const int pw = p >> 5;
+            // S = pivot column without the pivot row; the pivot record
+            for (int w = tid; w < WM; w += NT) Sv[w] = cand[(size_t)first * WM + w] & ~((w == pw) ? pbit : 0u);
+            if (tid == 0) { prow[npiv] = (uint16_t)p; pcolj[npiv] = (uint16_t)(j + first); }
+            __syncthreads();
+            // rows S ^= row p  <=>  every column of T with bit p set ^= S (and so does the syndrome column)
+            for (int c = tid; c < m; c += NT) {
+                if (TC[(size_t)c * WM + pw] & pbit)
+                    for (int w = 0; w < WM; ++w) TC[(size_t)c * WM + w] ^= Sv[w];
+            }
+            if (warp == NW - 1 && (bw[pw] & pbit))                                   // (read by every lane before any write: one warp)
+                for (int w = lane; w < WM; w += 32) bw[w] ^= Sv[w];
+            if (tid == 0) used[pw] |= pbit;
+            ++npiv;
+            j += first + 1;
+            __syncthreads();
+        }
+
+        // ---- solution and validity -----------------------------------------------------------------
+        int bad = 0;
+        for (int w = tid; w < WM; w += NT) {
+            const int rows = m - 32 * w;
+            const uint32_t live = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
+            if (bw[w] & ~used[w] & live) bad = 1;
+        }
+        bad = __syncthreads_or(bad);
+        if (bad) {                                                   // inconsistent syndrome: redo with the reference's pivot rule
+            if (tid == 0) P.redo_idx[atomicAdd(P.redo_count, 1u)] = (int32_t)shot;
+            continue;
+        }
+        for (int k = tid; k < npiv; k += NT) {
+            const int r = prow[k];
+            if ((bw[r >> 5] >> (r & 31)) & 1u) { const int v = ord[pcolj[k]]; atomicXor(&solw[v >> 5], 1u << (v & 31)); }
+        }
+        __syncthreads();
+        for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
+        if (tid == 0 && P.valid) P.valid[shot] = 1;
     }
 }
 

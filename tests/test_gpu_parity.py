@@ -389,14 +389,14 @@ def test_osd_after_bp_with_ties(bp_golden):
             assert np.array_equal(got, d[f"{key}_ms{pi}_osd0"][f])
 
 
-@pytest.mark.parametrize("hook", ["QLDPC_OSD_FORCE_BLOCK", "QLDPC_OSD_FORCE_ROWMAJOR"])
+@pytest.mark.parametrize("hook", ["QLDPC_OSD_FORCE_BLOCK", "QLDPC_OSD_FORCE_ROWMAJOR", "QLDPC_OSD_FORCE_BLOCK+QLDPC_OSD_FORCE_ROWMAJOR"])
 def test_osd_other_kernels_forced_on_small_codes(hook):
-    """The production OSD-0 kernel on the reference's codes is the column-major one (test_osd_golden runs it).  The
-    block-per-shot kernel (large check matrices) and the row-major warp kernel (elimination record for OSD-w) must agree
-    bit for bit with the golden vectors too: force each on the small codes in a fresh process (the hooks are read once
-    per process)."""
+    """The production OSD-0 kernel on the reference's codes is the column-major warp kernel (test_osd_golden runs it).
+    The block-per-shot kernels (large check matrices; column-major, and row-major behind it for inconsistent syndromes)
+    and the row-major warp kernel (elimination record for OSD-w) must agree bit for bit with the golden vectors too:
+    force each on the small codes in a fresh process (the hooks are read once per process)."""
     import os, subprocess, sys
-    env = dict(os.environ, **{hook: "1"})
+    env = dict(os.environ, **{h: "1" for h in hook.split("+")})
     code = r"""
 import json, os, sys
 import numpy as np

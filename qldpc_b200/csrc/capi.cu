@@ -795,14 +795,14 @@ static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_
         if (c->n > 65534 || c->m > 32767) return fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65534 columns or 32767 rows");
         if (P.rec_ordering) return fail(QLDPC_ERR_UNSUPPORTED, "OSD-w sweep (order > 0) is not available for check matrices with more than 160 rows");
         OSDBlockParams Q;
-        Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank;
+        Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank; Q.max_col_w = c->max_col_w;
         Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1;
         Q.idx = P.idx; Q.count_dev = P.count_dev; Q.count_host = P.count_host;
         Q.synd = P.synd; Q.llr = P.llr; Q.hard = P.hard; Q.out = P.out; Q.valid = P.valid;
         Q.redo_idx = nullptr; Q.redo_count = nullptr;
         static const bool force_rowmajor = getenv("QLDPC_OSD_FORCE_ROWMAJOR") != nullptr;    // test hook
         const long long cap = P.count_dev ? P.cap : P.count_host;
-        if (!force_rowmajor && cap > 0 && redo) {
+        if (!force_rowmajor && cap > 0 && redo && c->WM <= 32) {
             // column-major kernel; the shots it flags as inconsistent are redone by the row-major one
             CK(redo->reserve(sizeof(int32_t) * (size_t)cap + 16));
             Q.redo_count = redo->as<unsigned int>();

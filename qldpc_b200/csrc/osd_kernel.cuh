@@ -476,6 +476,7 @@ osd0_fast_kernel(const OSDParams P)
 // ------------------------------------------------------------------------------------------------
 struct OSDBlockParams {
     int m, n, WM, WN, rank;
+    int max_col_w;                // largest column weight of H
     const int32_t *var_ptr;       // [n+1]  CSC of H
     const uint32_t *vtab;         // [2E]   (edge, check) pairs per variable (any order)
     const int32_t *idx;
@@ -635,29 +636,34 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 }
 
 // ------------------------------------------------------------------------------------------------
-// OSD-0 for large check matrices, column-major transform: the production block kernel.
+// OSD-0 for large check matrices, column-major transform, forward elimination: the production block kernel.
 //
 // Same observation as osd0_fast_kernel: the OSD-0 solution does not depend on which row pivots a column, and a column
 // with no free row never gets one back.  The transform is stored by COLUMNS (TC[c] = column c of T, an m-bit vector of
-// WM words): the reduced column j = T h_j is the XOR of the <= few TC columns of the checks of variable ordering[j] --
+// WM words): the reduced column j = T h_j is the XOR of the <= 3 TC columns of the checks of variable ordering[j] --
 // ONE warp evaluates it (a word per lane) and finds its lowest free row; a row operation "rows S ^= row p" becomes
 // "every TC column with bit p set ^= S".  The 8 warps of the CTA test 8 consecutive candidate columns at once; the
 // first one with a free row pivots, the dependent ones before it are skipped for good, the ones after it are re-tested.
-// Block-wide synchronisation happens per PIVOT (3 barriers), not per column, and dependent columns (2/3 of a
-// space-time matrix) cost one warp-pass each.  Inconsistent syndromes are handed to osd0_block_kernel (redo list).
+// Two barriers per PIVOT, none per column; dependent columns (2/3 of a space-time matrix) cost one warp-pass each.
+// Only FREE rows are eliminated (S = free rows of the pivot column): pivot rows are frozen once chosen, T fills in like
+// L^-1 instead of B^-1, and the solution follows from a back-substitution over the pivots in reverse order (one warp,
+// the syndrome column in its registers).  Free rows evolve exactly as under Gauss-Jordan, so the pivot columns and the
+// consistency test are unchanged.  Inconsistent syndromes are handed to osd0_block_kernel (redo list).
+// The checks of column ordering[j] are packed 3 x 10 bits into the shared-memory words the sort keys occupied
+// (m < 1024, column weight <= 3: the space-time matrices; otherwise they are read from global memory).
 // ------------------------------------------------------------------------------------------------
 template <typename K>
 __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 {
     const int WM = (m + 31) / 32, WN = (n + 31) / 32;
     size_t o = 4 * (size_t)m * WM;                              // TC
-    o += 2 * (size_t)m * 2;                                     // pivot rows / pivot columns (uint16)
+    o += 2 * (size_t)m * 2;                                     // pivot rows / sorted positions of the pivot columns (uint16)
     o = (o + 3) & ~(size_t)3;
-    o += 4 * (size_t)WM * 3;                                    // used, b, S
+    o += 4 * (size_t)WM * 3;                                    // used (double-buffered), b
     o += 4 * (size_t)WM * (OSDB_THREADS / 32);                  // per-warp candidate columns
     o += 4 * (size_t)WN;                                        // solution words
     o = (o + 7) & ~(size_t)7;
-    o += sizeof(typename KeyBits<K>::type) * (size_t)n;         // keys
+    o += sizeof(typename KeyBits<K>::type) * (size_t)n;         // keys, then the packed check lists
     o += 2 * (size_t)n;                                         // ordering (uint16)
     return o + 64;
 }
@@ -674,14 +680,31 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
     uint32_t *TC = reinterpret_cast<uint32_t *>(smem);                      // [m][WM]  column c of T
     uint16_t *prow = reinterpret_cast<uint16_t *>(TC + (size_t)m * WM);    // [m] pivot row of the k-th pivot
     uint16_t *pcolj = prow + m;                                            // [m] sorted position of the k-th pivot column
-    uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(pcolj + m) + 3) & ~(uintptr_t)3);   // [WM]
-    uint32_t *bw = used + WM;                                               // [WM] syndrome column
-    uint32_t *Sv = bw + WM;                                                 // [WM] pivot column without the pivot row
-    uint32_t *cand = Sv + WM;                                               // [NW][WM]
+    uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(pcolj + m) + 3) & ~(uintptr_t)3);   // [2][WM]
+    uint32_t *bw = used + 2 * WM;                                           // [WM] syndrome column
+    uint32_t *cand = bw + WM;                                               // [NW][WM] free rows of the candidates
     uint32_t *solw = cand + (size_t)NW * WM;                                // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
+    uint32_t *chk = reinterpret_cast<uint32_t *>(keys);                    // [n] packed checks of column ordering[j] (after the sort)
     uint16_t *ord = reinterpret_cast<uint16_t *>(keys + n);
-    __shared__ int s_free[NW], s_p;
+    __shared__ int s_free[NW];
+    const bool packed_chk = (m < 1024) && (P.max_col_w <= 3);
+
+    // XOR of the TC columns of the checks of sorted position jj, word w
+    auto reduced_word = [&](int jj, int w) -> uint32_t {
+        uint32_t x = 0;
+        if (packed_chk) {
+            const uint32_t e = chk[jj];
+            const int cnt = (int)(e >> 30);
+            x = TC[(size_t)(e & 1023u) * WM + w];
+            if (cnt > 1) x ^= TC[(size_t)((e >> 10) & 1023u) * WM + w];
+            if (cnt > 2) x ^= TC[(size_t)((e >> 20) & 1023u) * WM + w];
+        } else {
+            const int col = ord[jj];
+            for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= TC[(size_t)P.vtab[2 * a + 1] * WM + w];
+        }
+        return x;
+    };
 
     const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
     for (long long it = blockIdx.x; it < count; it += gridDim.x) {
@@ -691,7 +714,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         __syncthreads();
         // ---- stable ascending order of |llr| by rank counting ---------------------------------
         for (int j = tid; j < n; j += NT) keys[j] = KeyBits<K>::get(llr[j]);
-        for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; }
+        for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; used[WM + w] = 0; }
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
         __syncthreads();
         for (int i = tid; i < n; i += NT) {
@@ -704,6 +727,15 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             for (; j < n; ++j) osd_count_lt(cnt, keys[j], ki);
             ord[-cnt] = (uint16_t)i;
         }
+        __syncthreads();                                              // keys are dead from here on
+        if (packed_chk)
+            for (int j = tid; j < n; j += NT) {
+                const int col = ord[j];
+                const int a0 = P.var_ptr[col], cnt = P.var_ptr[col + 1] - a0;
+                uint32_t e = (uint32_t)cnt << 30;
+                for (int k = 0; k < cnt; ++k) e |= P.vtab[2 * (a0 + k) + 1] << (10 * k);
+                chk[j] = e;
+            }
         // ---- residual syndrome s ^ H*hard; T = I ------------------------------------------------
         for (int v = tid; v < n; v += NT)
             if ((hard[v >> 5] >> (v & 31)) & 1u)
@@ -717,29 +749,27 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         }
         __syncthreads();
 
-        // ---- elimination -----------------------------------------------------------------------
+        // ---- forward elimination ---------------------------------------------------------------
         int j = 0, npiv = 0;
         const int rank = P.rank;
         while (j < n && npiv < rank) {
-            // warp w: reduced column of sorted position j + w, its free rows, the lowest of them
+            const uint32_t *ucur = used + (npiv & 1) * WM;
+            uint32_t *unxt = used + ((npiv + 1) & 1) * WM;
+            // warp w: free rows of the reduced column at sorted position j + w; the lowest of them would be its pivot
             const int jj = j + warp;
-            int myfree = -1;                                        // lowest free row of my candidate, -1: dependent
+            int myfree = -1;
             if (jj < n) {
-                const int col = ord[jj];
-                const int a0 = P.var_ptr[col], a1 = P.var_ptr[col + 1];
                 for (int w0 = 0; w0 < WM; w0 += 32) {
                     const int w = w0 + lane;
-                    uint32_t x = 0;
-                    if (w < WM)
-                        for (int a = a0; a < a1; ++a) x ^= TC[(size_t)P.vtab[2 * a + 1] * WM + w];
-                    if (w < WM) cand[(size_t)warp * WM + w] = x;
-                    const uint32_t fr = (w < WM) ? (x & ~used[w]) : 0u;
+                    uint32_t fr = (w < WM) ? (reduced_word(jj, w) & ~ucur[w]) : 0u;
                     const unsigned bal = __ballot_sync(FULL, fr != 0);
                     if (bal != 0 && myfree < 0) {
                         const int src = __ffs(bal) - 1;
                         const uint32_t f = __shfl_sync(FULL, fr, src);
                         myfree = 32 * (w0 + src) + __ffs(f) - 1;
+                        if (lane == src) fr &= fr - 1;                  // S = free rows without the pivot row
                     }
+                    if (w < WM) cand[(size_t)warp * WM + w] = fr;
                 }
             }
             if (lane == 0) s_free[warp] = myfree;
@@ -751,38 +781,61 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             const int p = s_free[first];
             const uint32_t pbit = 1u << (p & 31);
             const int pw = p >> 5;
-            // S = pivot column without the pivot row; the pivot record
-            for (int w = tid; w < WM; w += NT) Sv[w] = cand[(size_t)first * WM + w] & ~((w == pw) ? pbit : 0u);
-            if (tid == 0) { prow[npiv] = (uint16_t)p; pcolj[npiv] = (uint16_t)(j + first); }
-            __syncthreads();
-            // rows S ^= row p  <=>  every column of T with bit p set ^= S (and so does the syndrome column)
-            for (int c = tid; c < m; c += NT) {
-                if (TC[(size_t)c * WM + pw] & pbit)
-                    for (int w = 0; w < WM; ++w) TC[(size_t)c * WM + w] ^= Sv[w];
+            const uint32_t *Sv = cand + (size_t)first * WM;
+            // free rows S ^= row p  <=>  every column of T with bit p set ^= S (and so does the syndrome column)
+            // (a warp finds the columns with bit p among its 32-column chunks with a ballot, then XORs S into each of
+            //  them with one word per lane: no divergence, S in a register, conflict-free rows; WM <= 32 here)
+            const uint32_t sv = (lane < WM) ? Sv[lane] : 0u;
+            for (int c0 = warp * 32; c0 < m; c0 += NW * 32) {
+                const int c = c0 + lane;
+                unsigned hit = __ballot_sync(FULL, c < m && (TC[(size_t)c * WM + pw] & pbit));
+                while (hit) {
+                    const int cc = c0 + __ffs(hit) - 1;
+                    hit &= hit - 1;
+                    if (lane < WM) TC[(size_t)cc * WM + lane] ^= sv;
+                }
             }
-            if (warp == NW - 1 && (bw[pw] & pbit))                                   // (read by every lane before any write: one warp)
+            if (warp == NW - 1 && (bw[pw] & pbit))                                   // (bit p itself is not in S: the test is stable)
                 for (int w = lane; w < WM; w += 32) bw[w] ^= Sv[w];
-            if (tid == 0) used[pw] |= pbit;
+            for (int w = tid; w < WM; w += NT) unxt[w] = ucur[w] | ((w == pw) ? pbit : 0u);
+            if (tid == 0) { prow[npiv] = (uint16_t)p; pcolj[npiv] = (uint16_t)(j + first); }
             ++npiv;
             j += first + 1;
             __syncthreads();
         }
 
-        // ---- solution and validity -----------------------------------------------------------------
+        // ---- validity; back-substitution over the pivots in reverse order ---------------------------
+        const uint32_t *ufin = used + (npiv & 1) * WM;
         int bad = 0;
         for (int w = tid; w < WM; w += NT) {
             const int rows = m - 32 * w;
             const uint32_t live = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
-            if (bw[w] & ~used[w] & live) bad = 1;
+            if (bw[w] & ~ufin[w] & live) bad = 1;
         }
         bad = __syncthreads_or(bad);
         if (bad) {                                                   // inconsistent syndrome: redo with the reference's pivot rule
             if (tid == 0) P.redo_idx[atomicAdd(P.redo_count, 1u)] = (int32_t)shot;
             continue;
         }
-        for (int k = tid; k < npiv; k += NT) {
-            const int r = prow[k];
-            if ((bw[r >> 5] >> (r & 31)) & 1u) { const int v = ord[pcolj[k]]; atomicXor(&solw[v >> 5], 1u << (v & 31)); }
+        if (warp == 0) {
+            // x_k = b[p_k]; if set, b ^= reduced column j_k (its entries in the rows of the earlier pivots).  One word of b
+            // per lane and pass; passes over the word blocks are independent because every bit of b is read only after
+            // all later pivots have been applied, which the reverse order guarantees within a pass over ALL words --
+            // so the words are kept in shared memory and each step touches the whole column.
+            for (int k = npiv - 1; k >= 0; --k) {
+                const int r = prow[k], jk = pcolj[k];
+                const uint32_t bit = (bw[r >> 5] >> (r & 31)) & 1u;
+                __syncwarp();
+                if (bit) {
+                    for (int w = lane; w < WM; w += 32) {
+                        uint32_t x = reduced_word(jk, w);
+                        if (w == (r >> 5)) x &= ~(1u << (r & 31));       // keep x_k itself
+                        bw[w] ^= x & ufin[w];                            // (free rows are not involved any more)
+                    }
+                    if (lane == 0) { const int v = ord[jk]; solw[v >> 5] ^= 1u << (v & 31); }
+                }
+                __syncwarp();
+            }
         }
         __syncthreads();
         for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];

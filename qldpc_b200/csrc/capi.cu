@@ -767,7 +767,7 @@ static cudaError_t launch_osd_block(const qldpc_code *c, const OSDBlockParams &P
 template <typename K>
 static cudaError_t launch_osd_block_fast(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
 {
-    auto kern = osd0_block_fast_kernel<K>;
+    auto kern = (P.m < 1024 && P.max_col_w <= 3) ? osd0_block_fast_kernel<K, true> : osd0_block_fast_kernel<K, false>;
     const size_t smem = osdbf_smem_bytes<K>(P.m, P.n);
     if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -668,7 +668,7 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     return o + 64;
 }
 
-template <typename K>
+template <typename K, bool PACKED>
 __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSDBlockParams P)
 {
     typedef typename KeyBits<K>::type kbits;
@@ -688,7 +688,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
     uint32_t *chk = reinterpret_cast<uint32_t *>(keys);                    // [n] packed checks of column ordering[j] (after the sort)
     uint16_t *ord = reinterpret_cast<uint16_t *>(keys + n);
     __shared__ int s_free[NW];
-    const bool packed_chk = (m < 1024) && (P.max_col_w <= 3);
+    constexpr bool packed_chk = PACKED;               // m < 1024 and column weight <= 3 (checked by the host)
 
     // XOR of the TC columns of the checks of sorted position jj, word w
     auto reduced_word = [&](int jj, int w) -> uint32_t {
@@ -712,20 +712,48 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
         const uint32_t *hard = P.hard + (size_t)shot * WN;
         __syncthreads();
-        // ---- stable ascending order of |llr| by rank counting ---------------------------------
-        for (int j = tid; j < n; j += NT) keys[j] = KeyBits<K>::get(llr[j]);
+        // ---- stable ascending order of |llr| ----------------------------------------------------
         for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; used[WM + w] = 0; }
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
-        __syncthreads();
-        for (int i = tid; i < n; i += NT) {
-            const kbits ki = keys[i];
-            int cnt = 0;
-            int j = 0;
+        int N2 = 1;
+        while (N2 < n) N2 <<= 1;
+        if ((sizeof(kbits) + 2) * (size_t)N2 <= 4 * (size_t)m * WM) {
+            // bitonic sort of (key, index) pairs in the (still unused) transform area: O(n log^2 n) instead of the
+            // O(n^2) rank counting -- 78 stages of 2048 compare-exchanges for n = 2592
+            kbits *sk = reinterpret_cast<kbits *>(TC);
+            uint16_t *si = reinterpret_cast<uint16_t *>(sk + N2);
+            for (int j = tid; j < N2; j += NT) {
+                sk[j] = (j < n) ? KeyBits<K>::get(llr[j]) : ~(kbits)0;
+                si[j] = (uint16_t)((j < n) ? j : 0xFFFF);
+            }
+            __syncthreads();
+            for (int k = 2; k <= N2; k <<= 1)
+                for (int jd = k >> 1; jd > 0; jd >>= 1) {
+                    for (int t = tid; t < (N2 >> 1); t += NT) {
+                        const int i = ((t & ~(jd - 1)) << 1) | (t & (jd - 1));       // element with bit jd clear
+                        const int l = i | jd;
+                        const kbits ka = sk[i], kb = sk[l];
+                        const uint16_t ia = si[i], ib = si[l];
+                        const bool a_after_b = (ka > kb) || (ka == kb && ia > ib);
+                        const bool up = (i & k) == 0;                                // ascending block
+                        if (a_after_b == up) { sk[i] = kb; sk[l] = ka; si[i] = ib; si[l] = ia; }
+                    }
+                    __syncthreads();
+                }
+            for (int j = tid; j < n; j += NT) ord[j] = si[j];
+        } else {
+            for (int j = tid; j < n; j += NT) keys[j] = KeyBits<K>::get(llr[j]);
+            __syncthreads();
+            for (int i = tid; i < n; i += NT) {
+                const kbits ki = keys[i];
+                int cnt = 0;
+                int j = 0;
 #pragma unroll 4
-            for (; j < i; ++j) osd_count_lt(cnt, keys[j], ki + (kbits)1);        // j < i: key_j <= key_i
+                for (; j < i; ++j) osd_count_lt(cnt, keys[j], ki + (kbits)1);        // j < i: key_j <= key_i
 #pragma unroll 4
-            for (; j < n; ++j) osd_count_lt(cnt, keys[j], ki);
-            ord[-cnt] = (uint16_t)i;
+                for (; j < n; ++j) osd_count_lt(cnt, keys[j], ki);
+                ord[-cnt] = (uint16_t)i;
+            }
         }
         __syncthreads();                                              // keys are dead from here on
         if (packed_chk)
@@ -758,19 +786,16 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             // warp w: free rows of the reduced column at sorted position j + w; the lowest of them would be its pivot
             const int jj = j + warp;
             int myfree = -1;
-            if (jj < n) {
-                for (int w0 = 0; w0 < WM; w0 += 32) {
-                    const int w = w0 + lane;
-                    uint32_t fr = (w < WM) ? (reduced_word(jj, w) & ~ucur[w]) : 0u;
-                    const unsigned bal = __ballot_sync(FULL, fr != 0);
-                    if (bal != 0 && myfree < 0) {
-                        const int src = __ffs(bal) - 1;
-                        const uint32_t f = __shfl_sync(FULL, fr, src);
-                        myfree = 32 * (w0 + src) + __ffs(f) - 1;
-                        if (lane == src) fr &= fr - 1;                  // S = free rows without the pivot row
-                    }
-                    if (w < WM) cand[(size_t)warp * WM + w] = fr;
+            if (jj < n) {                                             // (WM <= 32: one word per lane)
+                uint32_t fr = (lane < WM) ? (reduced_word(jj, lane) & ~ucur[lane]) : 0u;
+                const unsigned bal = __ballot_sync(FULL, fr != 0);
+                if (bal != 0) {
+                    const int src = __ffs(bal) - 1;
+                    const uint32_t f = __shfl_sync(FULL, fr, src);
+                    myfree = 32 * src + __ffs(f) - 1;
+                    if (lane == src) fr &= fr - 1;                      // S = free rows without the pivot row
                 }
+                if (lane < WM) cand[(size_t)warp * WM + lane] = fr;
             }
             if (lane == 0) s_free[warp] = myfree;
             __syncthreads();

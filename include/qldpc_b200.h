@@ -69,7 +69,8 @@ typedef struct {
                            T-lanes-per-shot shared-memory kernel, anything else the thread-per-shot kernel,
                            in shared memory when the per-shot state fits, else HBM-staged;
                            1: force the HBM-staged kernel; 2: force the thread-per-shot kernel;
-                           3: force the warp-per-shot kernel (float32 min-sum on BB-shaped H)             */
+                           3: force the warp-per-shot kernel (float32 min-sum on BB-shaped H);
+                           4: force the CTA-per-shot kernel (float32 min-sum, space-time shaped H)         */
     int32_t lanes_per_shot; /* 0: auto | 4 | 8 (T-lanes-per-shot kernel) | 32 (warp-per-shot kernel)        */
     int32_t refill_min; /* 0: auto.  Idle shots per warp that trigger a refill from the shot cursor  */
     double alpha;       /* min-sum normalisation / sum-product scaling                               */

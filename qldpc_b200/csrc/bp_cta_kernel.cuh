@@ -1,0 +1,174 @@
+// Min-sum BP, float32, messages in registers, for check matrices too large for one warp: ONE CTA PER SHOT.
+//
+// The mapping of bp_warp_kernel.cuh (a lane owns checks with their incoming messages in registers, scatters the outgoing
+// messages into the columns of their variables, owns variables, gathers posteriors) spread over the NW warps of a CTA:
+// warp w owns check slots [w*SC, (w+1)*SC) and variable slots [w*SV, (w+1)*SV) of the host-built labelling
+// (bp_warp_layout.h, which also serves rows with fewer than RW edges: their spare edge slots read a row of +inf as
+// "posterior", start at qpad >= every real |Q| and settle at +clip, so they never change a sign or a minimum).  The
+// three __syncwarp of the warp kernel become block barriers, the convergence vote a __syncthreads_and.
+// Built for the space-time matrices of the reference (spaceTime.py: 864 x 2592, row weight 7-8, column weight <= 3 =>
+// 12 warps x (3 check slots, 7 variable slots), 43 KB of shared memory per shot): the message state that the HBM-staged
+// kernel streams through global memory every iteration (12 E bytes per shot-iteration) never leaves the SM.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "bp_kernel.cuh"
+#include "bp_warp_kernel.cuh"
+
+namespace qldpc {
+
+// shared memory of a CTA: planes [3][VPL][32] + dump row + posteriors [VPL][32] + inf row, VPL = NW * SV
+__host__ __device__ inline size_t bp_cta_smem(int VPL) { return 4 * (size_t)32 * (4 * VPL + 2); }
+
+template <int SC, int SV, int RW, bool TWO>
+__global__ void __launch_bounds__(384, 1)
+bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
+{
+    const int n = P.g.n, WN = P.g.WN, WM = P.g.WM;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) unsigned char smem[];
+    float *Rbuf = reinterpret_cast<float *>(smem);                 // [3][VPL][32] + dump row
+    float *Vbuf = Rbuf + 32 * (3 * VPL + 1);                       // [VPL][32] + inf row
+    __shared__ long long s_next;
+
+    // ---- per-lane tables into registers (BYTE offsets) ------------------------------------------------
+    uint32_t sidx[SC][RW], vidx[SC][RW], cinfo[SC];
+    float prior[SV];
+#pragma unroll
+    for (int i = 0; i < SV; ++i) {
+        const uint32_t v = W.vorig[(warp * SV + i) * 32 + lane];
+        prior[i] = (v != 0xffffffffu) ? reinterpret_cast<const float *>(P.prior)[v] + 0.f : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < SC; ++i) {
+        const int ig = warp * SC + i;
+        cinfo[i] = W.cinfo[ig * 32 + lane];
+#pragma unroll
+        for (int k = 0; k < RW; ++k) {
+            vidx[i][k] = W.vidx[(ig * RW + k) * 32 + lane];
+            sidx[i][k] = W.sidx[(ig * RW + k) * 32 + lane];
+        }
+    }
+    for (int r = tid; r < 32 * (3 * VPL + 1); r += blockDim.x) Rbuf[r] = 0.f;       // columns of padding positions stay zero
+    if (tid < 32) Vbuf[VPL * 32 + tid] = CUDART_INF_F;
+
+    const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
+    const float qpad = (float)P.qpad;
+    const int max_iter = P.max_iter;
+    unsigned long long iter_sum = 0;
+
+    auto load_synd = [&](long long sh, uint32_t (&w)[SC]) {
+#pragma unroll
+        for (int i = 0; i < SC; ++i) w[i] = (sh < P.B && cinfo[i] != 0xffffffffu) ? P.synd[(size_t)sh * WM + (cinfo[i] >> 5)] : 0u;
+    };
+    if (tid == 0) s_next = (long long)atomicAdd(P.cursor, 1ull);
+    __syncthreads();
+    long long shot = s_next;
+    uint32_t sw[SC];
+    load_synd(shot, sw);
+    __syncthreads();
+
+    while (shot < P.B) {
+        if (tid == 0) s_next = (long long)atomicAdd(P.cursor, 1ull);     // read by everyone after iteration 0
+        long long next_shot = 0;
+        uint32_t sbit[SC];
+        float salpha[SC];
+#pragma unroll
+        for (int i = 0; i < SC; ++i) {
+            sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
+            salpha[i] = __uint_as_float(__float_as_uint(alpha) ^ sbit[i]);
+        }
+        // Q = prior along the edges (decoding.py:21)
+#pragma unroll
+        for (int i = 0; i < SV; ++i) Vbuf[(warp * SV + i) * 32 + lane] = prior[i] + 0.f;
+        __syncthreads();
+        float Q[SC][RW];
+#pragma unroll
+        for (int i = 0; i < SC; ++i)
+#pragma unroll
+            for (int k = 0; k < RW; ++k) Q[i][k] = fminf(ldb(Vbuf, vidx[i][k]), qpad);
+
+        int iter = 0;
+        bool conv = false;
+        for (;; ++iter) {
+            // ================= horizontal step (lane-local; see bp_warp_kernel.cuh) =================
+            float R[SC][RW];
+#pragma unroll
+            for (int i = 0; i < SC; ++i) {
+                float pre[RW], suf[RW];
+                pre[1] = Q[i][0];
+                suf[RW - 2] = Q[i][RW - 1];
+#pragma unroll
+                for (int k = 2; k < RW; ++k) pre[k] = bpw_xmin(pre[k - 1], Q[i][k - 1]);
+#pragma unroll
+                for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_xmin(suf[k + 1], Q[i][k + 1]);
+#pragma unroll
+                for (int k = 0; k < RW; ++k) {
+                    const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
+                    const float r = __fmul_rn(o, salpha[i]);
+                    R[i][k] = r;
+                    if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + ((warp * SC + i) * RW + k) * 32 + lane), r);
+                    else stb(Rbuf, sidx[i][k], r);
+                }
+            }
+            __syncthreads();
+
+            // ================= vertical step: posteriors of the owned variables =====================
+            const bool last = (iter == max_iter - 1);
+#pragma unroll
+            for (int i = 0; i < SV; ++i) {
+                const int ig = warp * SV + i;
+                const float r0 = Rbuf[(0 * VPL + ig) * 32 + lane], r1 = Rbuf[(1 * VPL + ig) * 32 + lane], r2 = Rbuf[(2 * VPL + ig) * 32 + lane];
+                Vbuf[ig * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);
+            }
+            __syncthreads();
+
+            // ================= Q update in registers + syndrome of the hard decision =================
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < SC; ++i) {
+                uint32_t par = sbit[i];
+#pragma unroll
+                for (int k = 0; k < RW; ++k) {
+                    const float val = ldb(Vbuf, vidx[i][k]);
+                    par ^= __float_as_uint(val);            // (+inf of a padding slot: sign 0)
+                    float qn = __fsub_rn(val, R[i][k]);
+                    qn = bp_damp(damp, qn, omd, Q[i][k]);
+                    qn = fminf(fmaxf(qn, -clipv), clipv);
+                    Q[i][k] = qn;
+                }
+                ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);
+            }
+            conv = __syncthreads_and(ok) != 0;
+            if (iter == 0) {
+                next_shot = s_next;
+                load_synd(next_shot, sw);
+            }
+            if (conv || last) break;
+        }
+
+        // ---- retire the shot: hard decision = sign of the posteriors, in the order of H ----------------------
+        const bool wr_llr = P.llr != nullptr && (P.llr_mode == LLR_ALL || (P.llr_mode == LLR_FAILED && !conv));
+        for (int i = warp; i < WN; i += NW) {
+            const bool valid = lane + 32 * i < n;
+            const float val = valid ? ldb(Vbuf, __ldg(W.vpos + i * 32 + lane)) : 0.f;
+            const uint32_t w = __ballot_sync(FULL, valid && (val < 0.f));
+            if (lane == 0) P.hard[(size_t)shot * WN + i] = w;
+            if (wr_llr && valid) reinterpret_cast<float *>(P.llr)[(size_t)shot * n + lane + 32 * i] = val;
+        }
+        if (tid == 0) {
+            P.conv[shot] = conv ? 1 : 0;
+            if (P.iters) P.iters[shot] = iter;
+            if (!conv && P.fail_idx) P.fail_idx[atomicAdd(P.fail_count, 1u)] = (int32_t)shot;
+            iter_sum += (unsigned long long)(iter + 1);
+        }
+        shot = next_shot;
+        __syncthreads();                           // the posteriors are overwritten by the next shot's priors
+    }
+    if (P.iter_total && tid == 0 && iter_sum) atomicAdd(P.iter_total, iter_sum);
+}
+
+}  // namespace qldpc

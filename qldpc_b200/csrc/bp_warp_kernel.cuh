@@ -33,8 +33,9 @@ __device__ __forceinline__ float ldb(const float *base, uint32_t byte_off)
     return *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(base) + byte_off);
 }
 
-// per-warp shared memory: message planes [3][VPL][32] + one dump row [32] (padding lanes) + posteriors [VPL][32]
-__host__ __device__ inline size_t bp_warp_smem_per_warp(int VPL) { return 4 * (size_t)32 * (4 * VPL + 1); }
+// per-warp shared memory: message planes [3][VPL][32] + one dump row [32] (padding lanes) + posteriors [VPL][32] + a row of
+// +inf (what padding edge slots read as their "posterior")
+__host__ __device__ inline size_t bp_warp_smem_per_warp(int VPL) { return 4 * (size_t)32 * (4 * VPL + 2); }
 
 __device__ __forceinline__ void stb(float *base, uint32_t byte_off, float v)
 {
@@ -94,6 +95,8 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
     }
 #pragma unroll
     for (int r = 0; r < 3 * VPL + 1; ++r) Rbuf[r * 32 + lane] = 0.f;      // columns of padding positions stay zero for ever
+    Vbuf[VPL * 32 + lane] = CUDART_INF_F;
+    const float qpad = (float)P.qpad;
 
     const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
     const int max_iter = P.max_iter;
@@ -130,7 +133,7 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
         for (int i = 0; i < CPL; ++i)
 #pragma unroll
-            for (int k = 0; k < RW; ++k) Q[i][k] = ldb(Vbuf, vidx[i][k]);
+            for (int k = 0; k < RW; ++k) Q[i][k] = fminf(ldb(Vbuf, vidx[i][k]), qpad);      // padding slots start at qpad (>= every real |Q|)
 
         int iter = 0;
         bool conv = false;

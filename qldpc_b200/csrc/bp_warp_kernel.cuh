@@ -96,7 +96,6 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
     for (int r = 0; r < 3 * VPL + 1; ++r) Rbuf[r * 32 + lane] = 0.f;      // columns of padding positions stay zero for ever
     Vbuf[VPL * 32 + lane] = CUDART_INF_F;
-    const float qpad = (float)P.qpad;
 
     const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
     const int max_iter = P.max_iter;
@@ -133,7 +132,8 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
         for (int i = 0; i < CPL; ++i)
 #pragma unroll
-            for (int k = 0; k < RW; ++k) Q[i][k] = fminf(ldb(Vbuf, vidx[i][k]), qpad);      // padding slots start at qpad (>= every real |Q|)
+            for (int k = 0; k < RW; ++k) Q[i][k] = ldb(Vbuf, vidx[i][k]);      // (every check has RW edges here: only whole padding
+                                                                                 //  lanes read the +inf row, and nothing reads them)
 
         int iter = 0;
         bool conv = false;

@@ -774,11 +774,36 @@ static cudaError_t launch_osd_fast_inst(const qldpc_code *c, const OSDParams &P,
     return cudaGetLastError();
 }
 
+template <typename K, int WM, int NS2>
+static cudaError_t launch_osd_fast2_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
+{
+    auto kern = osd0_fast2_kernel<K, WM, NS2>;
+    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS * 2;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_WARPS * 32, smem);
+    long long grid = (long long)c->num_sms * std::max(1, occ);
+    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, (count_hint + 2 * OSD_WARPS - 1) / (2 * OSD_WARPS)));
+    kern<<<(int)grid, OSD_WARPS * 32, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
 // column-major kernel: the shapes of the reference's codes (m <= 160, n <= 288); cudaErrorNotSupported otherwise
 template <typename K>
 static cudaError_t launch_osd_fast(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
 {
     const int NS = (P.n + 31) / 32;
+    static const bool one_per_warp = getenv("QLDPC_OSD_ONE_SHOT_PER_WARP") != nullptr;    // test / comparison hook
+    if (!one_per_warp) {                       // two shots per warp where the registers allow it
+        const int NS2 = (P.n + 15) / 16;
+        if (P.WM == 2 && NS2 == 5) return launch_osd_fast2_inst<K, 2, 5>(c, P, count_hint, st);
+        if (P.WM == 2 && NS2 == 6) return launch_osd_fast2_inst<K, 2, 6>(c, P, count_hint, st);
+        if (P.WM == 2 && NS2 == 7) return launch_osd_fast2_inst<K, 2, 7>(c, P, count_hint, st);
+        if (P.WM == 3 && NS2 == 9) return launch_osd_fast2_inst<K, 3, 9>(c, P, count_hint, st);
+    }
     if (P.WM == 2 && NS == 3) return launch_osd_fast_inst<K, 2, 3>(c, P, count_hint, st);
     if (P.WM == 2 && NS == 4) return launch_osd_fast_inst<K, 2, 4>(c, P, count_hint, st);
     if (P.WM == 3 && NS == 5) return launch_osd_fast_inst<K, 3, 5>(c, P, count_hint, st);

@@ -464,6 +464,206 @@ osd0_fast_kernel(const OSDParams P)
 
 
 // ------------------------------------------------------------------------------------------------
+// osd0_fast_kernel with TWO shots per warp (16 lanes each): the ~50 warp-level instructions that find and broadcast a
+// pivot, and every instruction of the column update, now serve two shots, and a lane's rank counting serves twice as
+// many of its own keys per broadcast key.  Nothing is warp-uniform any more (the halves pivot different rows), so the
+// pivot word is picked with selects and a half without a pivot left runs the round with an empty pivot mask (no-ops).
+// The two halves walk the register slots together (slot s holds the columns at sorted positions 16 s + lane-in-half).
+// ------------------------------------------------------------------------------------------------
+template <typename K, int WM, int NS2>
+__global__ void __launch_bounds__(OSD_WARPS * 32)
+osd0_fast2_kernel(const OSDParams P)
+{
+    typedef typename KeyBits<K>::type kbits;
+    const int m = P.m, n = P.n, WN = P.WN;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *cmask = reinterpret_cast<uint32_t *>(smem);
+    for (int i = threadIdx.x; i < n * WM; i += blockDim.x) cmask[i] = P.colmask[i];
+    __syncthreads();
+    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * (2 * warp + half);
+    kbits *keys = reinterpret_cast<kbits *>(base);
+    uint16_t *ord = reinterpret_cast<uint16_t *>(base + sizeof(kbits) * (size_t)n);
+    uint32_t *solw = reinterpret_cast<uint32_t *>(base + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
+
+    const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
+    const long long npairs = (long long)gridDim.x * OSD_WARPS;
+    const unsigned FULL = 0xffffffffu;
+    const int rank = P.rank;
+
+    for (long long pair = (long long)blockIdx.x * OSD_WARPS + warp; 2 * pair < count; pair += npairs) {
+        const long long it = 2 * pair + half;
+        const bool live_half = it < count;                                  // (an odd count leaves the last half empty)
+        const long long shot = live_half ? (P.idx ? (long long)P.idx[it] : it) : 0;
+        const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
+        const uint32_t *hard = P.hard + (size_t)shot * WN;
+
+        // ---- ordering = argsort(|llr|), stable (OSD.py:10-11): rank by counting within the half ----------
+        kbits ki[NS2];
+        int cnt[NS2];
+#pragma unroll
+        for (int t = 0; t < NS2; ++t) {
+            const int i = 16 * t + hl;
+            ki[t] = (i < n) ? KeyBits<K>::get(llr[i]) : ~(kbits)0;        // padding sorts last
+            if (i < n) keys[i] = ki[t];
+            cnt[t] = 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int jb = 0; jb < NS2; ++jb) {                                   // keys 16 jb .. 16 jb + 15
+            kbits thr[NS2];
+#pragma unroll
+            for (int t = 0; t < NS2; ++t) thr[t] = (jb < t) ? ki[t] + (kbits)1 : ki[t];    // j < i: count key_j <= key_i
+            const int jend = min(16, n - 16 * jb);
+#pragma unroll 4
+            for (int jl = 0; jl < jend; ++jl) {
+                const kbits kj = keys[16 * jb + jl];
+#pragma unroll
+                for (int t = 0; t < NS2; ++t) {
+                    if (t == jb) osd_count_lt(cnt[t], kj, ki[t] + (kbits)(jl < hl));      // diagonal block: tie rule per lane
+                    else osd_count_lt(cnt[t], kj, thr[t]);
+                }
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < NS2; ++t) if (16 * t + hl < n) ord[-cnt[t]] = (uint16_t)(16 * t + hl);
+        __syncwarp();
+
+        // ---- residual syndrome s ^ H*hard (OSD.py:7-8), uniform within the half --------------------------
+        uint32_t b[WM];
+#pragma unroll
+        for (int w = 0; w < WM; ++w) b[w] = 0;
+        for (int v = hl; v < n; v += 16) {
+            if ((hard[v >> 5] >> (v & 31)) & 1u) {
+#pragma unroll
+                for (int w = 0; w < WM; ++w) b[w] ^= cmask[v * WM + w];
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < WM; ++w) {
+#pragma unroll
+            for (int o = 8; o >= 1; o >>= 1) b[w] ^= __shfl_xor_sync(FULL, b[w], o);
+            b[w] ^= P.synd[(size_t)shot * WM + w];
+        }
+
+        // ---- the columns in sorted order, WM words each ---------------------------------------------------
+        uint32_t c[NS2][WM];
+        int prow[NS2];
+#pragma unroll
+        for (int s = 0; s < NS2; ++s) {
+            const int j = 16 * s + hl;
+            const int col = (j < n) ? ord[j] : 0;
+#pragma unroll
+            for (int w = 0; w < WM; ++w) c[s][w] = (j < n && live_half) ? cmask[col * WM + w] : 0u;
+            prow[s] = -1;
+        }
+
+        // ---- elimination -------------------------------------------------------------------------------------
+        uint32_t used[WM];
+#pragma unroll
+        for (int w = 0; w < WM; ++w) used[w] = 0;
+        int npiv = 0;
+#pragma unroll
+        for (int s = 0; s < NS2; ++s) {
+            unsigned todo = 0xffffu;
+            while (true) {
+                uint32_t freebits = 0;
+#pragma unroll
+                for (int w = 0; w < WM; ++w) freebits |= c[s][w] & ~used[w];
+                const unsigned mine = (__ballot_sync(FULL, freebits != 0) >> (16 * half)) & todo;
+                const bool act = (npiv < rank) && (mine != 0);                 // this half pivots in this round
+                if (!__any_sync(FULL, act)) break;
+                const int l = act ? (__ffs(mine) - 1) : 0;
+                if (act) todo &= ~((2u << l) - 1u);
+                uint32_t col[WM], fr[WM];
+#pragma unroll
+                for (int w = 0; w < WM; ++w) {
+                    col[w] = __shfl_sync(FULL, c[s][w], 16 * half + l);
+                    fr[w] = col[w] & ~used[w];
+                }
+                int pw = WM - 1;
+                uint32_t fw = fr[WM - 1];
+#pragma unroll
+                for (int w = WM - 2; w >= 0; --w)
+                    if (fr[w] != 0) { pw = w; fw = fr[w]; }                  // first word with a free row
+                const uint32_t pbit = act ? (fw & (0u - fw)) : 0u;           // empty mask: the round is a no-op for this half
+                if (act && hl == l) prow[s] = 32 * pw + __ffs(pbit) - 1;
+                npiv += act ? 1 : 0;
+                uint32_t bsel = b[0];
+#pragma unroll
+                for (int w = 0; w < WM; ++w) {
+                    const uint32_t pm = (w == pw) ? pbit : 0u;
+                    used[w] |= pm;
+                    col[w] &= ~pm;                                           // the pivot row itself is not touched
+                    if (w == pw) bsel = b[w];
+                }
+                const uint32_t bm = (bsel & pbit) ? 0xffffffffu : 0u;
+#pragma unroll
+                for (int w = 0; w < WM; ++w) b[w] ^= col[w] & bm;
+#pragma unroll
+                for (int s2 = s; s2 < NS2; ++s2) {                            // (earlier positions are finished)
+                    uint32_t cw = c[s2][0];
+#pragma unroll
+                    for (int w = 1; w < WM; ++w) if (w == pw) cw = c[s2][w];
+                    const uint32_t cm = (cw & pbit) ? 0xffffffffu : 0u;
+#pragma unroll
+                    for (int w = 0; w < WM; ++w) c[s2][w] ^= col[w] & cm;
+                }
+            }
+        }
+
+        // ---- validity; e[pivot column] = reduced syndrome at its pivot row; xor hard (OSD.py:16-26) -----
+        bool bad = false;
+#pragma unroll
+        for (int w = 0; w < WM; ++w) {
+            const int rows = m - 32 * w;
+            const uint32_t live = rows >= 32 ? 0xffffffffu : (rows > 0 ? ((1u << rows) - 1u) : 0u);
+            bad = bad || ((b[w] & ~used[w] & live) != 0);
+        }
+        bad = bad && live_half;
+        if (!bad && live_half) {
+            for (int w = hl; w < WN; w += 16) solw[w] = hard[w];
+        }
+        __syncwarp();
+        if (!bad && live_half) {
+#pragma unroll
+            for (int s = 0; s < NS2; ++s) {
+                if (prow[s] >= 0) {
+                    uint32_t bw = b[0];
+#pragma unroll
+                    for (int w = 1; w < WM; ++w) if ((prow[s] >> 5) == w) bw = b[w];
+                    if ((bw >> (prow[s] & 31)) & 1u) {
+                        const int v = ord[16 * s + hl];
+                        atomicXor(&solw[v >> 5], 1u << (v & 31));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        if (!bad && live_half) {
+            for (int w = hl; w < WN; w += 16) P.out[(size_t)shot * WN + w] = solw[w];
+            if (hl == 0 && P.valid) P.valid[shot] = 1;
+        }
+        // Inconsistent syndrome (never the case for s = e H^T): redo that shot with the row-major rule, the whole warp on it.
+        const unsigned badmask = __ballot_sync(FULL, bad);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            if ((badmask >> (16 * h)) & 1u) {
+                const long long it_h = 2 * pair + h;
+                const long long shot_h = P.idx ? (long long)P.idx[it_h] : it_h;
+                unsigned char *base_h = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * (2 * warp + h);
+                uint16_t *ord_h = reinterpret_cast<uint16_t *>(base_h + sizeof(kbits) * (size_t)n);
+                uint32_t *solw_h = reinterpret_cast<uint32_t *>(base_h + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
+                osd0_rowmajor_shot<K, WM>(P, it_h, shot_h, cmask, ord_h, solw_h, lane);
+                __syncwarp();
+            }
+        }
+        __syncwarp();
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // OSD-0 for large check matrices (space-time / detector-error-model H: m > 160), one CTA per shot.
 //
 // Same algorithm and the same transform-matrix formulation as osd0_kernel, but T (m x m bits), the

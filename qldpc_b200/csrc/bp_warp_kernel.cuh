@@ -51,6 +51,37 @@ __device__ __forceinline__ float bpw_xmin(float a, float b)
     return d;
 }
 
+// psi(a) = -log(tanh(a / 2)) = log((1 + e^-a) / (1 - e^-a)) for a >= 0, its own inverse.  The sum-product check update in
+// the psi domain: |R_k| = 2 atanh(prod_{j != k} tanh(|Q_j| / 2)) = psi(sum_{j != k} psi(|Q_j|)).  Unlike the tanh domain,
+// float32 keeps its RELATIVE accuracy over the whole range here: near saturation the tanh product sits within 1e-7 of 1,
+// below the float32 resolution, while psi of a large argument is a tiny number with a full mantissa.
+//   a >= 1: u = e^-a <= 0.37, psi = 2 atanh(u) by its odd series (truncation < 5e-7 relative);
+//   a <  1: 1 - e^-a = -expm1(-a) by its series (no cancellation), psi = log((1 + u) / (1 - u)) >= 0.77.
+// psi(0) is clamped to psi at tanh = 1e-15, the reference's guard (beliefPropagation.py:122).
+__device__ __forceinline__ float bpw_psi(float a)
+{
+    const float u = __expf(-a);
+    const float u2 = u * u;
+    float big = fmaf(u2, 1.f / 11.f, 1.f / 9.f);
+    big = fmaf(u2, big, 1.f / 7.f);
+    big = fmaf(u2, big, 1.f / 5.f);
+    big = fmaf(u2, big, 1.f / 3.f);
+    big = fmaf(u2, big, 1.f);
+    big = 2.f * u * big;
+    const float z = -fminf(a, 1.f);
+    float e = fmaf(z, 1.f / 362880.f, 1.f / 40320.f);          // expm1(z) / z, degree 8 in z, |z| <= 1
+    e = fmaf(z, e, 1.f / 5040.f);
+    e = fmaf(z, e, 1.f / 720.f);
+    e = fmaf(z, e, 1.f / 120.f);
+    e = fmaf(z, e, 1.f / 24.f);
+    e = fmaf(z, e, 1.f / 6.f);
+    e = fmaf(z, e, 0.5f);
+    e = fmaf(z, e, 1.f);
+    const float d = -z * e;                                     // 1 - e^-a
+    const float small = __logf(__fdividef(2.f - d, d));
+    return fminf((a >= 1.f) ? big : small, 34.538776394910684f);
+}
+
 // Tables (global, built by the host -- bp_warp_layout.h -- for a labelling "position = slot * 32 + lane" of the checks
 // and of the variables that it is free to choose):
 //   sidx  [CPL*RW][32] byte offset in the message planes where edge slot k of the check at (i, lane) delivers its
@@ -65,7 +96,9 @@ struct BPWarpTables {
     const uint32_t *sidx, *sidx0, *vidx, *cinfo, *vorig, *vpos;
 };
 
-template <int CPL, int VPL, int RW, bool TWO>
+// VAR: 0 = normalised / damped / clipped min-sum (rework/decoding.py:5-75), 1 = sum-product (beliefPropagation.py:88-144),
+// 2 = sum-product with alpha, damping and clipping (rework/decoding.py:131-191); 1 and 2 in the psi domain (above).
+template <int CPL, int VPL, int RW, bool TWO, int VAR>
 __global__ void __launch_bounds__(BPW_WARPS * 32, (CPL * RW + VPL * 4 > 44) ? 1 : 2)
 bp_warp_kernel(const BPParams P, const BPWarpTables W)
 {
@@ -121,7 +154,7 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
         for (int i = 0; i < CPL; ++i) {
             sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
-            salpha[i] = __uint_as_float(__float_as_uint(alpha) ^ sbit[i]);
+            salpha[i] = __uint_as_float(__float_as_uint(VAR == 1 ? 1.f : alpha) ^ sbit[i]);
         }
         // Q = where(mask, prior, 0) (decoding.py:21): publish the priors, gather them along the edges
         __syncwarp();
@@ -146,16 +179,43 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 float pre[RW], suf[RW];
-                pre[1] = Q[i][0];
-                suf[RW - 2] = Q[i][RW - 1];
+                if (VAR == 0) {
+                    pre[1] = Q[i][0];
+                    suf[RW - 2] = Q[i][RW - 1];
 #pragma unroll
-                for (int k = 2; k < RW; ++k) pre[k] = bpw_xmin(pre[k - 1], Q[i][k - 1]);
+                    for (int k = 2; k < RW; ++k) pre[k] = bpw_xmin(pre[k - 1], Q[i][k - 1]);
 #pragma unroll
-                for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_xmin(suf[k + 1], Q[i][k + 1]);
+                    for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_xmin(suf[k + 1], Q[i][k + 1]);
+                } else {
+                    // psi domain: "all but k" = prefix + suffix SUMS of psi(|Q|) (no subtraction: no cancellation)
+                    float ps[RW];
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) ps[k] = bpw_psi(fabsf(Q[i][k]));
+                    pre[1] = ps[0];
+                    suf[RW - 2] = ps[RW - 1];
+#pragma unroll
+                    for (int k = 2; k < RW; ++k) pre[k] = pre[k - 1] + ps[k - 1];
+#pragma unroll
+                    for (int k = RW - 3; k >= 0; --k) suf[k] = suf[k + 1] + ps[k + 1];
+                }
+                uint32_t sgall = 0;                                    // xor of all sign bits (sum-product)
+                if (VAR != 0) {
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) sgall ^= __float_as_uint(Q[i][k]);
+                }
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
-                    const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
-                    const float r = __fmul_rn(o, salpha[i]);       // (+-alpha) * (+-magnitude): same rounding as alpha * magnitude
+                    float r;
+                    if (VAR == 0) {
+                        const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
+                        r = __fmul_rn(o, salpha[i]);       // (+-alpha) * (+-magnitude): same rounding as alpha * magnitude
+                    } else {
+                        const float sk = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : pre[k] + suf[k];
+                        // 2 atanh(clip(prod, 0.9999999)) (beliefPropagation.py:125-126): saturates at 16.81
+                        const float mag = fminf(bpw_psi(sk), 16.811242831518264f);
+                        const float signedmag = __uint_as_float(__float_as_uint(mag) | ((sgall ^ __float_as_uint(Q[i][k])) & 0x80000000u));
+                        r = __fmul_rn(signedmag, salpha[i]);           // (-1)^s, times alpha for the symmetric variant
+                    }
                     R[i][k] = r;
                     if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + (i * RW + k) * 32 + lane), r);
                     else stb(Rbuf, sidx[i][k], r);       // (padding lanes write garbage into the dump row)
@@ -184,8 +244,10 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
                     const float val = ldb(Vbuf, vidx[i][k]);
                     par ^= __float_as_uint(val);            // sign bit == hard decision (a sum with a non-zero prior is never -0.0)
                     float qn = __fsub_rn(val, R[i][k]);                                           // :63
-                    qn = bp_damp(damp, qn, omd, Q[i][k]);                                         // :65
-                    qn = fminf(fmaxf(qn, -clipv), clipv);                                         // :66
+                    if (VAR != 1) {                                                               // (plain sum-product: Q = values - R)
+                        qn = bp_damp(damp, qn, omd, Q[i][k]);                                     // :65
+                        qn = fminf(fmaxf(qn, -clipv), clipv);                                     // :66
+                    }
                     Q[i][k] = qn;
                 }
                 ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);

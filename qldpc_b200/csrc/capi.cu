@@ -409,6 +409,7 @@ struct BPGeom {
     bool staged;
     int tiled_T;          // 0: thread-per-shot kernels; 4 / 8: lanes per shot of the tiled kernel
     bool warp_kernel;     // warp-per-shot kernel (messages in registers)
+    int warp_var;         // its variant: 0 min-sum, 1 sum-product, 2 symmetric sum-product
     bool cta_kernel;      // CTA-per-shot kernel (messages in registers, several warps per shot)
     int shots_per_cta;
     int refill_min;
@@ -439,10 +440,11 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->gstate_bytes = 0;
         return QLDPC_OK;
     }
-    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM &&
+    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && cfg->precision == 32 &&
         (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
         G->staged = false;
         G->warp_kernel = true;
+        G->warp_var = cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2);
         G->threads = BPW_WARPS * 32;
         G->shots_per_cta = BPW_WARPS;
         G->smem = bp_warp_smem_per_warp(c->WN) * BPW_WARPS;
@@ -599,10 +601,10 @@ static cudaError_t launch_bp_tiled_w(const qldpc_code *c, const BPParams &P, con
     }
 }
 
-template <int CPL, int VPL, bool TWO>
-static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+template <int CPL, int VPL, bool TWO, int VAR>
+static cudaError_t launch_bp_warp_inst3(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    auto kern = bp_warp_kernel<CPL, VPL, 6, TWO>;
+    auto kern = bp_warp_kernel<CPL, VPL, 6, TWO, VAR>;
     if (G.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
         if (e != cudaSuccess) return e;
@@ -612,6 +614,14 @@ static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, 
     const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
     kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
     return cudaGetLastError();
+}
+
+template <int CPL, int VPL, bool TWO>
+static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    if (G.warp_var == 0) return launch_bp_warp_inst3<CPL, VPL, TWO, 0>(c, P, G, st);
+    if (G.warp_var == 1) return launch_bp_warp_inst3<CPL, VPL, TWO, 1>(c, P, G, st);
+    return launch_bp_warp_inst3<CPL, VPL, TWO, 2>(c, P, G, st);
 }
 
 template <int CPL, int VPL>

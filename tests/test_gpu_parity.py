@@ -140,6 +140,35 @@ def test_sum_product_f32_accuracy_is_measured_not_assumed(bp_golden):
     assert worst < 0.05
 
 
+def test_sum_product_f32_psi_domain_kernel_vs_f64():
+    """The float32 sum-product of the warp-per-shot kernel works in the psi domain (psi(a) = -log tanh(a/2)), which keeps
+    float32's relative accuracy near the check-node saturation where the tanh domain cannot: against the float64 kernel
+    it must (almost always) take the same decisions and exit at the same iteration, with a 99th-percentile relative LLR
+    error below 1e-4, and beat the tanh-domain float32 kernel on both counts."""
+    H, L = load_code_file("[[144, 12, 12]]")
+    n = H.shape[1]
+    from qldpc_b200 import Code, graph
+    code = Code(H, L, (graph.SEQ, graph.SEQ))
+    rng = np.random.default_rng(31)
+    err = (rng.random((6000, n)) < 0.05).astype(np.uint8)
+    synd = _synd(H, err)
+    prior = _prior(0.05, n)
+    for variant, kw in (("sum_product", {}), ("sum_product_sym", dict(alpha=0.9, damping=0.8, clip=20.0))):
+        ref = code.bp_decode_batch(synd, prior, variant, 50, precision=64, **kw)
+        stats = {}
+        for label, extra in (("psi", {}), ("tanh", dict(lanes_per_shot=8))):
+            cfg = code.config(variant, 50, precision=32, **extra, **kw)
+            assert code.geometry(cfg)["kernel"] == ("warp_per_shot" if label == "psi" else "tiled")
+            got = code.bp_decode_batch(synd, prior, variant, 50, precision=32, **extra, **kw)
+            same = (got[1] == ref[1]) & (got[3] == ref[3]) & (got[0] == ref[0]).all(1)
+            sel = ref[1] & same
+            rel = np.abs(got[2][sel] - ref[2][sel]) / np.maximum(np.abs(ref[2][sel]), 1e-3)
+            stats[label] = (same.mean(), np.quantile(rel, 0.99))
+        print(f"\n[f32 {variant}] identical fraction / q99 rel. LLR error: psi {stats['psi']}, tanh {stats['tanh']}")
+        assert stats["psi"][0] >= 0.99 and stats["psi"][1] < 1e-4, stats
+        assert stats["psi"][0] >= stats["tanh"][0] and stats["psi"][1] <= stats["tanh"][1], stats
+
+
 def test_non_uniform_prior_and_loop_version(bp_golden):
     d, meta = bp_golden
     H, _ = load_code_file("[[72, 12, 6]]")
@@ -291,9 +320,9 @@ def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
                                       ("sum_product_sym", 64, 0.9, 0.8, 20.0), ("sum_product", 32, 1.0, 1.0, 20.0),
                                       ("sum_product_sym", 32, 0.9, 0.8, 20.0)):
         k2 = dict(variant=variant, max_iter=40, alpha=al, damping=dm, clip=cl, precision=prec)
-        assert code.geometry(code.config(**k2))["kernel"] == "tiled"
+        assert code.geometry(code.config(lanes_per_shot=8, **k2))["kernel"] == "tiled"
         a = code.bp_decode_batch(synd[:1500], prior, staged=2, **k2)
-        b = code.bp_decode_batch(synd[:1500], prior, **k2)
+        b = code.bp_decode_batch(synd[:1500], prior, lanes_per_shot=8, **k2)
         for x, y in zip(a, b):
             assert np.array_equal(x, y), (stem, variant, prec)
     # non-uniform prior and default parameters (alpha = damping = 1)

@@ -15,6 +15,7 @@
 #include "bp_tiled_kernel.cuh"
 #include "bp_warp_kernel.cuh"
 #include "bp_cta_kernel.cuh"
+#include "bp_warp_kernel_f64.cuh"
 #include "bp_warp_layout.h"
 #include "misc_kernels.cuh"
 #include "osd_kernel.cuh"
@@ -440,14 +441,15 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->gstate_bytes = 0;
         return QLDPC_OK;
     }
-    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && cfg->precision == 32 &&
+    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && (cfg->precision == 32 || cfg->variant == QLDPC_MIN_SUM) &&
         (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
         G->staged = false;
         G->warp_kernel = true;
-        G->warp_var = cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2);
+        // 0 min-sum, 1 sum-product, 2 symmetric sum-product (float32); 3 float64 min-sum (the bit-exact parity mode)
+        G->warp_var = cfg->precision == 64 ? 3 : (cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2));
         G->threads = BPW_WARPS * 32;
         G->shots_per_cta = BPW_WARPS;
-        G->smem = bp_warp_smem_per_warp(c->WN) * BPW_WARPS;
+        G->smem = bp_warp_smem_per_warp(c->WN) * BPW_WARPS * (cfg->precision == 64 ? 2 : 1);
         G->grid = 0;                 // filled at launch from the occupancy query
         G->gstate_bytes = 0;
         return QLDPC_OK;
@@ -617,8 +619,24 @@ static cudaError_t launch_bp_warp_inst3(const qldpc_code *c, const BPParams &P, 
 }
 
 template <int CPL, int VPL, bool TWO>
+static cudaError_t launch_bp_warp_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    auto kern = bp_warp_kernel_f64<CPL, VPL, 6, TWO>;
+    if (G.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
+    return cudaGetLastError();
+}
+
+template <int CPL, int VPL, bool TWO>
 static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
+    if (G.warp_var == 3) return launch_bp_warp_f64<CPL, VPL, TWO>(c, P, G, st);
     if (G.warp_var == 0) return launch_bp_warp_inst3<CPL, VPL, TWO, 0>(c, P, G, st);
     if (G.warp_var == 1) return launch_bp_warp_inst3<CPL, VPL, TWO, 1>(c, P, G, st);
     return launch_bp_warp_inst3<CPL, VPL, TWO, 2>(c, P, G, st);

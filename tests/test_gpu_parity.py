@@ -315,6 +315,14 @@ def test_tiled_kernel_bit_identical_to_thread_per_shot(stem, p):
         got = code.bp_decode_batch(synd[:B], prior, **kw)
         for x, y in zip(got, ref):
             assert np.array_equal(x, y[:B])
+    # float64 min-sum (the bit-exact parity mode): warp-per-shot kernel by default
+    k64 = dict(variant="min_sum", max_iter=60, alpha=0.8, damping=0.7, clip=25.0, precision=64)
+    assert code.geometry(code.config(**k64))["kernel"] == "warp_per_shot"
+    a = code.bp_decode_batch(synd[:2000], prior, staged=2, **k64)
+    for extra in (dict(), dict(lanes_per_shot=8)):
+        b = code.bp_decode_batch(synd[:2000], prior, **extra, **k64)
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y), (stem, "float64", extra)
     # the other instantiations of the tiled kernel: float64 min-sum, sum-product (plain and damped) in both precisions
     for variant, prec, al, dm, cl in (("min_sum", 64, 0.8, 0.7, 25.0), ("sum_product", 64, 1.0, 1.0, 20.0),
                                       ("sum_product_sym", 64, 0.9, 0.8, 20.0), ("sum_product", 32, 1.0, 1.0, 20.0),

@@ -104,12 +104,13 @@ int qldpc_bp_geometry(qldpc_code *code, const qldpc_bp_config *cfg, int32_t *sho
  * optimised order the float32 kernel uses (`after`). */
 int qldpc_tiled_conflict_model(qldpc_code *code, int32_t lanes_per_shot, double *before, double *after);
 
-/* Warp-per-shot kernel (float32 min-sum on BB-shaped H): which lane owns which check / variable is free, and decides
- * the bank conflicts of the kernel's two shared-memory gathers.  Starts from the natural labelling; `steps` > 0 runs
- * that many steps of a deterministic simulated annealing on the modelled wavefront count (about 2.6 us per step, so
- * one-time set-up work outside any timed region), `steps` < 0 goes back to the natural labelling, 0 only reports.
- * Results of the kernel do not depend on the labelling (bit-identical).  Synchronises the device.
- *   cost[3] <- modelled gather wavefronts per shot-iteration: natural labelling, current labelling, floor.
+/* Warp-per-shot kernels (BB-shaped H): which lane owns which check / variable and in which register slot an edge sits
+ * is free, and decides the bank conflicts of the kernel's shared-memory scatter and gather.  qldpc_code_create builds a
+ * conflict-free labelling (balanced check slots, degree-bounded placement of the variables, Koenig edge colouring; < 1 ms
+ * for the reference's codes).  This call reports it and lets tests switch: `steps` < 0 installs the natural labelling
+ * (check c at lane c mod 32, ...), `steps` > 0 rebuilds the constructed one with that search budget, 0 only reports.
+ * Results of the kernels do not depend on the labelling (bit-identical).  Synchronises the device.
+ *   cost[3] <- modelled scatter + gather wavefronts per shot-iteration: natural labelling, current labelling, floor.
  * QLDPC_ERR_UNSUPPORTED when the kernel does not apply to this code. */
 int qldpc_warp_layout_tune(qldpc_code *code, int64_t steps, int32_t *cost);
 

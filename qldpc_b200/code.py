@@ -104,10 +104,10 @@ class Code:
                     lanes_per_shot=(0 if kind == 133 else kind - 100 if kind >= 100 else 1),
                     kernel=('hbm_staged' if kind == 1 else 'cta_per_shot' if kind == 133 else 'warp_per_shot' if kind == 132 else 'tiled' if kind >= 100 else 'thread_per_shot'))
 
-    def tune_warp_layout(self, steps=1_000_000):
-        """Bank-conflict search for the warp-per-shot kernel's labelling (one-time set-up, ~2.6 us per step; results
-        of the kernel are unchanged).  steps < 0: back to the natural labelling; 0: report only.
-        -> dict(natural, current, floor) modelled gather wavefronts per shot-iteration."""
+    def tune_warp_layout(self, steps=0):
+        """Lane labelling of the warp-per-shot kernels (results never depend on it).  steps = 0: report; steps < 0: install
+        the natural labelling; steps > 0: rebuild the constructed (conflict-free) one with that search budget.
+        -> dict(natural, current, floor): modelled scatter + gather wavefronts per shot-iteration."""
         cost = (ctypes.c_int32 * 3)()
         _lib.check(_lib.lib().qldpc_warp_layout_tune(self._h, int(steps), cost))
         return dict(natural=cost[0], current=cost[1], floor=cost[2])

@@ -60,6 +60,7 @@ struct BPParams {
     int max_iter;
     int sym;                    // sum-product: apply alpha / damping / clip (decoding.py:131)
     double alpha, damping, one_minus_damping, clip;
+    int prior_uniform;          // all priors equal (warp kernel: the message state starts as one constant)
     double qpad;                // max(clip, largest prior): start value of padding edge slots (bp_warp / bp_cta kernels)
     uint32_t *hard;             // [B][WN] packed hard decisions (out)
     uint8_t *conv;              // [B] (out)

@@ -129,6 +129,7 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
     for (int r = 0; r < 3 * VPL + 1; ++r) Rbuf[r * 32 + lane] = 0.f;      // columns of padding positions stay zero for ever
     Vbuf[VPL * 32 + lane] = CUDART_INF_F;
+    const float prior0 = reinterpret_cast<const float *>(P.prior)[0] + 0.f;
 
     const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
     const int max_iter = P.max_iter;
@@ -156,17 +157,25 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
             sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
             salpha[i] = __uint_as_float(__float_as_uint(VAR == 1 ? 1.f : alpha) ^ sbit[i]);
         }
-        // Q = where(mask, prior, 0) (decoding.py:21): publish the priors, gather them along the edges
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < VPL; ++i) Vbuf[i * 32 + lane] = prior[i] + 0.f;
-        __syncwarp();
+        // Q = where(mask, prior, 0) (decoding.py:21): one value when the prior is uniform, else publish the priors and
+        // gather them along the edges
         float Q[CPL][RW];
+        if (P.prior_uniform) {
 #pragma unroll
-        for (int i = 0; i < CPL; ++i)
+            for (int i = 0; i < CPL; ++i)
 #pragma unroll
-            for (int k = 0; k < RW; ++k) Q[i][k] = ldb(Vbuf, vidx[i][k]);      // (every check has RW edges here: only whole padding
+                for (int k = 0; k < RW; ++k) Q[i][k] = prior0;
+        } else {
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) Vbuf[i * 32 + lane] = prior[i] + 0.f;
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < CPL; ++i)
+#pragma unroll
+                for (int k = 0; k < RW; ++k) Q[i][k] = ldb(Vbuf, vidx[i][k]);  // (every check has RW edges here: only whole padding
                                                                                  //  lanes read the +inf row, and nothing reads them)
+        }
 
         int iter = 0;
         bool conv = false;

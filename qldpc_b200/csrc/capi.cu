@@ -91,6 +91,7 @@ struct qldpc_code {
     bool cta_ok = false;
     int max_row_w = 0;
     double prior_max = 0.0;
+    bool prior_uniform = false;
     bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;
@@ -565,7 +566,11 @@ static int set_prior(qldpc_code *c, const double *prior_host, cudaStream_t st)
     CK(cudaStreamSynchronize(st));
     c->prior_cache.assign(prior_host, prior_host + c->n);
     c->prior_max = 0.0;
-    for (int i = 0; i < c->n; ++i) c->prior_max = std::max(c->prior_max, std::fabs(prior_host[i]));
+    c->prior_uniform = true;
+    for (int i = 0; i < c->n; ++i) {
+        c->prior_max = std::max(c->prior_max, std::fabs(prior_host[i]));
+        c->prior_uniform = c->prior_uniform && (memcmp(&prior_host[i], &prior_host[0], sizeof(double)) == 0);
+    }
     return QLDPC_OK;
 }
 
@@ -727,6 +732,7 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.one_minus_damping = 1.0 - cfg->damping;     // `(1 - damping)` evaluated in float64 (decoding.py:65)
     P.clip = cfg->clip;
     P.qpad = std::max(cfg->clip, c->prior_max);
+    P.prior_uniform = c->prior_uniform ? 1 : 0;
     P.hard = hard;
     P.conv = conv;
     P.iters = iters;
@@ -1193,7 +1199,7 @@ extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg,
         P.prior = c->prior64.p;
         P.max_iter = cf.max_iter;
         P.sym = (cf.variant == QLDPC_SUM_PRODUCT_SYM);
-        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip; P.qpad = std::max(cf.clip, c->prior_max);
+        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip; P.qpad = std::max(cf.clip, c->prior_max); P.prior_uniform = 0;
         P.hard = c->ws_hard.as<uint32_t>(); P.conv = c->ws_conv.as<uint8_t>(); P.iters = nullptr;
         P.llr = nullptr; P.llr_mode = LLR_NONE;
         P.cursor = &ctrl->cursor; P.fail_idx = nullptr; P.fail_count = &ctrl->fail_count; P.iter_total = nullptr;

@@ -887,7 +887,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
     uint32_t *chk = reinterpret_cast<uint32_t *>(keys);                    // [n] packed checks of column ordering[j] (after the sort)
     uint16_t *ord = reinterpret_cast<uint16_t *>(keys + n);
-    __shared__ int s_free[NW];
+    __shared__ int s_pp[NW], s_pw[NW], s_k;
     constexpr bool packed_chk = PACKED;               // m < 1024 and column weight <= 3 (checked by the host)
 
     // XOR of the TC columns of the checks of sorted position jj, word w
@@ -977,60 +977,90 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         }
         __syncthreads();
 
-        // ---- forward elimination ---------------------------------------------------------------
+        // ---- forward elimination, NW candidate columns per round ----------------------------------
+        // Every warp evaluates one candidate against the current T.  Warp 0 then resolves the whole batch in order: a
+        // candidate with a free row pivots (lowest free row p, S = its other free rows), and every LATER candidate of the
+        // batch is brought up to date in registers (if it has row p: ^= S; row p is no longer free).  The batch of up to
+        // NW pivots is then applied to T -- each warp walks its own columns through the pivots in order, no barrier in
+        // between -- so a round costs three barriers for up to NW pivots and NW columns are finished per round.
         int j = 0, npiv = 0;
         const int rank = P.rank;
+        const uint32_t *ucur = used;
         while (j < n && npiv < rank) {
-            const uint32_t *ucur = used + (npiv & 1) * WM;
-            uint32_t *unxt = used + ((npiv + 1) & 1) * WM;
-            // warp w: free rows of the reduced column at sorted position j + w; the lowest of them would be its pivot
             const int jj = j + warp;
-            int myfree = -1;
-            if (jj < n) {                                             // (WM <= 32: one word per lane)
-                uint32_t fr = (lane < WM) ? (reduced_word(jj, lane) & ~ucur[lane]) : 0u;
-                const unsigned bal = __ballot_sync(FULL, fr != 0);
-                if (bal != 0) {
-                    const int src = __ffs(bal) - 1;
-                    const uint32_t f = __shfl_sync(FULL, fr, src);
-                    myfree = 32 * src + __ffs(f) - 1;
-                    if (lane == src) fr &= fr - 1;                      // S = free rows without the pivot row
-                }
-                if (lane < WM) cand[(size_t)warp * WM + lane] = fr;
-            }
-            if (lane == 0) s_free[warp] = myfree;
+            if (lane < WM) cand[(size_t)warp * WM + lane] = (jj < n) ? (reduced_word(jj, lane) & ~ucur[lane]) : 0u;
             __syncthreads();
-            int first = -1;
+            if (warp == 0) {
+                uint32_t fr[NW];
 #pragma unroll
-            for (int w = NW - 1; w >= 0; --w) if (s_free[w] >= 0) first = w;
-            if (first < 0) { j += NW; __syncthreads(); continue; }                 // NW dependent columns
-            const int p = s_free[first];
-            const uint32_t pbit = 1u << (p & 31);
-            const int pw = p >> 5;
-            const uint32_t *Sv = cand + (size_t)first * WM;
-            // free rows S ^= row p  <=>  every column of T with bit p set ^= S (and so does the syndrome column)
-            // (a warp finds the columns with bit p among its 32-column chunks with a ballot, then XORs S into each of
-            //  them with one word per lane: no divergence, S in a register, conflict-free rows; WM <= 32 here)
-            const uint32_t sv = (lane < WM) ? Sv[lane] : 0u;
+                for (int w = 0; w < NW; ++w) fr[w] = (lane < WM) ? cand[(size_t)w * WM + lane] : 0u;
+                int k = 0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) {
+                    const unsigned bal = __ballot_sync(FULL, fr[w] != 0);
+                    if (bal != 0 && npiv + k < rank) {                          // (uniform)
+                        const int src = __ffs(bal) - 1;
+                        const uint32_t f = __shfl_sync(FULL, fr[w], src);
+                        const int pb = __ffs(f) - 1;
+                        if (lane == src) fr[w] &= fr[w] - 1;                    // S = free rows without the pivot row
+                        if (lane < WM) cand[(size_t)w * WM + lane] = fr[w];
+                        if (lane == 0) { s_pp[k] = 32 * src + pb; s_pw[k] = w; }
+#pragma unroll
+                        for (int w2 = w + 1; w2 < NW; ++w2) {
+                            const uint32_t has = __shfl_sync(FULL, (fr[w2] >> pb) & 1u, src);
+                            if (has) fr[w2] ^= fr[w];
+                            if (lane == src) fr[w2] &= ~(1u << pb);             // row p is used from now on
+                        }
+                        ++k;
+                    }
+                }
+                if (lane == 0) s_k = k;
+            }
+            __syncthreads();
+            const int K = s_k;
+            // apply the batch: every column of T with bit p_a set ^= S_a, a = 0 .. K-1 in order (and so does the syndrome column)
             for (int c0 = warp * 32; c0 < m; c0 += NW * 32) {
                 const int c = c0 + lane;
-                unsigned hit = __ballot_sync(FULL, c < m && (TC[(size_t)c * WM + pw] & pbit));
-                while (hit) {
-                    const int cc = c0 + __ffs(hit) - 1;
-                    hit &= hit - 1;
-                    if (lane < WM) TC[(size_t)cc * WM + lane] ^= sv;
+                for (int a2 = 0; a2 < K; ++a2) {
+                    const int p = s_pp[a2];
+                    const uint32_t pbit = 1u << (p & 31);
+                    unsigned hit = __ballot_sync(FULL, c < m && (TC[(size_t)c * WM + (p >> 5)] & pbit));
+                    if (hit) {
+                        const uint32_t sv = (lane < WM) ? cand[(size_t)s_pw[a2] * WM + lane] : 0u;
+                        while (hit) {
+                            const int cc = c0 + __ffs(hit) - 1;
+                            hit &= hit - 1;
+                            if (lane < WM) TC[(size_t)cc * WM + lane] ^= sv;
+                        }
+                        __syncwarp();
+                    }
                 }
             }
-            if (warp == NW - 1 && (bw[pw] & pbit))                                   // (bit p itself is not in S: the test is stable)
-                for (int w = lane; w < WM; w += 32) bw[w] ^= Sv[w];
-            for (int w = tid; w < WM; w += NT) unxt[w] = ucur[w] | ((w == pw) ? pbit : 0u);
-            if (tid == 0) { prow[npiv] = (uint16_t)p; pcolj[npiv] = (uint16_t)(j + first); }
-            ++npiv;
-            j += first + 1;
+            if (warp == NW - 1) {
+                for (int a2 = 0; a2 < K; ++a2) {
+                    const int p = s_pp[a2];
+                    const bool hasb = (bw[p >> 5] >> (p & 31)) & 1u;
+                    __syncwarp();
+                    if (hasb && lane < WM) bw[lane] ^= cand[(size_t)s_pw[a2] * WM + lane];
+                    __syncwarp();
+                }
+            }
+            if (warp == 1) {
+                uint32_t u = (lane < WM) ? used[lane] : 0u;
+                for (int a2 = 0; a2 < K; ++a2) {
+                    const int p = s_pp[a2];
+                    if (lane == (p >> 5)) u |= 1u << (p & 31);
+                    if (lane == 0) { prow[npiv + a2] = (uint16_t)p; pcolj[npiv + a2] = (uint16_t)(j + s_pw[a2]); }
+                }
+                if (lane < WM) used[lane] = u;
+            }
+            npiv += K;
+            j += NW;
             __syncthreads();
         }
 
         // ---- validity; back-substitution over the pivots in reverse order ---------------------------
-        const uint32_t *ufin = used + (npiv & 1) * WM;
+        const uint32_t *ufin = used;
         int bad = 0;
         for (int w = tid; w < WM; w += NT) {
             const int rows = m - 32 * w;

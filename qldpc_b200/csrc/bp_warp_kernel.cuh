@@ -27,6 +27,7 @@
 namespace qldpc {
 
 constexpr int BPW_WARPS = 8;            // warps per CTA
+constexpr int BPW_GRAB = 4;             // shots a warp takes from the global cursor per atomic
 
 __device__ __forceinline__ float ldb(const float *base, uint32_t byte_off)
 {
@@ -135,21 +136,27 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
     const int max_iter = P.max_iter;
     unsigned long long iter_sum = 0;
 
-    // The shot index (global cursor) and the syndrome words of the NEXT shot are fetched while the current one is being
-    // decoded, so that neither the atomic nor the load latency is exposed between two shots.
+    // Shot indices (global cursor) and syndrome words are fetched TWO shots ahead: the atomic of shot k + 2 is issued at the
+    // top of shot k and read after its first iteration, when the syndrome loads of k + 2 are issued; they are consumed at
+    // the top of shot k + 2.  At low error rates a shot lasts one or two iterations, less than a global-memory round trip.
     auto load_synd = [&](long long sh, uint32_t (&w)[CPL]) {
 #pragma unroll
         for (int i = 0; i < CPL; ++i) w[i] = (sh < P.B && cinfo[i] != 0xffffffffu) ? P.synd[(size_t)sh * WM + (cinfo[i] >> 5)] : 0u;
     };
+    // (the cursor is advanced BPW_GRAB shots at a time: one atomic per shot on a single address saturates the L2 at about
+    //  1.4e9 shots/s, which short shots -- low error rates -- reach)
     unsigned long long s0 = 0;
-    if (lane == 0) s0 = atomicAdd(P.cursor, 1ull);
+    if (lane == 0) s0 = atomicAdd(P.cursor, (unsigned long long)BPW_GRAB);
     long long shot = (long long)__shfl_sync(FULL, s0, 0);
-    uint32_t sw[CPL];
+    long long next_shot = shot + 1, grp_next = shot + 2, grp_end = shot + BPW_GRAB;
+    uint32_t sw[CPL], swn[CPL];
     load_synd(shot, sw);
+    load_synd(next_shot, swn);
 
     while (shot < P.B) {
-        if (lane == 0) s0 = atomicAdd(P.cursor, 1ull);       // consumed after iteration 0
-        long long next_shot = 0;
+        const bool need_grab = grp_next >= grp_end;            // (warp-uniform) shot k + 2 starts a new group
+        if (need_grab && lane == 0) s0 = atomicAdd(P.cursor, (unsigned long long)BPW_GRAB);   // consumed after iteration 0
+        long long next2_shot = 0;
         uint32_t sbit[CPL];                      // syndrome bit of each owned check, moved to the sign-bit position
         float salpha[CPL];                       // (-1)^s * alpha
 #pragma unroll
@@ -263,8 +270,14 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
             }
             conv = __all_sync(FULL, ok);
             if (iter == 0) {
-                next_shot = (long long)__shfl_sync(FULL, s0, 0);
-                load_synd(next_shot, sw);
+                if (need_grab) {
+                    grp_next = (long long)__shfl_sync(FULL, s0, 0);
+                    grp_end = grp_next + BPW_GRAB;
+                }
+                next2_shot = grp_next++;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) sw[i] = swn[i];         // (issued one shot ago: landed)
+                load_synd(next2_shot, swn);
             }
             if (conv || last) break;
         }
@@ -290,6 +303,7 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
             iter_sum += (unsigned long long)(iter + 1);
         }
         shot = next_shot;
+        next_shot = next2_shot;
     }
     if (P.iter_total && lane == 0 && iter_sum) atomicAdd(P.iter_total, iter_sum);
 }

@@ -1361,8 +1361,23 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
     };
     int rc_all = QLDPC_OK;
     long long i = 0;
-    for (long long o = 0; o < B && rc_all == QLDPC_OK; o += chunk, ++i)
-        rc_all = enqueue(o, std::min<long long>(chunk, B - o), c->slot[i % qldpc_code::NSLOT]);
+    // Tapered schedule for large batches: the pipeline fills with a quarter- and a half-sized chunk and drains with a half-
+    // and a quarter-sized one, so that the first copy-in and the last copy-out (not hidden under compute) are short.
+    const bool taper = !getenv("QLDPC_HOST_NO_TAPER") && B >= 4 * chunk;
+    for (long long o = 0; o < B && rc_all == QLDPC_OK; ++i) {
+        long long b = chunk;
+        if (taper) {
+            const long long left = B - o;
+            if (o == 0) b = chunk / 4;
+            else if (o == chunk / 4) b = chunk / 2;
+            else if (left <= chunk / 4) b = left;
+            else if (left <= 3 * chunk / 4) b = left - chunk / 4;
+            else if (left < 7 * chunk / 4) b = left - 3 * chunk / 4;
+        }
+        b = std::min<long long>(b, B - o);
+        rc_all = enqueue(o, b, c->slot[i % qldpc_code::NSLOT]);
+        o += b;
+    }
     const std::string msg = g_err;
     for (cudaStream_t st : {c->st_in, c->st_comp, c->st_out})
         if (st && cudaStreamSynchronize(st) != cudaSuccess && rc_all == QLDPC_OK)

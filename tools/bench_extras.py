@@ -159,6 +159,11 @@ def main():
             synd = np.concatenate(blocks, axis=1).astype(np.uint8)
             res = r.run(p, B, dict(max_iter=50, **ms_kw), 0, synd_override=synd, reps=1)
             res_bp = r.run(p, B, dict(max_iter=50, **ms_kw), -1, synd_override=synd, reps=1)
+            # the same BP with the message state staged in HBM (what BASELINE config 4 names): the crossover figure
+            res_st = r.run(p, B, dict(max_iter=50, staged=1, **ms_kw), -1, synd_override=synd, reps=1)
+            staged = dict(kernel=res_st["kernel"], shots_per_s=res_st["shots_per_s"], shot_iterations_per_s=res_st["shot_iterations_per_s"],
+                          hbm_algorithmic_gbs=res_st["shot_iterations_per_s"] * 12 * E / 1e9,
+                          hbm_frac=res_st["shot_iterations_per_s"] * 12 * E / 1e9 / PEAKS.get("hbm_gbs", 6650.0))
             if res_bp["kernel"] == "cta_per_shot":
                 A = 15 * E + 2 * r.n + r.m                       # lane-ops per shot-iteration
                 peak = 148 * 128 * PEAKS.get("sm_max_mhz", 1965.0) * 1e6
@@ -174,7 +179,7 @@ def main():
                 label = "HBM-staged"
             emit(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, {label}", p=p, **res,
                  bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
-                 roofline=roof)
+                 roofline=roof, bp_only_hbm_staged=staged)
 
 
 if __name__ == "__main__":

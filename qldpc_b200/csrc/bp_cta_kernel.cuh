@@ -4,7 +4,8 @@
 // messages into the columns of their variables, owns variables, gathers posteriors) spread over the NW warps of a CTA:
 // warp w owns check slots [w*SC, (w+1)*SC) and variable slots [w*SV, (w+1)*SV) of the host-built labelling
 // (bp_warp_layout.h, which also serves rows with fewer than RW edges: their spare edge slots read a row of +inf as
-// "posterior", start at qpad >= every real |Q| and settle at +clip, so they never change a sign or a minimum).  The
+// "posterior", start at qpad >= every real |Q| and settle at +clip, so they never change a sign or a minimum; the
+// sum-product variants pin them at +inf instead, psi(inf) = 0).  The
 // three __syncwarp of the warp kernel become block barriers, the convergence vote a __syncthreads_and.
 // Built for the space-time matrices of the reference (spaceTime.py: 864 x 2592, row weight 7-8, column weight <= 3 =>
 // 12 warps x (3 check slots, 7 variable slots), 43 KB of shared memory per shot): the message state that the HBM-staged
@@ -22,7 +23,8 @@ namespace qldpc {
 // shared memory of a CTA: planes [3][VPL][32] + dump row + posteriors [VPL][32] + inf row, VPL = NW * SV
 __host__ __device__ inline size_t bp_cta_smem(int VPL) { return 4 * (size_t)32 * (4 * VPL + 2); }
 
-template <int SC, int SV, int RW, bool TWO>
+// VAR as in bp_warp_kernel: 0 min-sum, 1 sum-product, 2 symmetric sum-product (psi domain)
+template <int SC, int SV, int RW, bool TWO, int VAR>
 __global__ void __launch_bounds__(384, 1)
 bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 {
@@ -52,6 +54,11 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
             sidx[i][k] = W.sidx[(ig * RW + k) * 32 + lane];
         }
     }
+    uint32_t padmask = 0;                                          // edge slots that read the +inf row (SC * RW <= 32 bits)
+#pragma unroll
+    for (int i = 0; i < SC; ++i)
+#pragma unroll
+        for (int k = 0; k < RW; ++k) padmask |= (vidx[i][k] >= 4u * 32u * (uint32_t)VPL ? 1u : 0u) << (i * RW + k);
     for (int r = tid; r < 32 * (3 * VPL + 1); r += blockDim.x) Rbuf[r] = 0.f;       // columns of padding positions stay zero
     if (tid < 32) Vbuf[VPL * 32 + tid] = CUDART_INF_F;
 
@@ -79,7 +86,7 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 #pragma unroll
         for (int i = 0; i < SC; ++i) {
             sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
-            salpha[i] = __uint_as_float(__float_as_uint(alpha) ^ sbit[i]);
+            salpha[i] = __uint_as_float(__float_as_uint(VAR == 1 ? 1.f : alpha) ^ sbit[i]);
         }
         // Q = prior along the edges (decoding.py:21)
 #pragma unroll
@@ -89,7 +96,7 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 #pragma unroll
         for (int i = 0; i < SC; ++i)
 #pragma unroll
-            for (int k = 0; k < RW; ++k) Q[i][k] = fminf(ldb(Vbuf, vidx[i][k]), qpad);
+            for (int k = 0; k < RW; ++k) Q[i][k] = (VAR == 0) ? fminf(ldb(Vbuf, vidx[i][k]), qpad) : ldb(Vbuf, vidx[i][k]);
 
         int iter = 0;
         bool conv = false;
@@ -99,16 +106,41 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 #pragma unroll
             for (int i = 0; i < SC; ++i) {
                 float pre[RW], suf[RW];
-                pre[1] = Q[i][0];
-                suf[RW - 2] = Q[i][RW - 1];
+                if (VAR == 0) {
+                    pre[1] = Q[i][0];
+                    suf[RW - 2] = Q[i][RW - 1];
 #pragma unroll
-                for (int k = 2; k < RW; ++k) pre[k] = bpw_xmin(pre[k - 1], Q[i][k - 1]);
+                    for (int k = 2; k < RW; ++k) pre[k] = bpw_xmin(pre[k - 1], Q[i][k - 1]);
 #pragma unroll
-                for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_xmin(suf[k + 1], Q[i][k + 1]);
+                    for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_xmin(suf[k + 1], Q[i][k + 1]);
+                } else {
+                    float ps[RW];                                      // psi(+inf) = 0: padding slots drop out of the sums
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) ps[k] = bpw_psi(fabsf(Q[i][k]));
+                    pre[1] = ps[0];
+                    suf[RW - 2] = ps[RW - 1];
+#pragma unroll
+                    for (int k = 2; k < RW; ++k) pre[k] = pre[k - 1] + ps[k - 1];
+#pragma unroll
+                    for (int k = RW - 3; k >= 0; --k) suf[k] = suf[k + 1] + ps[k + 1];
+                }
+                uint32_t sgall = 0;
+                if (VAR != 0) {
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) sgall ^= __float_as_uint(Q[i][k]);
+                }
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
-                    const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
-                    const float r = __fmul_rn(o, salpha[i]);
+                    float r;
+                    if (VAR == 0) {
+                        const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
+                        r = __fmul_rn(o, salpha[i]);
+                    } else {
+                        const float sk = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : pre[k] + suf[k];
+                        const float mag = fminf(bpw_psi(sk), 16.811242831518264f);
+                        const float signedmag = __uint_as_float(__float_as_uint(mag) | ((sgall ^ __float_as_uint(Q[i][k])) & 0x80000000u));
+                        r = __fmul_rn(signedmag, salpha[i]);
+                    }
                     R[i][k] = r;
                     if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + ((warp * SC + i) * RW + k) * 32 + lane), r);
                     else stb(Rbuf, sidx[i][k], r);
@@ -136,8 +168,12 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
                     const float val = ldb(Vbuf, vidx[i][k]);
                     par ^= __float_as_uint(val);            // (+inf of a padding slot: sign 0)
                     float qn = __fsub_rn(val, R[i][k]);
-                    qn = bp_damp(damp, qn, omd, Q[i][k]);
-                    qn = fminf(fmaxf(qn, -clipv), clipv);
+                    if (VAR != 1) {
+                        qn = bp_damp(damp, qn, omd, Q[i][k]);
+                        qn = fminf(fmaxf(qn, -clipv), clipv);
+                    }
+                    // sum-product: a padding slot must stay at +inf (psi = 0); at +clip it would add psi(clip) to the sums
+                    if (VAR != 0 && ((padmask >> (i * RW + k)) & 1u)) qn = CUDART_INF_F;
                     Q[i][k] = qn;
                 }
                 ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);

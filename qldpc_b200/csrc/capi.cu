@@ -432,9 +432,10 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     G->refill_min = 1;
     G->warp_kernel = false;
     G->cta_kernel = false;
-    if ((cfg->staged == 0 || cfg->staged == 4) && c->cta_ok && cfg->precision == 32 && cfg->variant == QLDPC_MIN_SUM) {
+    if ((cfg->staged == 0 || cfg->staged == 4) && c->cta_ok && cfg->precision == 32) {
         G->staged = false;
         G->cta_kernel = true;
+        G->warp_var = cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2);
         G->threads = c->cta_nw * 32;
         G->shots_per_cta = 1;
         G->smem = bp_cta_smem(7 * c->cta_nw);
@@ -655,7 +656,9 @@ static cudaError_t launch_bp_warp_inst(const qldpc_code *c, const BPParams &P, c
 
 static cudaError_t launch_bp_cta(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    auto kern = c->two_tables ? bp_cta_kernel<3, 7, 8, true> : bp_cta_kernel<3, 7, 8, false>;
+    const int var = G.warp_var;
+    auto kern = c->two_tables ? (var == 0 ? bp_cta_kernel<3, 7, 8, true, 0> : var == 1 ? bp_cta_kernel<3, 7, 8, true, 1> : bp_cta_kernel<3, 7, 8, true, 2>)
+                              : (var == 0 ? bp_cta_kernel<3, 7, 8, false, 0> : var == 1 ? bp_cta_kernel<3, 7, 8, false, 1> : bp_cta_kernel<3, 7, 8, false, 2>);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
     if (e != cudaSuccess) return e;
     int occ = 1;

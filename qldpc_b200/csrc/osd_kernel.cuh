@@ -1017,11 +1017,11 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                 if (lane == 0) s_k = k;
             }
             __syncthreads();
-            const int K = s_k;
+            const int nacc = s_k;                                   // pivots accepted in this round
             // apply the batch: every column of T with bit p_a set ^= S_a, a = 0 .. K-1 in order (and so does the syndrome column)
             for (int c0 = warp * 32; c0 < m; c0 += NW * 32) {
                 const int c = c0 + lane;
-                for (int a2 = 0; a2 < K; ++a2) {
+                for (int a2 = 0; a2 < nacc; ++a2) {
                     const int p = s_pp[a2];
                     const uint32_t pbit = 1u << (p & 31);
                     unsigned hit = __ballot_sync(FULL, c < m && (TC[(size_t)c * WM + (p >> 5)] & pbit));
@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                 }
             }
             if (warp == NW - 1) {
-                for (int a2 = 0; a2 < K; ++a2) {
+                for (int a2 = 0; a2 < nacc; ++a2) {
                     const int p = s_pp[a2];
                     const bool hasb = (bw[p >> 5] >> (p & 31)) & 1u;
                     __syncwarp();
@@ -1047,14 +1047,14 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             }
             if (warp == 1) {
                 uint32_t u = (lane < WM) ? used[lane] : 0u;
-                for (int a2 = 0; a2 < K; ++a2) {
+                for (int a2 = 0; a2 < nacc; ++a2) {
                     const int p = s_pp[a2];
                     if (lane == (p >> 5)) u |= 1u << (p & 31);
                     if (lane == 0) { prow[npiv + a2] = (uint16_t)p; pcolj[npiv + a2] = (uint16_t)(j + s_pw[a2]); }
                 }
                 if (lane < WM) used[lane] = u;
             }
-            npiv += K;
+            npiv += nacc;
             j += NW;
             __syncthreads();
         }

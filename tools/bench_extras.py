@@ -180,6 +180,12 @@ def main():
             emit(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, {label}", p=p, **res,
                  bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
                  roofline=roof, bp_only_hbm_staged=staged)
+            if p == 0.001:      # the reference decodes these matrices with sum-product (studies/studyTT.py:49)
+                sp32 = r.run(p, B, dict(variant="sum_product", max_iter=50, precision=32), 0, synd_override=synd, reps=1)
+                sp64 = r.run(p, B // 8, dict(variant="sum_product", max_iter=50, precision=64), 0, synd_override=synd[:B // 8], reps=1)
+                emit(f"4: space-time [[144,12,12]]x12 (864x2592) p={p} sum-product BP50 + OSD-0, f32 psi domain (CTA-per-shot)", p=p, **sp32,
+                     float64_hbm_staged=dict(shots=sp64["shots"], shots_per_s=sp64["shots_per_s"], kernel=sp64["kernel"],
+                                             shot_iterations_per_s=sp64["shot_iterations_per_s"]))
 
 
 if __name__ == "__main__":

@@ -25,7 +25,7 @@ __host__ __device__ inline size_t bp_cta_smem(int VPL) { return 4 * (size_t)32 *
 
 // VAR as in bp_warp_kernel: 0 min-sum, 1 sum-product, 2 symmetric sum-product (psi domain)
 template <int SC, int SV, int RW, bool TWO, int VAR>
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(SC >= 3 ? 384 : 576, 1)
 bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 {
     const int n = P.g.n, WN = P.g.WN, WM = P.g.WM;

@@ -87,7 +87,7 @@ struct qldpc_code {
     // CTA-per-shot kernel (bp_cta_kernel.cuh): labelling with NW * 3 check slots and NW * 7 variable slots
     uint32_t *d_ctab = nullptr;
     BPWarpTables ctab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int cta_nw = 0, cta_cost[3] = {0, 0, 0};
+    int cta_nw = 0, cta_sc = 3, cta_sv = 7, cta_cost[3] = {0, 0, 0};
     bool cta_ok = false;
     int max_row_w = 0;
     double prior_max = 0.0;
@@ -333,13 +333,20 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
     // CTA-per-shot kernel: larger matrices with row weight <= 8 and column weight <= 3 (the space-time matrices): the
     // smallest number of warps NW <= 12 whose 3 NW check slots / 7 NW variable slots admit a conflict-free labelling
     if (!c->warp_ok && m > 160 && c->max_row_w <= 8 && c->max_col_w <= 3 && !getenv("QLDPC_NO_CTA_KERNEL")) {
-        for (int nw = std::max(2, (m + 95) / 96); nw <= 12 && !c->cta_ok; ++nw) {
-            if (7 * nw * 32 < n) continue;
-            WarpLayoutBuilder lb(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 8, 3 * nw, 7 * nw);
-            if (!lb.construct(400000)) continue;
-            if (int rc = layout_tables_upload(lb.tables(), &c->d_ctab, &c->ctab, c->cta_cost)) return rc;
-            c->cta_nw = nw;
-            c->cta_ok = bp_cta_smem(7 * nw) <= (size_t)c->smem_optin;
+        // shapes (check slots, variable slots per warp): (3, 7) with up to 12 warps, else (2, 5) with up to 18 (measured on
+        // the 864 x 2592 matrix: 87.5 against 84.0 M shot-iterations/s at p = 0.003 -- lighter warps do not pay)
+        const int shapes[2][3] = {{3, 7, 12}, {2, 5, 18}};
+        const int first_shape = getenv("QLDPC_CTA_SHAPE_2_5") ? 1 : 0;
+        for (int sh = first_shape; sh < 2 && !c->cta_ok; ++sh) {
+            const int sc = shapes[sh][0], sv = shapes[sh][1], nwmax = shapes[sh][2];
+            for (int nw = std::max(2, (m + 32 * sc - 1) / (32 * sc)); nw <= nwmax && !c->cta_ok; ++nw) {
+                if (sv * nw * 32 < n) continue;
+                WarpLayoutBuilder lb(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 8, sc * nw, sv * nw);
+                if (!lb.construct(400000)) continue;
+                if (int rc = layout_tables_upload(lb.tables(), &c->d_ctab, &c->ctab, c->cta_cost)) return rc;
+                c->cta_nw = nw; c->cta_sc = sc; c->cta_sv = sv;
+                c->cta_ok = bp_cta_smem(sv * nw) <= (size_t)c->smem_optin;
+            }
         }
     }
     std::vector<uint32_t> Lrows((size_t)std::max(k, 0) * c->WN, 0u), Hrows((size_t)m * c->WN, 0u);
@@ -438,7 +445,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->warp_var = cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2);
         G->threads = c->cta_nw * 32;
         G->shots_per_cta = 1;
-        G->smem = bp_cta_smem(7 * c->cta_nw);
+        G->smem = bp_cta_smem(c->cta_sv * c->cta_nw);
         G->grid = 0;
         G->gstate_bytes = 0;
         return QLDPC_OK;
@@ -657,14 +664,20 @@ static cudaError_t launch_bp_warp_inst(const qldpc_code *c, const BPParams &P, c
 static cudaError_t launch_bp_cta(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
     const int var = G.warp_var;
-    auto kern = c->two_tables ? (var == 0 ? bp_cta_kernel<3, 7, 8, true, 0> : var == 1 ? bp_cta_kernel<3, 7, 8, true, 1> : bp_cta_kernel<3, 7, 8, true, 2>)
-                              : (var == 0 ? bp_cta_kernel<3, 7, 8, false, 0> : var == 1 ? bp_cta_kernel<3, 7, 8, false, 1> : bp_cta_kernel<3, 7, 8, false, 2>);
+    void (*kern)(const BPParams, const BPWarpTables, int) = nullptr;
+#define QLDPC_CTA_PICK(SC, SV)                                                                                              \
+    kern = c->two_tables ? (var == 0 ? bp_cta_kernel<SC, SV, 8, true, 0> : var == 1 ? bp_cta_kernel<SC, SV, 8, true, 1>     \
+                                                                                    : bp_cta_kernel<SC, SV, 8, true, 2>)    \
+                         : (var == 0 ? bp_cta_kernel<SC, SV, 8, false, 0> : var == 1 ? bp_cta_kernel<SC, SV, 8, false, 1>   \
+                                                                                     : bp_cta_kernel<SC, SV, 8, false, 2>)
+    if (c->cta_sc == 2) { QLDPC_CTA_PICK(2, 5); } else { QLDPC_CTA_PICK(3, 7); }
+#undef QLDPC_CTA_PICK
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
     const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), P.B));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->ctab, 7 * c->cta_nw);
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->ctab, c->cta_sv * c->cta_nw);
     return cudaGetLastError();
 }
 

@@ -64,6 +64,7 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 
     const float alpha = (float)P.alpha, damp = (float)P.damping, omd = (float)P.one_minus_damping, clipv = (float)P.clip;
     const float qpad = (float)P.qpad;
+    const float prior0 = reinterpret_cast<const float *>(P.prior)[0] + 0.f;
     const int max_iter = P.max_iter;
     unsigned long long iter_sum = 0;
 
@@ -88,15 +89,22 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
             sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
             salpha[i] = __uint_as_float(__float_as_uint(VAR == 1 ? 1.f : alpha) ^ sbit[i]);
         }
-        // Q = prior along the edges (decoding.py:21)
-#pragma unroll
-        for (int i = 0; i < SV; ++i) Vbuf[(warp * SV + i) * 32 + lane] = prior[i] + 0.f;
-        __syncthreads();
+        // Q = prior along the edges (decoding.py:21); padding slots: qpad (min-sum) or +inf (sum-product)
         float Q[SC][RW];
+        if (P.prior_uniform) {
 #pragma unroll
-        for (int i = 0; i < SC; ++i)
+            for (int i = 0; i < SC; ++i)
 #pragma unroll
-            for (int k = 0; k < RW; ++k) Q[i][k] = (VAR == 0) ? fminf(ldb(Vbuf, vidx[i][k]), qpad) : ldb(Vbuf, vidx[i][k]);
+                for (int k = 0; k < RW; ++k) Q[i][k] = ((padmask >> (i * RW + k)) & 1u) ? (VAR == 0 ? qpad : CUDART_INF_F) : prior0;
+        } else {
+#pragma unroll
+            for (int i = 0; i < SV; ++i) Vbuf[(warp * SV + i) * 32 + lane] = prior[i] + 0.f;
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < SC; ++i)
+#pragma unroll
+                for (int k = 0; k < RW; ++k) Q[i][k] = (VAR == 0) ? fminf(ldb(Vbuf, vidx[i][k]), qpad) : ldb(Vbuf, vidx[i][k]);
+        }
 
         int iter = 0;
         bool conv = false;

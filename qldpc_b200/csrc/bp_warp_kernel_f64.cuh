@@ -91,9 +91,9 @@ bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
         bool conv = false;
         for (;; ++iter) {
             // ================= horizontal step (lane-local) ========================================
-            // R[k] = alpha * (-1)^s * prod_{j != k} sign(Q[j]) * min_{j != k} |Q[j]| (decoding.py:41-55).  "All but k" is
-            // prefix (x) suffix of the xorsign-min; the minimum over the others IS min1, or min2 at the arg-min (ties
-            // included), so the values equal the reference's where(|Q| == min1, min2, min1) selection exactly.
+            // R[k] = alpha * (-1)^s * prod_{j != k} sign(Q[j]) * min_{j != k} |Q[j]| (decoding.py:41-55).  The minimum over
+            // the others IS min1, or min2 at the arg-min (ties included), so the values equal the reference's
+            // where(|Q| == min1, min2, min1) selection exactly.
             double R[CPL][RW];
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
@@ -131,8 +131,7 @@ bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
             __syncwarp();
 
             // ================= Q update in registers + syndrome of the hard decision =================
-            // The check is satisfied by the hard decisions iff the xor of the posterior sign bits equals its syndrome bit
-            // (3-input LOP3s: the ALU pipe has room since the check pass moved to FMNMX.XORSIGN).
+            // The check is satisfied by the hard decisions iff the xor of the posterior sign bits equals its syndrome bit.
             bool ok = true;
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {

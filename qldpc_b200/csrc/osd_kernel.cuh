@@ -64,6 +64,13 @@ __device__ __forceinline__ void osd_count_lt(int &cnt, unsigned long long a, uns
         : "r"((uint32_t)a), "r"((uint32_t)(a >> 32)), "r"((uint32_t)b), "r"((uint32_t)(b >> 32)));
 }
 
+// The same count on the FMA pipe (the OSD kernels saturate the ALU pipe): x = a - b as a multiply-add, then the sign bit of
+// x -- hi32(x * 2) -- accumulated by a second one.  cnt counts UP here; valid for a, b <= 2^31 (float keys).
+__device__ __forceinline__ void osd_count_lt_fma(int &cnt, uint32_t a, uint32_t b)
+{
+    asm("{\n\t.reg .u32 t;\n\tmad.lo.u32 t, %2, 0xffffffff, %1;\n\tmad.hi.u32 %0, t, 2, %0;\n\t}" : "+r"(cnt) : "r"(a), "r"(b));
+}
+
 template <typename K> struct KeyBits;
 template <> struct KeyBits<float> {
     typedef uint32_t type;
@@ -336,13 +343,18 @@ osd0_fast_kernel(const OSDParams P)
                 const kbits kj = keys[32 * jb + jl];
 #pragma unroll
                 for (int t = 0; t < NS; ++t) {
-                    if (t == jb) osd_count_lt(cnt[t], kj, ki[t] + (kbits)(jl < lane));     // diagonal block: tie rule per lane
-                    else osd_count_lt(cnt[t], kj, thr[t]);
+                    const kbits bound = (t == jb) ? ki[t] + (kbits)(jl < lane) : thr[t];     // diagonal block: tie rule per lane
+                    if constexpr (sizeof(kbits) == 4) {
+                        osd_count_lt_fma(cnt[t], kj, bound);               // subtraction on the FMA pipe, counts up
+                    } else {
+                        osd_count_lt(cnt[t], kj, bound);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int t = 0; t < NS; ++t) if (32 * t + lane < n) ord[-cnt[t]] = (uint16_t)(32 * t + lane);      // (cnt counts down)
+        for (int t = 0; t < NS; ++t)
+            if (32 * t + lane < n) ord[(sizeof(kbits) == 4) ? cnt[t] : -cnt[t]] = (uint16_t)(32 * t + lane);      // (the borrow counters count down)
         __syncwarp();
 
         // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------
@@ -520,13 +532,18 @@ osd0_fast2_kernel(const OSDParams P)
                 const kbits kj = keys[16 * jb + jl];
 #pragma unroll
                 for (int t = 0; t < NS2; ++t) {
-                    if (t == jb) osd_count_lt(cnt[t], kj, ki[t] + (kbits)(jl < hl));      // diagonal block: tie rule per lane
-                    else osd_count_lt(cnt[t], kj, thr[t]);
+                    const kbits bound = (t == jb) ? ki[t] + (kbits)(jl < hl) : thr[t];       // diagonal block: tie rule per lane
+                    if constexpr (sizeof(kbits) == 4) {
+                        osd_count_lt_fma(cnt[t], kj, bound);               // subtraction on the FMA pipe, counts up
+                    } else {
+                        osd_count_lt(cnt[t], kj, bound);
+                    }
                 }
             }
         }
 #pragma unroll
-        for (int t = 0; t < NS2; ++t) if (16 * t + hl < n) ord[-cnt[t]] = (uint16_t)(16 * t + hl);
+        for (int t = 0; t < NS2; ++t)
+            if (16 * t + hl < n) ord[(sizeof(kbits) == 4) ? cnt[t] : -cnt[t]] = (uint16_t)(16 * t + hl);
         __syncwarp();
 
         // ---- residual syndrome s ^ H*hard (OSD.py:7-8), uniform within the half --------------------------

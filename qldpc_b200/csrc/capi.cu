@@ -339,10 +339,12 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
         const int first_shape = getenv("QLDPC_CTA_SHAPE_2_5") ? 1 : 0;
         for (int sh = first_shape; sh < 2 && !c->cta_ok; ++sh) {
             const int sc = shapes[sh][0], sv = shapes[sh][1], nwmax = shapes[sh][2];
-            for (int nw = std::max(2, (m + 32 * sc - 1) / (32 * sc)); nw <= nwmax && !c->cta_ok; ++nw) {
+            int tries = 0;                                  // (a failed search costs ~0.1 s: at most three per shape)
+            for (int nw = std::max(2, (m + 32 * sc - 1) / (32 * sc)); nw <= nwmax && !c->cta_ok && tries < 3; ++nw) {
                 if (sv * nw * 32 < n) continue;
+                ++tries;
                 WarpLayoutBuilder lb(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 8, sc * nw, sv * nw);
-                if (!lb.construct(400000)) continue;
+                if (!lb.construct(200000)) continue;
                 if (int rc = layout_tables_upload(lb.tables(), &c->d_ctab, &c->ctab, c->cta_cost)) return rc;
                 c->cta_nw = nw; c->cta_sc = sc; c->cta_sv = sv;
                 c->cta_ok = bp_cta_smem(sv * nw) <= (size_t)c->smem_optin;

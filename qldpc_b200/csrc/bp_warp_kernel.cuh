@@ -34,6 +34,30 @@ __device__ __forceinline__ float ldb(const float *base, uint32_t byte_off)
     return *reinterpret_cast<const float *>(reinterpret_cast<const unsigned char *>(base) + byte_off);
 }
 
+// Packed float32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100: two IEEE-rounded float32 operations per issue slot).  The kernel is
+// bound by issue slots, not by the FMA pipe, so pairing the message updates of neighbouring edges is free throughput.
+// Each component is rounded exactly like the scalar instruction: results do not change.
+__device__ __forceinline__ void bpw_sub2(float a0, float a1, float b0, float b1, float &r0, float &r1)
+{
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tsub.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void bpw_add2(float a0, float a1, float b0, float b1, float &r0, float &r1)
+{
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tadd.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void bpw_mul2(float a0, float a1, float b0, float b1, float &r0, float &r1)
+{
+    asm("{\n\t.reg .b64 a, b, c;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmul.rn.f32x2 c, a, b;\n\tmov.b64 {%0, %1}, c;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void bpw_fma2(float a0, float a1, float b0, float b1, float c0, float c1, float &r0, float &r1)
+{
+    asm("{\n\t.reg .b64 a, b, c, d;\n\tmov.b64 a, {%2, %3};\n\tmov.b64 b, {%4, %5};\n\tmov.b64 c, {%6, %7};\n\tfma.rn.f32x2 d, a, b, c;\n\tmov.b64 {%0, %1}, d;\n\t}"
+        : "=f"(r0), "=f"(r1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+
 // per-warp shared memory: message planes [3][VPL][32] + one dump row [32] (padding lanes) + posteriors [VPL][32] + a row of
 // +inf (what padding edge slots read as their "posterior")
 __host__ __device__ inline size_t bp_warp_smem_per_warp(int VPL) { return 4 * (size_t)32 * (4 * VPL + 2); }
@@ -219,22 +243,27 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
                     for (int k = 0; k < RW; ++k) sgall ^= __float_as_uint(Q[i][k]);
                 }
+                float o[RW];
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
-                    float r;
                     if (VAR == 0) {
-                        const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
-                        r = __fmul_rn(o, salpha[i]);       // (+-alpha) * (+-magnitude): same rounding as alpha * magnitude
+                        o[k] = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
                     } else {
                         const float sk = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : pre[k] + suf[k];
                         // 2 atanh(clip(prod, 0.9999999)) (beliefPropagation.py:125-126): saturates at 16.81
                         const float mag = fminf(bpw_psi(sk), 16.811242831518264f);
-                        const float signedmag = __uint_as_float(__float_as_uint(mag) | ((sgall ^ __float_as_uint(Q[i][k])) & 0x80000000u));
-                        r = __fmul_rn(signedmag, salpha[i]);           // (-1)^s, times alpha for the symmetric variant
+                        o[k] = __uint_as_float(__float_as_uint(mag) | ((sgall ^ __float_as_uint(Q[i][k])) & 0x80000000u));
                     }
-                    R[i][k] = r;
-                    if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + (i * RW + k) * 32 + lane), r);
-                    else stb(Rbuf, sidx[i][k], r);       // (padding lanes write garbage into the dump row)
+                }
+#pragma unroll
+                for (int k = 0; k < RW; k += 2) {
+                    // (+-alpha) * (+-magnitude): same rounding as alpha * magnitude; (-1)^s only for plain sum-product
+                    bpw_mul2(o[k], o[k + 1], salpha[i], salpha[i], R[i][k], R[i][k + 1]);
+#pragma unroll
+                    for (int kk = k; kk < k + 2; ++kk) {
+                        if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + (i * RW + kk) * 32 + lane), R[i][kk]);
+                        else stb(Rbuf, sidx[i][kk], R[i][kk]);       // (padding lanes write garbage into the dump row)
+                    }
                 }
             }
             __syncwarp();
@@ -242,9 +271,18 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
             // ================= vertical step: posteriors of the owned variables =====================
             const bool last = (iter == max_iter - 1);
 #pragma unroll
-            for (int i = 0; i < VPL; ++i) {
+            for (int i = 0; i + 1 < VPL; i += 2) {                                                  // two slots per packed add
+                float a0 = Rbuf[(0 * VPL + i) * 32 + lane], a1 = Rbuf[(0 * VPL + i + 1) * 32 + lane];
+                bpw_add2(a0, a1, Rbuf[(1 * VPL + i) * 32 + lane], Rbuf[(1 * VPL + i + 1) * 32 + lane], a0, a1);
+                bpw_add2(a0, a1, Rbuf[(2 * VPL + i) * 32 + lane], Rbuf[(2 * VPL + i + 1) * 32 + lane], a0, a1);
+                bpw_add2(a0, a1, prior[i], prior[i + 1], a0, a1);                                   // :61-62
+                Vbuf[i * 32 + lane] = a0;
+                Vbuf[(i + 1) * 32 + lane] = a1;
+            }
+            if (VPL & 1) {
+                constexpr int i = VPL - 1;
                 const float r0 = Rbuf[(0 * VPL + i) * 32 + lane], r1 = Rbuf[(1 * VPL + i) * 32 + lane], r2 = Rbuf[(2 * VPL + i) * 32 + lane];
-                Vbuf[i * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);        // :61-62
+                Vbuf[i * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);
             }
             __syncwarp();
 
@@ -255,16 +293,22 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 uint32_t par = sbit[i];
+                static_assert(RW % 2 == 0, "edge slots are updated in pairs");
 #pragma unroll
-                for (int k = 0; k < RW; ++k) {
-                    const float val = ldb(Vbuf, vidx[i][k]);
-                    par ^= __float_as_uint(val);            // sign bit == hard decision (a sum with a non-zero prior is never -0.0)
-                    float qn = __fsub_rn(val, R[i][k]);                                           // :63
+                for (int k = 0; k < RW; k += 2) {
+                    const float v0 = ldb(Vbuf, vidx[i][k]), v1 = ldb(Vbuf, vidx[i][k + 1]);
+                    par ^= __float_as_uint(v0) ^ __float_as_uint(v1);   // sign bit == hard decision (a sum with a non-zero prior is never -0.0)
+                    float q0, q1;
+                    bpw_sub2(v0, v1, R[i][k], R[i][k + 1], q0, q1);                              // :63
                     if (VAR != 1) {                                                               // (plain sum-product: Q = values - R)
-                        qn = bp_damp(damp, qn, omd, Q[i][k]);                                     // :65
-                        qn = fminf(fmaxf(qn, -clipv), clipv);                                     // :66
+                        float t0, t1;
+                        bpw_mul2(omd, omd, Q[i][k], Q[i][k + 1], t0, t1);                         // :65, same roundings as bp_damp(float)
+                        bpw_fma2(damp, damp, q0, q1, t0, t1, q0, q1);
+                        q0 = fminf(fmaxf(q0, -clipv), clipv);                                     // :66
+                        q1 = fminf(fmaxf(q1, -clipv), clipv);
                     }
-                    Q[i][k] = qn;
+                    Q[i][k] = q0;
+                    Q[i][k + 1] = q1;
                 }
                 ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);
             }

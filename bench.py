@@ -369,7 +369,7 @@ def main():
                             "peak_gbs": peaks.get("hbm_gbs"), "note": "on-chip path: HBM traffic is negligible by design"},
                     "traffic": None}
         try:   # DRAM bytes per launch from the committed ncu capture of the same kernel (per shot x shots per launch)
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r1j_bp_ncu.json" if geom["kernel"] == "warp_per_shot" else "r1e_bp_ncu.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r1k_bp_ncu.json" if geom["kernel"] == "warp_per_shot" else "r1e_bp_ncu.json")))
             roofline["traffic"] = cap["dram_bytes_per_shot"] * min(B, CH)
             roofline["ncu_capture"] = {k: cap[k] for k in ("source", "issue_slots_busy_pct", "alu_pipe_pct", "lsu_pipe_pct",
                                                             "shared_wavefronts_pct_of_peak", "ipc_per_sm", "dram_bytes_per_shot")}

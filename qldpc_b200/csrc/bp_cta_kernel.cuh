@@ -137,21 +137,25 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
 #pragma unroll
                     for (int k = 0; k < RW; ++k) sgall ^= __float_as_uint(Q[i][k]);
                 }
+                float o[RW];
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
-                    float r;
                     if (VAR == 0) {
-                        const float o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
-                        r = __fmul_rn(o, salpha[i]);
+                        o[k] = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_xmin(pre[k], suf[k]);
                     } else {
                         const float sk = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : pre[k] + suf[k];
                         const float mag = fminf(bpw_psi(sk), 16.811242831518264f);
-                        const float signedmag = __uint_as_float(__float_as_uint(mag) | ((sgall ^ __float_as_uint(Q[i][k])) & 0x80000000u));
-                        r = __fmul_rn(signedmag, salpha[i]);
+                        o[k] = __uint_as_float(__float_as_uint(mag) | ((sgall ^ __float_as_uint(Q[i][k])) & 0x80000000u));
                     }
-                    R[i][k] = r;
-                    if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + ((warp * SC + i) * RW + k) * 32 + lane), r);
-                    else stb(Rbuf, sidx[i][k], r);
+                }
+#pragma unroll
+                for (int k = 0; k < RW; k += 2) {                      // packed float32 pairs, see bp_warp_kernel.cuh
+                    bpw_mul2(o[k], o[k + 1], salpha[i], salpha[i], R[i][k], R[i][k + 1]);
+#pragma unroll
+                    for (int kk = k; kk < k + 2; ++kk) {
+                        if (TWO && iter == 0) stb(Rbuf, __ldg(W.sidx0 + ((warp * SC + i) * RW + kk) * 32 + lane), R[i][kk]);
+                        else stb(Rbuf, sidx[i][kk], R[i][kk]);
+                    }
                 }
             }
             __syncthreads();
@@ -159,7 +163,17 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
             // ================= vertical step: posteriors of the owned variables =====================
             const bool last = (iter == max_iter - 1);
 #pragma unroll
-            for (int i = 0; i < SV; ++i) {
+            for (int i = 0; i + 1 < SV; i += 2) {
+                const int ig = warp * SV + i;
+                float a0 = Rbuf[(0 * VPL + ig) * 32 + lane], a1 = Rbuf[(0 * VPL + ig + 1) * 32 + lane];
+                bpw_add2(a0, a1, Rbuf[(1 * VPL + ig) * 32 + lane], Rbuf[(1 * VPL + ig + 1) * 32 + lane], a0, a1);
+                bpw_add2(a0, a1, Rbuf[(2 * VPL + ig) * 32 + lane], Rbuf[(2 * VPL + ig + 1) * 32 + lane], a0, a1);
+                bpw_add2(a0, a1, prior[i], prior[i + 1], a0, a1);
+                Vbuf[ig * 32 + lane] = a0;
+                Vbuf[(ig + 1) * 32 + lane] = a1;
+            }
+            if (SV & 1) {
+                constexpr int i = SV - 1;
                 const int ig = warp * SV + i;
                 const float r0 = Rbuf[(0 * VPL + ig) * 32 + lane], r1 = Rbuf[(1 * VPL + ig) * 32 + lane], r2 = Rbuf[(2 * VPL + ig) * 32 + lane];
                 Vbuf[ig * 32 + lane] = __fadd_rn(__fadd_rn(__fadd_rn(r0, r1), r2), prior[i]);
@@ -172,17 +186,23 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
             for (int i = 0; i < SC; ++i) {
                 uint32_t par = sbit[i];
 #pragma unroll
-                for (int k = 0; k < RW; ++k) {
-                    const float val = ldb(Vbuf, vidx[i][k]);
-                    par ^= __float_as_uint(val);            // (+inf of a padding slot: sign 0)
-                    float qn = __fsub_rn(val, R[i][k]);
+                for (int k = 0; k < RW; k += 2) {
+                    const float v0 = ldb(Vbuf, vidx[i][k]), v1 = ldb(Vbuf, vidx[i][k + 1]);
+                    par ^= __float_as_uint(v0) ^ __float_as_uint(v1);   // (+inf of a padding slot: sign 0)
+                    float q0, q1;
+                    bpw_sub2(v0, v1, R[i][k], R[i][k + 1], q0, q1);
                     if (VAR != 1) {
-                        qn = bp_damp(damp, qn, omd, Q[i][k]);
-                        qn = fminf(fmaxf(qn, -clipv), clipv);
+                        float t0, t1;
+                        bpw_mul2(omd, omd, Q[i][k], Q[i][k + 1], t0, t1);
+                        bpw_fma2(damp, damp, q0, q1, t0, t1, q0, q1);
+                        q0 = fminf(fmaxf(q0, -clipv), clipv);
+                        q1 = fminf(fmaxf(q1, -clipv), clipv);
                     }
                     // sum-product: a padding slot must stay at +inf (psi = 0); at +clip it would add psi(clip) to the sums
-                    if (VAR != 0 && ((padmask >> (i * RW + k)) & 1u)) qn = CUDART_INF_F;
-                    Q[i][k] = qn;
+                    if (VAR != 0 && ((padmask >> (i * RW + k)) & 1u)) q0 = CUDART_INF_F;
+                    if (VAR != 0 && ((padmask >> (i * RW + k + 1)) & 1u)) q1 = CUDART_INF_F;
+                    Q[i][k] = q0;
+                    Q[i][k + 1] = q1;
                 }
                 ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);
             }

@@ -15,8 +15,10 @@
 //     followed by one __all_sync.
 // Which lane owns what, and in which register slot an edge sits, is chosen by the host (bp_warp_layout.h) so that
 // scatter and gather are bank-conflict free: CPL*RW + 4*VPL + CPL*RW wavefronts per shot-iteration (56 for
-// [[144,12,12]]) and ~240 warp-instructions, against ~150 wavefronts per shot and ~560 instructions in the tiled kernel.
-// A warp decodes exactly one shot, retires it and fetches the next one from the global cursor: no divergence.
+// [[144,12,12]]) and ~225 warp-instructions (the float32 adds / multiplies / FMAs of neighbouring edges are issued as packed
+// pairs, FADD2 / FMUL2 / FFMA2), against ~150 wavefronts per shot and ~560 instructions in the tiled kernel.
+// A warp decodes exactly one shot, retires it and fetches the next one from the global cursor (four shots per atomic, two
+// shots ahead): no divergence.  The same kernel runs the reference's sum-product in the psi domain (VAR = 1, 2).
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>

@@ -10,115 +10,18 @@
 #include <string>
 #include <vector>
 
-#include "../../include/qldpc_b200.h"
-#include "bp_kernel.cuh"
-#include "bp_tiled_kernel.cuh"
-#include "bp_warp_kernel.cuh"
-#include "bp_cta_kernel.cuh"
-#include "bp_warp_kernel_f64.cuh"
-#include "bp_warp_layout.h"
-#include "misc_kernels.cuh"
-#include "osd_kernel.cuh"
+#include "capi_internal.h"
+#include "misc_kernels.cuh"     // non-template kernels: defined in this translation unit only
 #include "osdw_kernel.cuh"
 
-using namespace qldpc;
-
 static thread_local std::string g_err;
-static int fail(int code, const std::string &msg)
+int qldpc_fail(int code, const std::string &msg)
 {
     g_err = msg;
     return code;
 }
-#define CK(call)                                                                                   \
-    do {                                                                                           \
-        cudaError_t e_ = (call);                                                                   \
-        if (e_ != cudaSuccess)                                                                     \
-            return fail(QLDPC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) +       \
-                                            " (" __FILE__ ":" + std::to_string(__LINE__) + ")");  \
-    } while (0)
+static int fail(int code, const std::string &msg) { return qldpc_fail(code, msg); }
 
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
-};
-
-struct Ctrl {                       // device control block, zeroed before every BP launch
-    unsigned long long cursor;
-    unsigned long long iter_total;
-    unsigned int fail_count;
-    unsigned int pad;
-};
-
-struct qldpc_code {
-    int m = 0, n = 0, E = 0, k = 0, WM = 0, WN = 0;
-    int uniform_row_w = 0, max_col_w = 0, two_tables = 0;
-    int rank = 0;                                       // GF(2) rank of H
-    int num_sms = 0, smem_optin = 0;
-    int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_var_ptr = nullptr;
-    uint32_t *d_vtab0 = nullptr, *d_vtab1 = nullptr, *d_colmask = nullptr, *d_Lrows = nullptr, *d_Hrows = nullptr;
-    // T-lanes-per-shot kernel tables: 4 words per position {e0, e1, e2, v}, e = check | k << 16.  [0]: identity positions
-    // (float64: the reference's addition order is kept as is), [1]/[2]: positions optimised for TL = 4 / 8 (float32)
-    uint32_t *d_vell0[3] = {nullptr, nullptr, nullptr}, *d_vell1[3] = {nullptr, nullptr, nullptr};
-    double tiled_conflict_cost[3][2] = {{0, 0}, {0, 0}, {0, 0}};   // modelled wavefronts per shot-iteration: before / after
-    uint32_t *d_wtab = nullptr;                                    // warp-per-shot kernel: the six tables of BPWarpTables, back to back
-    BPWarpTables wtab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    WarpLayoutBuilder *wlayout = nullptr;                          // labelling of checks / variables / edge slots (host)
-    int warp_cost[3] = {0, 0, 0};                                  // gather wavefronts per shot-iteration: natural, current, floor
-    bool warp_ok = false;
-    // CTA-per-shot kernel (bp_cta_kernel.cuh): labelling with NW * 3 check slots and NW * 7 variable slots
-    uint32_t *d_ctab = nullptr;
-    BPWarpTables ctab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    int cta_nw = 0, cta_sc = 3, cta_sv = 7, cta_cost[3] = {0, 0, 0};
-    bool cta_ok = false;
-    int max_row_w = 0;
-    double prior_max = 0.0;
-    bool prior_uniform = false;
-    bool tiled_ok = false;
-    std::vector<double> prior_cache;
-    DevBuf prior32, prior64, ctrl, gstate;
-    DevBuf ws_redo;
-    DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
-        ws_weight, ws_cnt, ws_llr_in, ws_rec;
-    // Three-stage pipeline of the host-pointer decode call: a copy-in stream, a compute stream and a copy-out stream,
-    // chained per chunk by events; chunk buffers rotate over NSLOT slots.  Kernels of different chunks never share the
-    // GPU (each runs at full speed), the copies of the neighbouring chunks run under them.
-    struct Slot {
-        DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail, redo;
-        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
-        bool used = false;
-    };
-    static constexpr int NSLOT = 4;
-    Slot slot[NSLOT];
-    cudaStream_t st_in = nullptr, st_comp = nullptr, st_out = nullptr;
-    BPGraphDev graph() const
-    {
-        BPGraphDev g;
-        g.m = m; g.n = n; g.E = E; g.WM = WM; g.WN = WN;
-        g.uniform_row_w = uniform_row_w; g.max_col_w = max_col_w; g.two_tables = two_tables;
-        g.row_ptr = d_row_ptr; g.col_idx = d_col_idx; g.var_ptr = d_var_ptr;
-        g.vtab0 = d_vtab0; g.vtab1 = d_vtab1; g.colmask = d_colmask;
-        return g;
-    }
-};
 
 extern "C" const char *qldpc_last_error(void) { return g_err.c_str(); }
 extern "C" int qldpc_version(void) { return 100; }
@@ -416,18 +319,6 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
 // ------------------------------------------------------------------------------------------------
 // BP launch geometry
 // ------------------------------------------------------------------------------------------------
-struct BPGeom {
-    bool staged;
-    int tiled_T;          // 0: thread-per-shot kernels; 4 / 8: lanes per shot of the tiled kernel
-    bool warp_kernel;     // warp-per-shot kernel (messages in registers)
-    int warp_var;         // its variant: 0 min-sum, 1 sum-product, 2 symmetric sum-product
-    bool cta_kernel;      // CTA-per-shot kernel (messages in registers, several warps per shot)
-    int shots_per_cta;
-    int refill_min;
-    int threads, grid;
-    size_t smem;
-    size_t gstate_bytes;
-};
 
 static int kernel_variant(int v) { return v == QLDPC_MIN_SUM ? VAR_MIN_SUM : VAR_SUM_PRODUCT; }
 
@@ -584,140 +475,6 @@ static int set_prior(qldpc_code *c, const double *prior_host, cudaStream_t st)
     return QLDPC_OK;
 }
 
-template <typename T, int VAR, int WMS, bool SMEM>
-static cudaError_t launch_bp_inst(const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    auto kern = bp_decode_kernel<T, VAR, WMS, SMEM>;
-    if (SMEM) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
-        if (e != cudaSuccess) return e;
-    }
-    kern<<<G.grid, G.threads, G.smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-template <typename T, int VAR, int TL, int WMS>
-static cudaError_t launch_bp_tiled_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    auto kern = bp_tiled_kernel<T, VAR, TL, WMS, 6>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
-    if (e != cudaSuccess) return e;
-    const int ti = (sizeof(T) == 8) ? 0 : (TL == 4 ? 1 : 2);     // float64 keeps identity positions
-    kern<<<G.grid, G.threads, G.smem, st>>>(P, c->d_vell0[ti], c->d_vell1[ti], G.refill_min);
-    return cudaGetLastError();
-}
-
-template <typename T, int VAR, int TL>
-static cudaError_t launch_bp_tiled_w(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    switch (P.g.WM) {
-    case 2: return launch_bp_tiled_inst<T, VAR, TL, 2>(c, P, G, st);
-    case 3: return launch_bp_tiled_inst<T, VAR, TL, 3>(c, P, G, st);
-    case 5: return launch_bp_tiled_inst<T, VAR, TL, 5>(c, P, G, st);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-template <int CPL, int VPL, bool TWO, int VAR>
-static cudaError_t launch_bp_warp_inst3(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    auto kern = bp_warp_kernel<CPL, VPL, 6, TWO, VAR>;
-    if (G.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
-        if (e != cudaSuccess) return e;
-    }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
-    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
-    return cudaGetLastError();
-}
-
-template <int CPL, int VPL, bool TWO>
-static cudaError_t launch_bp_warp_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    auto kern = bp_warp_kernel_f64<CPL, VPL, 6, TWO>;
-    if (G.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
-        if (e != cudaSuccess) return e;
-    }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
-    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
-    return cudaGetLastError();
-}
-
-template <int CPL, int VPL, bool TWO>
-static cudaError_t launch_bp_warp_inst2(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    if (G.warp_var == 3) return launch_bp_warp_f64<CPL, VPL, TWO>(c, P, G, st);
-    if (G.warp_var == 0) return launch_bp_warp_inst3<CPL, VPL, TWO, 0>(c, P, G, st);
-    if (G.warp_var == 1) return launch_bp_warp_inst3<CPL, VPL, TWO, 1>(c, P, G, st);
-    return launch_bp_warp_inst3<CPL, VPL, TWO, 2>(c, P, G, st);
-}
-
-template <int CPL, int VPL>
-static cudaError_t launch_bp_warp_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    return c->two_tables ? launch_bp_warp_inst2<CPL, VPL, true>(c, P, G, st) : launch_bp_warp_inst2<CPL, VPL, false>(c, P, G, st);
-}
-
-static cudaError_t launch_bp_cta(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    const int var = G.warp_var;
-    void (*kern)(const BPParams, const BPWarpTables, int) = nullptr;
-#define QLDPC_CTA_PICK(SC, SV)                                                                                              \
-    kern = c->two_tables ? (var == 0 ? bp_cta_kernel<SC, SV, 8, true, 0> : var == 1 ? bp_cta_kernel<SC, SV, 8, true, 1>     \
-                                                                                    : bp_cta_kernel<SC, SV, 8, true, 2>)    \
-                         : (var == 0 ? bp_cta_kernel<SC, SV, 8, false, 0> : var == 1 ? bp_cta_kernel<SC, SV, 8, false, 1>   \
-                                                                                     : bp_cta_kernel<SC, SV, 8, false, 2>)
-    if (c->cta_sc == 2) { QLDPC_CTA_PICK(2, 5); } else { QLDPC_CTA_PICK(3, 7); }
-#undef QLDPC_CTA_PICK
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
-    if (e != cudaSuccess) return e;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
-    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), P.B));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->ctab, c->cta_sv * c->cta_nw);
-    return cudaGetLastError();
-}
-
-static cudaError_t launch_bp_warp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    if (c->WM == 2 && c->WN == 3) return launch_bp_warp_inst<2, 3>(c, P, G, st);
-    if (c->WM == 2 && c->WN == 4) return launch_bp_warp_inst<2, 4>(c, P, G, st);
-    if (c->WM == 3 && c->WN == 5) return launch_bp_warp_inst<3, 5>(c, P, G, st);
-    if (c->WM == 5 && c->WN == 9) return launch_bp_warp_inst<5, 9>(c, P, G, st);
-    return cudaErrorInvalidValue;
-}
-
-static cudaError_t launch_bp_tiled(const qldpc_code *c, const BPParams &P, const BPGeom &G, int precision, int kv, cudaStream_t st)
-{
-    if (precision == 32 && kv == VAR_MIN_SUM)
-        return G.tiled_T == 4 ? launch_bp_tiled_w<float, VAR_MIN_SUM, 4>(c, P, G, st) : launch_bp_tiled_w<float, VAR_MIN_SUM, 8>(c, P, G, st);
-    if (G.tiled_T != 8) return cudaErrorInvalidValue;
-    if (precision == 32) return launch_bp_tiled_w<float, VAR_SUM_PRODUCT, 8>(c, P, G, st);
-    if (kv == VAR_MIN_SUM) return launch_bp_tiled_w<double, VAR_MIN_SUM, 8>(c, P, G, st);
-    return launch_bp_tiled_w<double, VAR_SUM_PRODUCT, 8>(c, P, G, st);
-}
-
-template <typename T, int VAR>
-static cudaError_t launch_bp_tv(const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    if (G.staged) return launch_bp_inst<T, VAR, 0, false>(P, G, st);
-    switch (P.g.WM) {
-    case 1: return launch_bp_inst<T, VAR, 1, true>(P, G, st);
-    case 2: return launch_bp_inst<T, VAR, 2, true>(P, G, st);
-    case 3: return launch_bp_inst<T, VAR, 3, true>(P, G, st);
-    case 4: case 5: {
-        // WM == 4 runs the 5-word instantiation on a 5-word view?  No: keep exact strides.
-        if (P.g.WM == 5) return launch_bp_inst<T, VAR, 5, true>(P, G, st);
-        return launch_bp_inst<T, VAR, 4, true>(P, G, st);
-    }
-    default: return cudaErrorInvalidValue;
-    }
-}
 
 static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
                           const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters, void *llr,
@@ -771,10 +528,8 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
         e = launch_bp_warp(c, P, G, st);
     else if (G.tiled_T)
         e = launch_bp_tiled(c, P, G, cfg->precision, kv, st);
-    else if (cfg->precision == 64)
-        e = (kv == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
     else
-        e = (kv == VAR_MIN_SUM) ? launch_bp_tv<float, VAR_MIN_SUM>(P, G, st) : launch_bp_tv<float, VAR_SUM_PRODUCT>(P, G, st);
+        e = launch_bp_generic(P, G, cfg->precision, kv, st);
     if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("bp_decode_kernel launch: ") + cudaGetErrorString(e));
     return QLDPC_OK;
 }
@@ -792,174 +547,6 @@ extern "C" int qldpc_bp_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg, co
 // ------------------------------------------------------------------------------------------------
 // OSD
 // ------------------------------------------------------------------------------------------------
-template <typename K, int WM>
-static cudaError_t launch_osd_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
-{
-    auto kern = osd0_kernel<K, WM>;
-    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_WARPS * 32, smem);
-    long long grid = (long long)c->num_sms * std::max(1, occ);
-    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, (count_hint + OSD_WARPS - 1) / OSD_WARPS));
-    kern<<<(int)grid, OSD_WARPS * 32, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-template <typename K, int WM, int NS>
-static cudaError_t launch_osd_fast_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
-{
-    auto kern = osd0_fast_kernel<K, WM, NS>;
-    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_WARPS * 32, smem);
-    long long grid = (long long)c->num_sms * std::max(1, occ);
-    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, (count_hint + OSD_WARPS - 1) / OSD_WARPS));
-    kern<<<(int)grid, OSD_WARPS * 32, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-template <typename K, int WM, int NS2>
-static cudaError_t launch_osd_fast2_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
-{
-    auto kern = osd0_fast2_kernel<K, WM, NS2>;
-    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS * 2;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-    }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSD_WARPS * 32, smem);
-    long long grid = (long long)c->num_sms * std::max(1, occ);
-    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, (count_hint + 2 * OSD_WARPS - 1) / (2 * OSD_WARPS)));
-    kern<<<(int)grid, OSD_WARPS * 32, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-// column-major kernel: the shapes of the reference's codes (m <= 160, n <= 288); cudaErrorNotSupported otherwise
-template <typename K>
-static cudaError_t launch_osd_fast(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
-{
-    const int NS = (P.n + 31) / 32;
-    static const bool one_per_warp = getenv("QLDPC_OSD_ONE_SHOT_PER_WARP") != nullptr;    // test / comparison hook
-    if (!one_per_warp) {                       // two shots per warp where the registers allow it
-        const int NS2 = (P.n + 15) / 16;
-        if (P.WM == 2 && NS2 == 5) return launch_osd_fast2_inst<K, 2, 5>(c, P, count_hint, st);
-        if (P.WM == 2 && NS2 == 6) return launch_osd_fast2_inst<K, 2, 6>(c, P, count_hint, st);
-        if (P.WM == 2 && NS2 == 7) return launch_osd_fast2_inst<K, 2, 7>(c, P, count_hint, st);
-        if (P.WM == 3 && NS2 == 9) return launch_osd_fast2_inst<K, 3, 9>(c, P, count_hint, st);
-    }
-    if (P.WM == 2 && NS == 3) return launch_osd_fast_inst<K, 2, 3>(c, P, count_hint, st);
-    if (P.WM == 2 && NS == 4) return launch_osd_fast_inst<K, 2, 4>(c, P, count_hint, st);
-    if (P.WM == 3 && NS == 5) return launch_osd_fast_inst<K, 3, 5>(c, P, count_hint, st);
-    if (P.WM == 5 && NS == 9) return launch_osd_fast_inst<K, 5, 9>(c, P, count_hint, st);
-    return cudaErrorNotSupported;
-}
-
-template <typename K>
-static cudaError_t launch_osd_k(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
-{
-    static const bool force_rowmajor = getenv("QLDPC_OSD_FORCE_ROWMAJOR") != nullptr;    // test hook
-    if (!P.rec_ordering && !force_rowmajor) {
-        const cudaError_t e = launch_osd_fast<K>(c, P, count_hint, st);
-        if (e != cudaErrorNotSupported) return e;
-    }
-    switch (P.WM) {
-    case 1: return launch_osd_inst<K, 1>(c, P, count_hint, st);
-    case 2: return launch_osd_inst<K, 2>(c, P, count_hint, st);
-    case 3: return launch_osd_inst<K, 3>(c, P, count_hint, st);
-    case 4: return launch_osd_inst<K, 4>(c, P, count_hint, st);
-    case 5: return launch_osd_inst<K, 5>(c, P, count_hint, st);
-    default: return cudaErrorInvalidValue;
-    }
-}
-
-template <typename K>
-static cudaError_t launch_osd_block(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
-{
-    auto kern = osd0_block_kernel<K>;
-    const size_t smem = osdb_smem_bytes<K>(P.m, P.n);
-    if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSDB_THREADS, smem);
-    long long grid = (long long)c->num_sms * std::max(1, occ);
-    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, count_hint));
-    kern<<<(int)grid, OSDB_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-template <typename K>
-static cudaError_t launch_osd_block_fast(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
-{
-    auto kern = (P.m < 1024 && P.max_col_w <= 3) ? osd0_block_fast_kernel<K, true> : osd0_block_fast_kernel<K, false>;
-    const size_t smem = osdbf_smem_bytes<K>(P.m, P.n);
-    if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSDB_THREADS, smem);
-    long long grid = (long long)c->num_sms * std::max(1, occ);
-    if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, count_hint));
-    kern<<<(int)grid, OSDB_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
-}
-
-static bool osd_use_block(const qldpc_code *c)
-{
-    static const bool force = getenv("QLDPC_OSD_FORCE_BLOCK") != nullptr;    // test hook
-    return force || c->WM > 5 || c->n > 65535;
-}
-
-static int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st, DevBuf *redo = nullptr)
-{
-    P.m = c->m; P.n = c->n; P.WM = c->WM; P.WN = c->WN;
-    P.rank = c->rank;
-    P.colmask = c->d_colmask;
-    if (osd_use_block(c)) {
-        if (c->n > 65534 || c->m > 32767) return fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65534 columns or 32767 rows");
-        if (P.rec_ordering) return fail(QLDPC_ERR_UNSUPPORTED, "OSD-w sweep (order > 0) is not available for check matrices with more than 160 rows");
-        OSDBlockParams Q;
-        Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank; Q.max_col_w = c->max_col_w;
-        Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1;
-        Q.idx = P.idx; Q.count_dev = P.count_dev; Q.count_host = P.count_host;
-        Q.synd = P.synd; Q.llr = P.llr; Q.hard = P.hard; Q.out = P.out; Q.valid = P.valid;
-        Q.redo_idx = nullptr; Q.redo_count = nullptr;
-        static const bool force_rowmajor = getenv("QLDPC_OSD_FORCE_ROWMAJOR") != nullptr;    // test hook
-        const long long cap = P.count_dev ? P.cap : P.count_host;
-        if (!force_rowmajor && cap > 0 && redo && c->WM <= 32) {
-            // column-major kernel; the shots it flags as inconsistent are redone by the row-major one
-            CK(redo->reserve(sizeof(int32_t) * (size_t)cap + 16));
-            Q.redo_count = redo->as<unsigned int>();
-            Q.redo_idx = redo->as<int32_t>() + 4;
-            CK(cudaMemsetAsync(Q.redo_count, 0, sizeof(unsigned int), st));
-            cudaError_t e = llr_f64 ? launch_osd_block_fast<double>(c, Q, count_hint, st) : launch_osd_block_fast<float>(c, Q, count_hint, st);
-            if (e != cudaSuccess)
-                return fail(e == cudaErrorInvalidValue ? QLDPC_ERR_UNSUPPORTED : QLDPC_ERR_CUDA,
-                            std::string("osd0_block_fast_kernel launch (check matrix too large for shared memory?): ") + cudaGetErrorString(e));
-            Q.idx = Q.redo_idx; Q.count_dev = Q.redo_count; Q.count_host = 0;
-            e = llr_f64 ? launch_osd_block<double>(c, Q, -1, st) : launch_osd_block<float>(c, Q, -1, st);
-            if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osd0_block_kernel (redo) launch: ") + cudaGetErrorString(e));
-            return QLDPC_OK;
-        }
-        cudaError_t e = llr_f64 ? launch_osd_block<double>(c, Q, count_hint, st) : launch_osd_block<float>(c, Q, count_hint, st);
-        if (e != cudaSuccess)
-            return fail(e == cudaErrorInvalidValue ? QLDPC_ERR_UNSUPPORTED : QLDPC_ERR_CUDA,
-                        std::string("osd0_block_kernel launch (check matrix too large for shared memory?): ") + cudaGetErrorString(e));
-        return QLDPC_OK;
-    }
-    cudaError_t e = llr_f64 ? launch_osd_k<double>(c, P, count_hint, st) : launch_osd_k<float>(c, P, count_hint, st);
-    if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osd0_kernel launch: ") + cudaGetErrorString(e));
-    return QLDPC_OK;
-}
 
 extern "C" int qldpc_osd_decode_dev(qldpc_code *c, const int32_t *idx, const uint32_t *count_dev, int64_t count_host,
                                     const uint32_t *synd, const void *llr, int32_t llr_f64, const uint32_t *hard,
@@ -1224,8 +811,7 @@ extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg,
         P.gstate = c->gstate.p;
         P.r_dump = c->ws_rec.p;
         P.dump_iter = dump_iter;
-        cudaError_t e = (kernel_variant(cf.variant) == VAR_MIN_SUM) ? launch_bp_tv<double, VAR_MIN_SUM>(P, G, st)
-                                                                    : launch_bp_tv<double, VAR_SUM_PRODUCT>(P, G, st);
+        cudaError_t e = launch_bp_generic(P, G, 64, kernel_variant(cf.variant), st);
         if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("bp_decode_kernel (messages) launch: ") + cudaGetErrorString(e));
         CK(cudaMemcpyAsync(r_edges + (size_t)o * c->E, c->ws_rec.p, 8 * (size_t)b * c->E, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));

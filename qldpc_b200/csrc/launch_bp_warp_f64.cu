@@ -1,0 +1,35 @@
+// Launchers of the warp-per-shot float64 min-sum kernels (bp_warp_kernel_f64.cuh): the bit-exact parity mode.
+#include "capi_internal.h"
+
+template <int CPL, int VPL, bool TWO>
+static cudaError_t launch_f64_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    auto kern = bp_warp_kernel_f64<CPL, VPL, 6, TWO>;
+    if (G.smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
+        if (e != cudaSuccess) return e;
+    }
+    int occ = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
+    return cudaGetLastError();
+}
+
+template <int CPL, int VPL>
+static cudaError_t launch_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    return c->two_tables ? launch_f64_inst<CPL, VPL, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false>(c, P, G, st);
+}
+
+#define QLDPC_WARP_SHAPES(F)                                                  \
+    if (c->WM == 2 && c->WN == 3) return F<2, 3>(c, P, G, st);                \
+    if (c->WM == 2 && c->WN == 4) return F<2, 4>(c, P, G, st);                \
+    if (c->WM == 3 && c->WN == 5) return F<3, 5>(c, P, G, st);                \
+    if (c->WM == 5 && c->WN == 9) return F<5, 9>(c, P, G, st);                \
+    return cudaErrorInvalidValue
+
+cudaError_t launch_bp_warp_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
+{
+    QLDPC_WARP_SHAPES(launch_f64);
+}

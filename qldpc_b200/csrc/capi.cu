@@ -83,7 +83,8 @@ static int layout_tables_upload(const WarpLayout &L, uint32_t **dbuf, BPWarpTabl
 // (re)builds the device tables of the warp-per-shot kernel from c->wlayout; the device must be idle
 static int warp_tables_upload(qldpc_code *c)
 {
-    return layout_tables_upload(c->wlayout->tables(), &c->d_wtab, &c->wtab, c->warp_cost);
+    if (int rc = layout_tables_upload(c->wlayout->tables(), &c->d_wtab, &c->wtab, c->warp_cost)) return rc;
+    return layout_tables_upload(c->wlayout64->tables(), &c->d_wtab64, &c->wtab64, c->warp64_cost);
 }
 
 static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const int32_t *col_idx, const int32_t *var_ptr,
@@ -230,7 +231,8 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
     c->warp_ok = c->tiled_ok && ((c->WM == 2 && (c->WN == 3 || c->WN == 4)) || (c->WM == 3 && c->WN == 5) || (c->WM == 5 && c->WN == 9));
     if (c->warp_ok) {
         c->wlayout = new WarpLayoutBuilder(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 6);
-        if (!getenv("QLDPC_WARP_NATURAL_LAYOUT")) c->wlayout->construct();
+        c->wlayout64 = new WarpLayoutBuilder(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 6, 0, 0, 16);
+        if (!getenv("QLDPC_WARP_NATURAL_LAYOUT")) { c->wlayout->construct(); c->wlayout64->construct(); }
         if (int rc = warp_tables_upload(c)) return rc;
     }
     // CTA-per-shot kernel: larger matrices with row weight <= 8 and column weight <= 3 (the space-time matrices): the
@@ -299,14 +301,16 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
     for (int ti = 0; ti < 3; ++ti) { cudaFree(c->d_vell0[ti]); cudaFree(c->d_vell1[ti]); }
     cudaFree(c->d_wtab);
+    cudaFree(c->d_wtab64);
+    delete c->wlayout64;
     cudaFree(c->d_ctab);
     delete c->wlayout;
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags, &c->ws_redo,
-                      &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec};
+                      &c->ws_weight, &c->ws_cnt, &c->ws_llr_in, &c->ws_rec, &c->ws_inv};
     for (DevBuf *b : bufs) b->release();
     for (auto &sl : c->slot) {
-        DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail, &sl.redo};
+        DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail, &sl.redo, &sl.valid, &sl.inv};
         for (DevBuf *b : sb) b->release();
         for (cudaEvent_t e : {sl.ev_in, sl.ev_comp, sl.ev_out})
             if (e) cudaEventDestroy(e);
@@ -343,15 +347,18 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         G->gstate_bytes = 0;
         return QLDPC_OK;
     }
-    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && (cfg->precision == 32 || cfg->variant == QLDPC_MIN_SUM) &&
+    // (float64 warp kernel: no -0.0 canonicalisation, valid for damping > 0, clip >= 0 and max_iter <= 500 -- see its header)
+    const bool f64_warp_ok = cfg->variant == QLDPC_MIN_SUM && cfg->damping > 0.0 && cfg->clip >= 0.0 && cfg->max_iter <= 500;
+    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && (cfg->precision == 32 || f64_warp_ok) &&
         (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
         G->staged = false;
         G->warp_kernel = true;
         // 0 min-sum, 1 sum-product, 2 symmetric sum-product (float32); 3 float64 min-sum (the bit-exact parity mode)
         G->warp_var = cfg->precision == 64 ? 3 : (cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2));
-        G->threads = BPW_WARPS * 32;
-        G->shots_per_cta = BPW_WARPS;
-        G->smem = bp_warp_smem_per_warp(c->WN) * BPW_WARPS * (cfg->precision == 64 ? 2 : 1);
+        const int nw = cfg->precision == 64 ? BPW64_WARPS : BPW_WARPS;
+        G->threads = nw * 32;
+        G->shots_per_cta = nw;
+        G->smem = cfg->precision == 64 ? bp_warp64_smem_per_warp(c->WN) * nw : bp_warp_smem_per_warp(c->WN) * nw;
         G->grid = 0;                 // filled at launch from the occupancy query
         G->gstate_bytes = 0;
         return QLDPC_OK;
@@ -426,8 +433,8 @@ extern "C" int qldpc_warp_layout_tune(qldpc_code *c, int64_t steps, int32_t *cos
     if (!c) return fail(QLDPC_ERR_ARG, "qldpc_warp_layout_tune: null code");
     if (!c->warp_ok) return fail(QLDPC_ERR_UNSUPPORTED, "qldpc_warp_layout_tune: the warp-per-shot kernel does not apply to this code");
     CK(cudaDeviceSynchronize());
-    if (steps < 0) c->wlayout->natural();
-    if (steps > 0) c->wlayout->construct(steps);
+    if (steps < 0) { c->wlayout->natural(); c->wlayout64->natural(); }
+    if (steps > 0) { c->wlayout->construct(steps); c->wlayout64->construct(steps); }
     if (steps != 0)
         if (int rc = warp_tables_upload(c)) return rc;
     if (cost) { cost[0] = c->warp_cost[0]; cost[1] = c->warp_cost[1]; cost[2] = c->warp_cost[2]; }
@@ -663,19 +670,64 @@ extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// OSD-w sweep stage (performOSD_enhanced with order > 0, OSD_enhanced.py:58-131) behind an OSD-0 launch that wrote `valid`:
+// the shots of the list whose OSD-0 solution misses the syndrome are compacted on the device and swept by osdw_kernel,
+// with the count read from device memory (no host synchronisation).  hard == null: BP hard decision = llr < 0.
+// ------------------------------------------------------------------------------------------------
+static int osdw_supported(const qldpc_code *c, int32_t order)
+{
+    if (order <= 0) return QLDPC_OK;
+    if (order > OSDW_MAX_ORDER) return fail(QLDPC_ERR_ARG, "OSD order must be <= 16");
+    // block-per-shot OSD (m > 160): no sweep kernel.  A full-rank H makes every syndrome consistent, so the sweep is dead
+    // code there (OSD_enhanced.py:58-60) and OSD-0 is the exact answer; a rank-deficient one is refused.
+    if (osd_use_block(c) && c->rank < c->m)
+        return fail(QLDPC_ERR_UNSUPPORTED, "OSD-w sweep (order > 0) is not available for rank-deficient check matrices with more than 160 rows");
+    return QLDPC_OK;
+}
+
+static int osdw_stage(qldpc_code *c, const int32_t *idx, const uint32_t *count_dev, long long count_host, long long cap,
+                      const uint32_t *synd, const void *llr, int llr_f64, const uint32_t *hard, uint32_t *out, const uint8_t *valid,
+                      int32_t order, int64_t max_combinations, DevBuf *inv_buf, cudaStream_t st)
+{
+    if (order <= 0 || osd_use_block(c) || cap <= 0) return QLDPC_OK;
+    CK(inv_buf->reserve(sizeof(int32_t) * (size_t)cap + 16));
+    unsigned int *inv_count = inv_buf->as<unsigned int>();
+    int32_t *inv_idx = inv_buf->as<int32_t>() + 4;
+    CK(cudaMemsetAsync(inv_count, 0, sizeof(unsigned int), st));
+    compact_invalid_kernel<<<(int)std::max<long long>(1, std::min<long long>((cap + 255) / 256, (long long)c->num_sms * 8)), 256, 0, st>>>(
+        idx, count_dev, count_host, valid, inv_idx, inv_count);
+    CK(cudaGetLastError());
+    OSDWParams W;
+    memset(&W, 0, sizeof(W));
+    W.m = c->m; W.n = c->n; W.WM = c->WM; W.WN = c->WN; W.rank = c->rank;
+    W.Hrows = c->d_Hrows; W.colmask = c->d_colmask;
+    W.idx = inv_idx; W.count_dev = inv_count; W.count = 0;
+    W.synd = synd; W.llr = llr; W.llr_f32 = llr_f64 ? 0 : 1; W.hard = hard;
+    W.sol = out; W.valid = valid;
+    W.order = order;
+    W.max_combinations = max_combinations > 0 ? max_combinations : 0;
+    cudaError_t e = launch_osdw(W, c->num_sms, st);
+    if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osdw_kernel launch: ") + cudaGetErrorString(e));
+    return QLDPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // fused BP -> OSD
 // ------------------------------------------------------------------------------------------------
 static const long long CHUNK = 1ll << 24;   // shots per internal launch (bounds the LLR hand-off workspace: 4n bytes per shot)
 
-// BP, then OSD-0 on the compacted BP failures, for at most CHUNK shots, with explicit workspaces
+// BP, then OSD-0 on the compacted BP failures -- and, for osd_order > 0, the OSD-w sweep on those whose OSD-0 solution misses
+// the syndrome (never the case for syndromes of the form e * H^T) -- for at most CHUNK shots, with explicit workspaces
 static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior_host, long long b, const uint32_t *synd,
                        int32_t osd_order, uint32_t *corr, uint8_t *conv, int32_t *iters, uint64_t *iter_total,
-                       DevBuf *ctrl, DevBuf *gstate, DevBuf *llr_buf, DevBuf *fail_buf, DevBuf *redo_buf, cudaStream_t st)
+                       DevBuf *ctrl, DevBuf *gstate, DevBuf *llr_buf, DevBuf *fail_buf, DevBuf *redo_buf, DevBuf *valid_buf, DevBuf *inv_buf,
+                       cudaStream_t st)
 {
     const int tsize = cfg->precision == 64 ? 8 : 4;
     void *llr = nullptr;
     int32_t *fidx = nullptr;
     uint32_t *fcnt = nullptr;
+    if (int rc = osdw_supported(c, osd_order)) return rc;
     if (osd_order >= 0) {
         CK(llr_buf->reserve((size_t)b * c->n * tsize));
         CK(fail_buf->reserve(sizeof(int32_t) * (size_t)b + 16));
@@ -687,6 +739,7 @@ static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *
                             ctrl, gstate, st);
     if (rc) return rc;
     if (osd_order >= 0) {
+        const bool sweep = osd_order > 0 && !osd_use_block(c);
         OSDParams P;
         memset(&P, 0, sizeof(P));
         P.idx = fidx; P.count_dev = fcnt; P.count_host = 0;
@@ -694,11 +747,15 @@ static int bposd_chunk(qldpc_code *c, const qldpc_bp_config *cfg, const double *
         P.llr = llr;
         P.hard = corr;
         P.out = corr;
-        // OSD-w == OSD-0 whenever the OSD-0 solution satisfies the syndrome (OSD_enhanced.py:58-60),
-        // which is always the case for syndromes of the form e * H^T.
+        if (sweep) {                       // (the flag is written for the listed shots only; the sweep reads no others)
+            CK(valid_buf->reserve((size_t)b));
+            P.valid = valid_buf->as<uint8_t>();
+        }
         P.cap = b;
         rc = osd_launch(c, P, tsize == 8, -1, st, redo_buf);
         if (rc) return rc;
+        if (sweep)
+            if ((rc = osdw_stage(c, fidx, fcnt, 0, b, synd, llr, tsize == 8, nullptr, corr, P.valid, osd_order, 0, inv_buf, st))) return rc;
     }
     return QLDPC_OK;
 }
@@ -713,7 +770,7 @@ extern "C" int qldpc_bposd_decode_dev(qldpc_code *c, const qldpc_bp_config *cfg,
     for (long long o = 0; o < B; o += CHUNK) {
         const long long b = std::min<long long>(CHUNK, B - o);
         if (int rc = bposd_chunk(c, cfg, prior_host, b, synd + (size_t)o * c->WM, osd_order, corr + (size_t)o * c->WN, conv + o,
-                                 iters ? iters + o : nullptr, iter_total, &c->ctrl, &c->gstate, &c->ws_llr, &c->ws_fail, &c->ws_redo, st))
+                                 iters ? iters + o : nullptr, iter_total, &c->ctrl, &c->gstate, &c->ws_llr, &c->ws_fail, &c->ws_redo, &c->ws_valid, &c->ws_inv, st))
             return rc;
     }
     return QLDPC_OK;
@@ -823,6 +880,7 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
                                      int32_t order, int64_t max_combinations, uint8_t *out)
 {
     if (!c || !synd || !llr || !hard || !out) return fail(QLDPC_ERR_ARG, "qldpc_osd_decode_host: null argument");
+    if (int rc = osdw_supported(c, order)) return rc;
     cudaStream_t st = 0;
     const long long chunk = 1ll << 18;
     for (long long o = 0; o < B; o += chunk) {
@@ -847,39 +905,10 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
         P.hard = c->ws_hard.as<uint32_t>();
         P.out = c->ws_err.as<uint32_t>();
         P.valid = c->ws_valid.as<uint8_t>();
-        const bool want_rec = order > 0 && !osd_use_block(c);
-        if (want_rec) {
-            const size_t rec = (size_t)b * (4 * (size_t)c->n + 4 * (size_t)c->m + c->m + 4) + 64;
-            CK(c->ws_rec.reserve(rec));
-            unsigned char *r = c->ws_rec.as<unsigned char>();
-            P.rec_ordering = reinterpret_cast<int32_t *>(r);             r += 4 * (size_t)b * c->n;
-            P.rec_pivcol = reinterpret_cast<int32_t *>(r);               r += 4 * (size_t)b * c->m;
-            P.rec_npiv = reinterpret_cast<int32_t *>(r);                 r += 4 * (size_t)b;
-            P.rec_sred = reinterpret_cast<uint8_t *>(r);
-        }
         if (int rc = osd_launch(c, P, 1, b, st, &c->ws_redo)) return rc;
-        bool any_invalid = false;
-        if (want_rec) {     // the sweep is dead code whenever every OSD-0 solution satisfies its syndrome (OSD_enhanced.py:58-60)
-            std::vector<uint8_t> hv((size_t)b);
-            CK(cudaMemcpyAsync(hv.data(), c->ws_valid.p, (size_t)b, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            for (uint8_t x : hv) any_invalid |= (x == 0);
-        }
-        if (want_rec && any_invalid) {
-            // OSD-w sweep on the shots whose OSD-0 solution misses the syndrome (OSD_enhanced.py:66-131)
-            OSDWParams W;
-            memset(&W, 0, sizeof(W));
-            W.m = c->m; W.n = c->n; W.WM = c->WM; W.WN = c->WN;
-            W.Hrows = c->d_Hrows;
-            W.count = b;
-            W.synd = P.synd; W.llr = reinterpret_cast<const double *>(P.llr); W.hard = P.hard;
-            W.sol = P.out; W.valid = P.valid;
-            W.rec_ordering = P.rec_ordering; W.rec_pivcol = P.rec_pivcol; W.rec_sred = P.rec_sred; W.rec_npiv = P.rec_npiv;
-            W.order = order;
-            W.max_combinations = max_combinations > 0 ? max_combinations : 0;
-            cudaError_t e = launch_osdw(W, c->num_sms, st);
-            if (e != cudaSuccess) return fail(QLDPC_ERR_CUDA, std::string("osdw_kernel launch: ") + cudaGetErrorString(e));
-        }
+        // OSD-w sweep on the shots whose OSD-0 solution misses the syndrome (OSD_enhanced.py:58-131)
+        if (int rc = osdw_stage(c, nullptr, nullptr, b, b, P.synd, P.llr, 1, P.hard, P.out, P.valid, order, max_combinations, &c->ws_inv, st))
+            return rc;
         if (int rc = qldpc_unpack_bits_dev(c->ws_err.as<uint32_t>(), c->ws_u8b.as<uint8_t>(), b, c->n, st)) return rc;
         CK(cudaMemcpyAsync(out + (size_t)o * c->n, c->ws_u8b.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -947,7 +976,7 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         if (!packed)
             if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, c->st_comp)) return rc;
         if (int rc = bposd_chunk(c, cfg, prior, b, sl.synd.as<uint32_t>(), osd_order, sl.hard.as<uint32_t>(), sl.conv.as<uint8_t>(),
-                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, &sl.redo, c->st_comp))
+                                 sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, &sl.redo, &sl.valid, &sl.inv, c->st_comp))
             return rc;
         if (!packed)
             if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, c->st_comp)) return rc;

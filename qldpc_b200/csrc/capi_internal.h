@@ -76,6 +76,11 @@ struct qldpc_code {
     uint32_t *d_wtab = nullptr;                                    // warp-per-shot kernel: the six tables of BPWarpTables, back to back
     BPWarpTables wtab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     WarpLayoutBuilder *wlayout = nullptr;                          // labelling of checks / variables / edge slots (host)
+    // float64 warp kernel: the same tables for a labelling with 16-lane conflict domains (64-bit shared-memory words)
+    uint32_t *d_wtab64 = nullptr;
+    BPWarpTables wtab64 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    WarpLayoutBuilder *wlayout64 = nullptr;
+    int warp64_cost[3] = {0, 0, 0};
     int warp_cost[3] = {0, 0, 0};                                  // gather wavefronts per shot-iteration: natural, current, floor
     bool warp_ok = false;
     // CTA-per-shot kernel (bp_cta_kernel.cuh): labelling with NW * 3 check slots and NW * 7 variable slots
@@ -91,12 +96,12 @@ struct qldpc_code {
     DevBuf prior32, prior64, ctrl, gstate;
     DevBuf ws_redo;
     DevBuf ws_synd, ws_hard, ws_err, ws_conv, ws_iters, ws_llr, ws_fail, ws_valid, ws_u8a, ws_u8b, ws_flags,
-        ws_weight, ws_cnt, ws_llr_in, ws_rec;
+        ws_weight, ws_cnt, ws_llr_in, ws_rec, ws_inv;
     // Three-stage pipeline of the host-pointer decode call: a copy-in stream, a compute stream and a copy-out stream,
     // chained per chunk by events; chunk buffers rotate over NSLOT slots.  Kernels of different chunks never share the
     // GPU (each runs at full speed), the copies of the neighbouring chunks run under them.
     struct Slot {
-        DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail, redo;
+        DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail, redo, valid, inv;
         cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
         bool used = false;
     };

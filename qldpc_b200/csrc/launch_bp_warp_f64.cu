@@ -11,8 +11,8 @@ static cudaError_t launch_f64_inst(const qldpc_code *c, const BPParams &P, const
     }
     int occ = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
-    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW_WARPS - 1) / BPW_WARPS));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab);
+    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW64_WARPS - 1) / BPW64_WARPS));
+    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab64);      // (labelling for 16-lane conflict domains)
     return cudaGetLastError();
 }
 

@@ -76,7 +76,7 @@ template <typename K>
 static cudaError_t launch_osd_k(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
 {
     static const bool force_rowmajor = getenv("QLDPC_OSD_FORCE_ROWMAJOR") != nullptr;    // test hook
-    if (!P.rec_ordering && !force_rowmajor) {
+    if (!force_rowmajor) {
         const cudaError_t e = launch_osd_fast<K>(c, P, count_hint, st);
         if (e != cudaErrorNotSupported) return e;
     }
@@ -135,7 +135,6 @@ int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, c
     P.colmask = c->d_colmask;
     if (osd_use_block(c)) {
         if (c->n > 65534 || c->m > 32767) return qldpc_fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65534 columns or 32767 rows");
-        if (P.rec_ordering) return qldpc_fail(QLDPC_ERR_UNSUPPORTED, "OSD-w sweep (order > 0) is not available for check matrices with more than 160 rows");
         OSDBlockParams Q;
         Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank; Q.max_col_w = c->max_col_w;
         Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1;

@@ -303,4 +303,16 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckParams P)
     }
 }
 
+// Shots of a list (idx / count, identity when idx is null) whose OSD-0 solution missed the syndrome (valid == 0): compacted
+// into out_idx, count in out_count (zeroed by the caller).  The OSD-w sweep runs on that list (osdw_kernel.cuh).
+__global__ void compact_invalid_kernel(const int32_t *idx, const unsigned int *count_dev, long long count_host, const uint8_t *valid,
+                                       int32_t *out_idx, unsigned int *out_count)
+{
+    const long long count = count_dev ? (long long)*count_dev : count_host;
+    for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < count; it += (long long)gridDim.x * blockDim.x) {
+        const int32_t shot = idx ? idx[it] : (int32_t)it;
+        if (!valid[shot]) out_idx[atomicAdd(out_count, 1u)] = shot;
+    }
+}
+
 }  // namespace qldpc

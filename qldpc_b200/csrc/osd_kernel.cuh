@@ -44,11 +44,6 @@ struct OSDParams {
     const uint32_t *hard;         // [B][WN]  BP hard decision
     uint32_t *out;                // [B][WN]  solution (may alias hard)
     uint8_t *valid;               // [B] solution satisfies the syndrome (may be null)
-    // elimination record for the OSD-w sweep (all may be null), indexed by position in idx
-    int32_t *rec_ordering;        // [count][n]
-    int32_t *rec_pivcol;          // [count][m]  pivot column (permuted index) of position k, -1 if none
-    uint8_t *rec_sred;            // [count][m]  reduced syndrome by position
-    int32_t *rec_npiv;            // [count]
 };
 
 // cnt -= (a < b), as a subtract-with-borrow pair (2 instructions; the compiler's own lowering of `cnt += (a < b)` is
@@ -97,13 +92,24 @@ __host__ __device__ inline size_t osd_smem_per_warp(int n)
 
 // Row-major elimination of one shot by one warp, given its ordering `ord` (shared memory): residual syndrome,
 // gf2_elimination with the reference's pivot-row rule, solution, validity flag, optional elimination record.
-template <typename K, int WM>
-__device__ __forceinline__ void osd0_rowmajor_shot(const OSDParams &P, long long it, long long shot, const uint32_t *cmask,
+// (inputs / outputs of ONE shot; the record pointers may be null, or point into shared memory -- osdw_kernel.cuh)
+struct OSDShotIO {
+    const uint32_t *hard;         // [WN]
+    const uint32_t *synd;         // [WM]
+    uint32_t *out;                // [WN]
+    uint8_t *valid;               // [1] or null
+    int32_t *rec_ordering;        // [n] or null: with it rec_pivcol [m], rec_sred [m], rec_npiv [1]
+    int32_t *rec_pivcol;
+    uint8_t *rec_sred;
+    int32_t *rec_npiv;
+};
+
+template <int WM>
+__device__ __forceinline__ void osd0_rowmajor_shot(int m, int n, int WN, int rank_of_H, const OSDShotIO &io, const uint32_t *cmask,
                                                    const uint16_t *ord, uint32_t *solw, int lane)
 {
-    const int m = P.m, n = P.n, WN = P.WN;
     const unsigned FULL = 0xffffffffu;
-    const uint32_t *hard = P.hard + (size_t)shot * WN;
+    const uint32_t *hard = io.hard;
             // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------
             uint32_t rs[WM];
     #pragma unroll
@@ -115,7 +121,7 @@ __device__ __forceinline__ void osd0_rowmajor_shot(const OSDParams &P, long long
                 }
             }
     #pragma unroll
-            for (int w = 0; w < WM; ++w) rs[w] = __reduce_xor_sync(FULL, rs[w]) ^ P.synd[(size_t)shot * WM + w];
+            for (int w = 0; w < WM; ++w) rs[w] = __reduce_xor_sync(FULL, rs[w]) ^ io.synd[w];
 
             // ---- T = I, b = residual, positions = row index ------------------------------------
             uint32_t T[WM][WM];
@@ -133,7 +139,7 @@ __device__ __forceinline__ void osd0_rowmajor_shot(const OSDParams &P, long long
 
             // ---- gf2_elimination (OSD.py:31-72) -------------------------------------------------
             int row = 0;
-            const int rank = P.rank;
+            const int rank = rank_of_H;
             for (int j = 0; j < n && row < rank; ++j) {     // `row >= m` (:43); past `rank` pivots no column can pivot
                 const int col = ord[j];
                 uint32_t cm[WM];
@@ -204,23 +210,38 @@ __device__ __forceinline__ void osd0_rowmajor_shot(const OSDParams &P, long long
                 }
             }
             __syncwarp();
-            for (int w = lane; w < WN; w += 32) P.out[(size_t)shot * WN + w] = solw[w];
-            if (lane == 0 && P.valid) P.valid[shot] = any_bad ? 0 : 1;
+            for (int w = lane; w < WN; w += 32) io.out[w] = solw[w];
+            if (lane == 0 && io.valid) *io.valid = any_bad ? 0 : 1;
 
             // ---- elimination record for the OSD-w sweep -----------------------------------------
-            if (P.rec_ordering) {
-                for (int j = lane; j < n; j += 32) P.rec_ordering[(size_t)it * n + j] = ord[j];
-                for (int r = lane; r < m; r += 32) P.rec_pivcol[(size_t)it * m + r] = -1;
+            if (io.rec_ordering) {
+                for (int j = lane; j < n; j += 32) io.rec_ordering[j] = ord[j];
+                for (int r = lane; r < m; r += 32) io.rec_pivcol[r] = -1;
                 __syncwarp();
     #pragma unroll
                 for (int i = 0; i < WM; ++i) {
                     if (lane + 32 * i < m) {
-                        P.rec_pivcol[(size_t)it * m + pos[i]] = pcol[i];
-                        P.rec_sred[(size_t)it * m + pos[i]] = (uint8_t)bbit[i];
+                        io.rec_pivcol[pos[i]] = pcol[i];
+                        io.rec_sred[pos[i]] = (uint8_t)bbit[i];
                     }
                 }
-                if (lane == 0) P.rec_npiv[it] = row;
+                if (lane == 0) *io.rec_npiv = row;
             }
+}
+
+// the same on the batch arrays of OSDParams (no record)
+template <typename K, int WM>
+__device__ __forceinline__ void osd0_rowmajor_shot(const OSDParams &P, long long it, long long shot, const uint32_t *cmask,
+                                                   const uint16_t *ord, uint32_t *solw, int lane)
+{
+    OSDShotIO io;
+    io.hard = P.hard + (size_t)shot * P.WN;
+    io.synd = P.synd + (size_t)shot * P.WM;
+    io.out = P.out + (size_t)shot * P.WN;
+    io.valid = P.valid ? P.valid + shot : nullptr;
+    io.rec_ordering = nullptr; io.rec_pivcol = nullptr; io.rec_sred = nullptr; io.rec_npiv = nullptr;
+    (void)it;
+    osd0_rowmajor_shot<WM>(P.m, P.n, P.WN, P.rank, io, cmask, ord, solw, lane);
 }
 
 template <typename K, int WM>

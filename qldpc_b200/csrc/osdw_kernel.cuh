@@ -17,27 +17,37 @@
 //     strictly-smallest metric wins, OSD-0 being the first incumbent.
 // Candidates are independent, so the sequential rule collapses to a lexicographic minimum over
 // (invalid?, metric, enumeration index), evaluated in parallel: one candidate per thread.
+//
+// The kernel runs on a device-side list of shots (idx / count_dev: the shots whose OSD-0 solution missed the syndrome,
+// compacted by compact_invalid_kernel -- no host synchronisation) and RECOMPUTES the elimination record (ordering, pivot
+// columns by position, reduced syndrome) in shared memory: stable argsort of |llr| and the reference's row-major
+// Gauss-Jordan by warp 0, the very code of osd_kernel.cuh (template parameter WM, <= 5 words = 160 rows).  In the BP -> OSD
+// pipelines the BP hard decision is taken from the sign of the posterior LLR (hard = llr < 0), because the OSD-0 stage has
+// already overwritten it with its solution.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
 
+#include "osd_kernel.cuh"
+
 namespace qldpc {
 
 struct OSDWParams {
     int m, n, WM, WN;
+    int rank;                     // GF(2) rank of H
     const uint32_t *Hrows;        // [m][WN] packed rows of H, original column order
-    long long count;              // shots
-    const uint32_t *synd;         // [count][WM]
-    const double *llr;            // [count][n]
-    const uint32_t *hard;         // [count][WN]
-    uint32_t *sol;                // [count][WN]  in: OSD-0 solution, out: best solution
-    const uint8_t *valid;         // [count]  1: OSD-0 solution satisfies the syndrome -> untouched
-    const int32_t *rec_ordering;  // [count][n]
-    const int32_t *rec_pivcol;    // [count][m]
-    const uint8_t *rec_sred;      // [count][m]
-    const int32_t *rec_npiv;      // [count]
+    const uint32_t *colmask;      // [n][WM] packed columns of H
+    const int32_t *idx;           // [count] shot ids to process (null: identity)
+    const unsigned int *count_dev;// number of entries (device) ...
+    long long count;              // ... or given by the host when count_dev == null
+    const uint32_t *synd;         // [B][WM]
+    const void *llr;              // [B][n] double, or float when llr_f32
+    int llr_f32;
+    const uint32_t *hard;         // [B][WN] BP hard decision; null: llr < 0
+    uint32_t *sol;                // [B][WN] out: best solution
+    const uint8_t *valid;         // [B]  1: OSD-0 solution satisfies the syndrome -> untouched (null: sweep every shot)
     int order;
     long long max_combinations;   // 0: no limit
 };
@@ -84,6 +94,7 @@ __device__ double osdw_pairwise(const double *absllr, const uint32_t *sol, int S
     return __dadd_rn(osdw_pairwise(absllr, sol, S, lo, n2), osdw_pairwise(absllr, sol, S, lo + n2, cnt - n2));
 }
 
+template <int WME>
 __global__ void __launch_bounds__(OSDW_THREADS) osdw_kernel(const OSDWParams P)
 {
     const int m = P.m, n = P.n, WM = P.WM, WN = P.WN;
@@ -102,6 +113,13 @@ __global__ void __launch_bounds__(OSDW_THREADS) osdw_kernel(const OSDWParams P)
     uint32_t *sred = reinterpret_cast<uint32_t *>(testpos + OSDW_MAX_T);// [m] (one per word, simple)
     uint32_t *scratch_e = sred + m;                                    // [WN][S] per-thread permuted candidate
     uint32_t *scratch_s = scratch_e + (size_t)WN * S;                  // [WN][S] per-thread solution, original order
+    // work area of the in-kernel elimination (warp 0)
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>((reinterpret_cast<uintptr_t>(scratch_s + (size_t)WN * S) + 7) & ~(uintptr_t)7);  // [n]
+    uint32_t *cmask = reinterpret_cast<uint32_t *>(keys + n);          // [n][WM]
+    uint32_t *solw = cmask + (size_t)n * WM;                           // [WN]
+    uint16_t *ord16 = reinterpret_cast<uint16_t *>(solw + WN);         // [n]
+    uint8_t *sred8 = reinterpret_cast<uint8_t *>(ord16 + n);           // [m]
+    for (int i = tid; i < n * WM; i += S) cmask[i] = P.colmask[i];
     __shared__ OSDWKey s_key[OSDW_THREADS];
     __shared__ int s_npiv, s_T;
     __shared__ long long s_total;
@@ -120,20 +138,50 @@ __global__ void __launch_bounds__(OSDW_THREADS) osdw_kernel(const OSDWParams P)
     __syncthreads();
     auto C = [&](int a, int b) -> long long { return (b < 0 || b > a) ? 0 : binom[a * (OSDW_MAX_ORDER + 1) + b]; };
 
-    for (long long shot = blockIdx.x; shot < P.count; shot += gridDim.x) {
-        if (P.valid[shot]) continue;                                   // OSD_enhanced.py:58-60
+    const long long count = P.count_dev ? (long long)*P.count_dev : P.count;
+    for (long long it = blockIdx.x; it < count; it += gridDim.x) {
+        const long long shot = P.idx ? (long long)P.idx[it] : it;
+        if (P.valid && P.valid[shot]) continue;                        // OSD_enhanced.py:58-60
         __syncthreads();
-        // ---- load the elimination record ---------------------------------------------------
-        for (int j = tid; j < n; j += S) {
-            ord[j] = P.rec_ordering[(size_t)shot * n + j];
-            absllr[j] = fabs(P.llr[(size_t)shot * n + j]);
+        auto llr_at = [&](int j) -> double {
+            return P.llr_f32 ? (double)reinterpret_cast<const float *>(P.llr)[(size_t)shot * n + j]
+                             : reinterpret_cast<const double *>(P.llr)[(size_t)shot * n + j];
+        };
+        for (int j = tid; j < n; j += S) absllr[j] = fabs(llr_at(j));
+        for (int w = tid; w < WN; w += S) {
+            uint32_t hw = 0;
+            if (P.hard) hw = P.hard[(size_t)shot * WN + w];
+            else
+                for (int b = 0; b < 32 && 32 * w + b < n; ++b) hw |= (uint32_t)(llr_at(32 * w + b) < 0.0) << b;   // hard = values < 0
+            hardp[w] = hw;
+            eperm[w] = 0;
         }
-        for (int r = tid; r < m; r += S) {
-            pivcol[r] = P.rec_pivcol[(size_t)shot * m + r];
-            sred[r] = P.rec_sred[(size_t)shot * m + r];
+        {
+            // ---- elimination record: stable argsort of |llr| (OSD_enhanced.py:34-35), gf2_elimination (:180-224) by warp 0 ----
+            for (int j = tid; j < n; j += S) keys[j] = KeyBits<double>::get(llr_at(j));
+            __syncthreads();
+            if (tid < 32) {
+                for (int i = tid; i < n; i += 32) {
+                    const unsigned long long ki = keys[i];
+                    int cnt = 0;
+                    for (int j = 0; j < n; ++j) cnt += (keys[j] < ki) || (keys[j] == ki && j < i);
+                    ord16[cnt] = (uint16_t)i;
+                }
+                __syncwarp();
+                OSDShotIO io;
+                io.hard = hardp;
+                io.synd = P.synd + (size_t)shot * WM;
+                io.out = solw;
+                io.valid = nullptr;
+                io.rec_ordering = ord;
+                io.rec_pivcol = pivcol;
+                io.rec_sred = sred8;
+                io.rec_npiv = &s_npiv;
+                osd0_rowmajor_shot<WME>(m, n, WN, P.rank, io, cmask, ord16, solw, tid);
+            }
+            __syncthreads();
+            for (int r = tid; r < m; r += S) sred[r] = sred8[r];
         }
-        for (int w = tid; w < WN; w += S) { hardp[w] = P.hard[(size_t)shot * WN + w]; eperm[w] = 0; }
-        if (tid == 0) s_npiv = P.rec_npiv[shot];
         __syncthreads();
         const int npiv = s_npiv;
         // permuted unreduced rows: Hp[r] bit j = H[r][ord[j]]
@@ -259,18 +307,33 @@ inline size_t osdw_smem_bytes(int m, int n, int WM, int WN)
 {
     size_t o = 8 * (size_t)n + 8 * (size_t)(OSDW_MAX_T + 1) * (OSDW_MAX_ORDER + 1);
     o += 4 * ((size_t)m * WN + 2 * (size_t)WN + WM + n + m + OSDW_MAX_T + m + 2 * (size_t)WN * OSDW_THREADS);
+    o += 8 + 8 * (size_t)n + 4 * (size_t)n * WM + 4 * (size_t)WN + 2 * (size_t)n + (size_t)m;      // in-kernel elimination
     return o + 64;
+}
+
+template <int WME>
+inline cudaError_t launch_osdw_inst(const OSDWParams &P, int num_sms, cudaStream_t st)
+{
+    const size_t smem = osdw_smem_bytes(P.m, P.n, P.WM, P.WN);
+    cudaError_t e = cudaFuncSetAttribute(osdw_kernel<WME>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    long long grid = (long long)num_sms * 2;
+    if (!P.count_dev) grid = std::min<long long>(grid, P.count);
+    osdw_kernel<WME><<<(int)std::max<long long>(1, grid), OSDW_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
 }
 
 inline cudaError_t launch_osdw(const OSDWParams &P, int num_sms, cudaStream_t st)
 {
     if (P.order > OSDW_MAX_ORDER) return cudaErrorInvalidValue;
-    const size_t smem = osdw_smem_bytes(P.m, P.n, P.WM, P.WN);
-    cudaError_t e = cudaFuncSetAttribute(osdw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    const int grid = (int)std::max<long long>(1, std::min<long long>(P.count, (long long)num_sms * 2));
-    osdw_kernel<<<grid, OSDW_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
+    switch (P.WM) {
+    case 1: return launch_osdw_inst<1>(P, num_sms, st);
+    case 2: return launch_osdw_inst<2>(P, num_sms, st);
+    case 3: return launch_osdw_inst<3>(P, num_sms, st);
+    case 4: return launch_osdw_inst<4>(P, num_sms, st);
+    case 5: return launch_osdw_inst<5>(P, num_sms, st);
+    default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace qldpc

@@ -1,6 +1,6 @@
 // Host-only check of the lane labelling of the warp- / CTA-per-shot BP kernels (qldpc_b200/csrc/bp_warp_layout.h):
 // builds the labelling for a check matrix read from a text file and verifies the tables the kernels consume.
-//   layout_check <graph.txt> <RW> <check_slots> <var_slots>      graph.txt: m n / row_ptr / col_idx / var_ptr / var_edge / edge_check
+//   layout_check <graph.txt> <RW> <check_slots> <var_slots> [lanes = 32 | 16]      graph.txt: m n / row_ptr / col_idx / var_ptr / var_edge / edge_check
 #include "../../qldpc_b200/csrc/bp_warp_layout.h"
 
 #include <cstdio>
@@ -27,9 +27,9 @@ int main(int argc, char **argv)
     for (auto &x : vp) if (std::fscanf(f, "%d", &x) != 1) return 2;
     for (auto &x : ve) if (std::fscanf(f, "%d", &x) != 1) return 2;
     for (auto &x : ec) if (std::fscanf(f, "%d", &x) != 1) return 2;
-    const int RW = std::atoi(argv[2]), cs = std::atoi(argv[3]), vs = std::atoi(argv[4]);
+    const int RW = std::atoi(argv[2]), cs = std::atoi(argv[3]), vs = std::atoi(argv[4]), W = argc > 5 ? std::atoi(argv[5]) : 32;
 
-    qldpc::WarpLayoutBuilder b(m, n, rp.data(), ci.data(), vp.data(), ve.data(), ve.data(), ec.data(), RW, cs, vs);
+    qldpc::WarpLayoutBuilder b(m, n, rp.data(), ci.data(), vp.data(), ve.data(), ve.data(), ec.data(), RW, cs, vs, W);
     const bool ok = b.construct();
     const qldpc::WarpLayout L = b.tables();
     std::printf("m=%d n=%d RW=%d slots %d/%d conflict_free=%d natural=%d cost=%d floor=%d\n", m, n, RW, L.CPL, L.VPL, (int)ok, L.cost_natural,
@@ -60,7 +60,10 @@ int main(int argc, char **argv)
                 const size_t at = (size_t)(i * RW + k) * 32 + l;
                 const uint32_t vword = L.vidx[at] / 4, sword = L.sidx[at] / 4;
                 REQUIRE(L.vidx[at] % 4 == 0 && L.sidx[at] % 4 == 0);
-                REQUIRE(++bank_rd[vword & 31] == 1 && ++bank_wr[sword & 31] == 1);      // bank-conflict free
+                // bank-conflict free: 32 lanes in 32 different columns (32-bit words), or -- 64-bit words, lanes = 16 -- the 16
+                // lanes of each half-warp in 16 different bank pairs
+                if (W == 32) REQUIRE(++bank_rd[vword & 31] == 1 && ++bank_wr[sword & 31] == 1);
+                else REQUIRE(++bank_rd[(l / 16) * 16 + (vword & 15)] == 1 && ++bank_wr[(l / 16) * 16 + (sword & 15)] == 1);
                 const uint32_t c = L.cinfo[i * 32 + l];
                 if (vword >= (uint32_t)VPL * 32) {                                       // padding slot
                     REQUIRE(vword < (uint32_t)(VPL + 1) * 32);

@@ -50,6 +50,16 @@ def test_lane_labelling_is_conflict_free_and_consistent(checker, tmp_path, stem,
     assert "LAYOUT-OK" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("stem", ["[[72, 12, 6]]", "[[90, 8, 10]]", "[[108, 8, 10]]", "[[144, 12, 12]]", "[[288, 12, 18]]"])
+def test_half_warp_labelling_for_64bit_words(checker, tmp_path, stem):
+    """float64 kernel: 64-bit shared-memory accesses are served per half-warp; the labelling built with 16-lane conflict
+    domains puts the 16 lanes of every half in 16 different bank pairs."""
+    g = str(tmp_path / "g.txt")
+    _dump(load_code_file(stem)[0], g)
+    r = subprocess.run([checker, g, "6", "0", "0", "16"], capture_output=True, text=True, timeout=300)
+    assert "LAYOUT-OK" in r.stdout, r.stdout + r.stderr
+
+
 def _random_regular(m, n, cw, rw, seed):
     """Random bipartite graph with column weight cw and row weight rw (configuration model, no double edges)."""
     rng = np.random.default_rng(seed)

@@ -134,14 +134,21 @@ int qldpc_bp_messages_host(qldpc_code *code, const qldpc_bp_config *cfg, const d
 /* Batched OSD.  Stands in for performOSD (decoding/OSD.py:3) when order == 0 and
  * performOSD_enhanced (decoding/OSD_enhanced.py:5) otherwise; max_combinations <= 0 means None.
  *   synd [B][m] uint8, llr [B][n] float64, hard [B][n] uint8/int8 -> out [B][n] uint8.
- * Column order: stable ascending |llr| (ties -> lower index). */
+ * Column order: stable ascending |llr| (ties -> lower index).
+ * order > 0: the combination sweep (OSD_enhanced.py:66-131) runs on the shots whose OSD-0 solution misses the syndrome,
+ * selected on the device; order <= 16.  Check matrices with more than 160 rows: order > 0 is accepted when H has full row
+ * rank (every syndrome is then consistent and the sweep is dead code, OSD_enhanced.py:58-60) and refused with
+ * QLDPC_ERR_UNSUPPORTED otherwise. */
 int qldpc_osd_decode_host(qldpc_code *code, int64_t B, const uint8_t *synd, const double *llr,
                           const uint8_t *hard, int32_t order, int64_t max_combinations, uint8_t *out);
 
 /* Fused BP -> OSD on the BP failures: the per-shot body of the reference's Monte-Carlo loops
  * (paperResults.py:71-77, paperResults_GPU.py:108-123, rework/main.py:80-88).
- * osd_order < 0: BP only.   synd [B][m] uint8 -> corr [B][n] uint8, conv [B] uint8 (BP flag),
- * iters [B] int32 (may be NULL).  This is the call bench.py times end to end. */
+ * osd_order < 0: BP only; 0: performOSD; > 0: performOSD_enhanced(order = osd_order), i.e. OSD-0 plus the combination
+ * sweep on the shots whose OSD-0 solution misses the syndrome (possible only for syndromes outside the column space of H,
+ * e.g. with measurement errors); same limits as qldpc_osd_decode_host.
+ * synd [B][m] uint8 -> corr [B][n] uint8, conv [B] uint8 (BP flag), iters [B] int32 (may be NULL).
+ * This is the call bench.py times end to end. */
 int qldpc_bposd_decode_host(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, int64_t B,
                             const uint8_t *synd, int32_t osd_order, uint8_t *corr, uint8_t *conv,
                             int32_t *iters);
@@ -168,6 +175,11 @@ int qldpc_syndrome_host(qldpc_code *code, int64_t B, const uint8_t *err, uint8_t
  * independent draws (paperResults.py:61-63). */
 int qldpc_sample_host(qldpc_code *code, double p, uint64_t seed, uint64_t first_shot, int32_t draws,
                       int64_t B, uint8_t *err, uint8_t *synd);
+/* the same with measurement errors: every syndrome bit is then flipped with probability q_meas, the
+ * "simple phenomenological error model" of paperResults.py:66-68 (Philox stream "MEAS" of the same
+ * (seed, shot id) counter space).  Such syndromes need not lie in the column space of H. */
+int qldpc_sample_noisy_host(qldpc_code *code, double p, double q_meas, uint64_t seed, uint64_t first_shot,
+                            int32_t draws, int64_t B, uint8_t *err, uint8_t *synd);
 
 /* Whole Monte-Carlo point on the device: sample -> BP -> OSD on failures -> checks -> counters.
  * Shots [first_shot, first_shot + nshots) of the stream `seed`; counters are ADDED into
@@ -176,6 +188,10 @@ int qldpc_sample_host(qldpc_code *code, double p, uint64_t seed, uint64_t first_
 int qldpc_mc_sweep(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, double p,
                    uint64_t seed, uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order,
                    int32_t distance, uint64_t *counters);
+/* the same with measurement errors of rate q_meas on the syndrome (see qldpc_sample_noisy_host) */
+int qldpc_mc_sweep_noisy(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior, double p,
+                         double q_meas, uint64_t seed, uint64_t first_shot, int64_t nshots, int32_t draws,
+                         int32_t osd_order, int32_t distance, uint64_t *counters);
 
 /* Posterior-LLR histograms without returning B*n floats (BP_per_Iteration.py:56,60 and rework/Alvarado.py:159-162 collect
  * every posterior LLR on the host): device-sampled shots as in qldpc_mc_sweep, BP only, hist [3][nbins] uint64 ADDED into:
@@ -211,10 +227,14 @@ int qldpc_check_dev(qldpc_code *code, int64_t B, const uint32_t *err, const uint
 
 int qldpc_syndrome_dev(qldpc_code *code, int64_t B, const uint32_t *err, uint32_t *synd, void *stream);
 
+/* XORs measurement errors of rate q into packed syndromes synd [B][WM] (paperResults.py:66-68) */
+int qldpc_measurement_noise_dev(qldpc_code *code, double q, uint64_t seed, uint64_t first_shot, int64_t B,
+                                uint32_t *synd, void *stream);
+
 int qldpc_sample_dev(qldpc_code *code, double p, uint64_t seed, uint64_t first_shot, int32_t draws,
                      int64_t B, uint32_t *err, uint32_t *synd, void *stream);
 
-/* fused BP -> OSD-0 (osd_order >= 0) on packed device syndromes; corr [B][words_n] */
+/* fused BP -> OSD (osd_order as in qldpc_bposd_decode_host) on packed device syndromes; corr [B][words_n] */
 int qldpc_bposd_decode_dev(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
                            const uint32_t *synd, int32_t osd_order, uint32_t *corr, uint8_t *conv,
                            int32_t *iters, uint64_t *iter_total, void *stream);

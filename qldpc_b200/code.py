@@ -213,26 +213,27 @@ class Code:
             _lib.check(_lib.lib().qldpc_syndrome_host(self._h, err.shape[0], _vp(err), _vp(syn)), "qldpc_syndrome_host")
         return syn.view(np.int8)
 
-    def sample(self, p, B, seed=0, first_shot=0, draws=1):
-        """Device Philox sampler -> (errors int8 (B,n), syndromes int8 (B,m))."""
+    def sample(self, p, B, seed=0, first_shot=0, draws=1, meas_p=0.0):
+        """Device Philox sampler -> (errors int8 (B,n), syndromes int8 (B,m)).  meas_p > 0: every syndrome bit is flipped
+        with that probability (the phenomenological model the reference keeps commented out, paperResults.py:66-68)."""
         err = np.zeros((B, self.n), np.uint8)
         syn = np.zeros((B, self.m), np.uint8)
         if B:
-            _lib.check(_lib.lib().qldpc_sample_host(self._h, float(p), int(seed), int(first_shot), int(draws), B, _vp(err),
-                                                   _vp(syn)), "qldpc_sample_host")
+            _lib.check(_lib.lib().qldpc_sample_noisy_host(self._h, float(p), float(meas_p), int(seed), int(first_shot), int(draws), B,
+                                                         _vp(err), _vp(syn)), "qldpc_sample_noisy_host")
         return err.view(np.int8), syn.view(np.int8)
 
     def mc_sweep(self, p, nshots, prior=None, seed=0, first_shot=0, draws=1, variant="min_sum", max_iter=50, alpha=1.0,
-                 damping=1.0, clip=20.0, precision=32, osd_order=0, distance=None, staged=False):
-        """One Monte-Carlo point entirely on the device.  -> dict of counters."""
+                 damping=1.0, clip=20.0, precision=32, osd_order=0, distance=None, staged=False, meas_p=0.0):
+        """One Monte-Carlo point entirely on the device.  -> dict of counters.  meas_p: measurement-error rate (see sample)."""
         cfg = self.config(variant, max_iter, alpha, damping, clip, precision, staged)
         pe = p if draws == 1 else 2 * p * (1 - p)
         pr = self._prior(np.log((1 - pe) / pe) if prior is None else prior)
         counters = np.zeros(_lib.NUM_COUNTERS, np.uint64)
         d = self.distance if distance is None else distance
-        _lib.check(_lib.lib().qldpc_mc_sweep(self._h, ctypes.byref(cfg), _vp(pr), float(p), int(seed), int(first_shot),
-                                             int(nshots), int(draws), int(osd_order), int(d or 0), _vp(counters)),
-                   "qldpc_mc_sweep")
+        _lib.check(_lib.lib().qldpc_mc_sweep_noisy(self._h, ctypes.byref(cfg), _vp(pr), float(p), float(meas_p), int(seed),
+                                                   int(first_shot), int(nshots), int(draws), int(osd_order), int(d or 0),
+                                                   _vp(counters)), "qldpc_mc_sweep_noisy")
         return dict(zip(_lib.COUNTER_NAMES, (int(x) for x in counters)))
 
 

@@ -634,6 +634,18 @@ extern "C" int qldpc_sample_dev(qldpc_code *c, double p, uint64_t seed, uint64_t
     return QLDPC_OK;
 }
 
+extern "C" int qldpc_measurement_noise_dev(qldpc_code *c, double q, uint64_t seed, uint64_t first_shot, int64_t B, uint32_t *synd,
+                                           void *stream)
+{
+    if (!c || !synd) return fail(QLDPC_ERR_ARG, "qldpc_measurement_noise_dev: null argument");
+    if (!(q >= 0.0 && q < 1.0)) return fail(QLDPC_ERR_ARG, "qldpc_measurement_noise_dev: need 0 <= q < 1");
+    if (B <= 0 || q == 0.0) return QLDPC_OK;
+    const uint32_t thr = (uint32_t)std::min<double>(4294967295.0, q * 4294967296.0);
+    meas_noise_kernel<<<grid_for(B * c->WM, 256, c->num_sms), 256, 0, (cudaStream_t)stream>>>(synd, B, c->m, c->WM, thr, seed, first_shot);
+    CK(cudaGetLastError());
+    return QLDPC_OK;
+}
+
 extern "C" int qldpc_check_dev(qldpc_code *c, int64_t B, const uint32_t *err, const uint32_t *corr, const uint32_t *synd,
                                const uint8_t *conv, const int32_t *iters, int32_t distance, uint8_t *flags,
                                int32_t *weight, uint64_t *counters_dev, void *stream)
@@ -1113,6 +1125,12 @@ extern "C" int qldpc_syndrome_host(qldpc_code *c, int64_t B, const uint8_t *err,
 extern "C" int qldpc_sample_host(qldpc_code *c, double p, uint64_t seed, uint64_t first_shot, int32_t draws, int64_t B,
                                  uint8_t *err, uint8_t *synd)
 {
+    return qldpc_sample_noisy_host(c, p, 0.0, seed, first_shot, draws, B, err, synd);
+}
+
+extern "C" int qldpc_sample_noisy_host(qldpc_code *c, double p, double q_meas, uint64_t seed, uint64_t first_shot, int32_t draws,
+                                       int64_t B, uint8_t *err, uint8_t *synd)
+{
     if (!c || !err || !synd) return fail(QLDPC_ERR_ARG, "qldpc_sample_host: null argument");
     cudaStream_t st = 0;
     const long long chunk = 1ll << 20;
@@ -1124,6 +1142,7 @@ extern "C" int qldpc_sample_host(qldpc_code *c, double p, uint64_t seed, uint64_
         if (int rc = qldpc_sample_dev(c, p, seed, first_shot + (uint64_t)o, draws, b, c->ws_err.as<uint32_t>(),
                                       c->ws_synd.as<uint32_t>(), st))
             return rc;
+        if (int rc = qldpc_measurement_noise_dev(c, q_meas, seed, first_shot + (uint64_t)o, b, c->ws_synd.as<uint32_t>(), st)) return rc;
         if (int rc = qldpc_unpack_bits_dev(c->ws_err.as<uint32_t>(), c->ws_u8a.as<uint8_t>(), b, c->n, st)) return rc;
         CK(cudaMemcpyAsync(err + (size_t)o * c->n, c->ws_u8a.p, (size_t)b * c->n, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
@@ -1183,6 +1202,13 @@ extern "C" int qldpc_mc_sweep(qldpc_code *c, const qldpc_bp_config *cfg, const d
                               uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order, int32_t distance,
                               uint64_t *counters)
 {
+    return qldpc_mc_sweep_noisy(c, cfg, prior, p, 0.0, seed, first_shot, nshots, draws, osd_order, distance, counters);
+}
+
+extern "C" int qldpc_mc_sweep_noisy(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, double p, double q_meas,
+                                    uint64_t seed, uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order,
+                                    int32_t distance, uint64_t *counters)
+{
     if (!c || !counters) return fail(QLDPC_ERR_ARG, "qldpc_mc_sweep: null argument");
     if (int rc = check_cfg(cfg)) return rc;
     cudaStream_t st = 0;
@@ -1199,6 +1225,7 @@ extern "C" int qldpc_mc_sweep(qldpc_code *c, const qldpc_bp_config *cfg, const d
         if (int rc = qldpc_sample_dev(c, p, seed, first_shot + (uint64_t)o, draws, b, c->ws_err.as<uint32_t>(),
                                       c->ws_synd.as<uint32_t>(), st))
             return rc;
+        if (int rc = qldpc_measurement_noise_dev(c, q_meas, seed, first_shot + (uint64_t)o, b, c->ws_synd.as<uint32_t>(), st)) return rc;
         if (int rc = qldpc_bposd_decode_dev(c, cfg, prior, b, c->ws_synd.as<uint32_t>(), osd_order, c->ws_hard.as<uint32_t>(),
                                             c->ws_conv.as<uint8_t>(), c->ws_iters.as<int32_t>(), nullptr, st))
             return rc;

@@ -135,6 +135,32 @@ __global__ void sample_kernel(const SampleParams P)
     }
 }
 
+// ---- measurement errors: every syndrome bit flipped with probability q, the "simple phenomenological error model" the
+// reference keeps one uncomment away (paperResults.py:66-68).  One thread per (shot, 32-check word); Philox stream 0x4d454153
+// ("MEAS") of the same (seed, global shot id) counter space as sample_kernel, so results are shard-invariant too.
+__global__ void meas_noise_kernel(uint32_t *synd, long long B, int m, int WM, uint32_t threshold, unsigned long long seed,
+                                  unsigned long long first_shot)
+{
+    const long long total = B * WM;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long s = t / WM;
+        const int w = (int)(t - s * WM);
+        const unsigned long long sid = first_shot + (unsigned long long)s;
+        uint32_t bits = 0;
+        for (int q = 0; q < 8; ++q) {
+            const uint4 r = philox4x32_10(make_uint4((uint32_t)sid, (uint32_t)(sid >> 32), (uint32_t)(w * 8 + q), 0x4d454153u), key);
+            bits |= (uint32_t)(r.x < threshold) << (4 * q);
+            bits |= (uint32_t)(r.y < threshold) << (4 * q + 1);
+            bits |= (uint32_t)(r.z < threshold) << (4 * q + 2);
+            bits |= (uint32_t)(r.w < threshold) << (4 * q + 3);
+        }
+        const int hi = min(32, m - 32 * w);
+        if (hi < 32) bits &= (1u << hi) - 1u;
+        synd[t] ^= bits;
+    }
+}
+
 // ---- syndromes of given errors: synd = err * H^T mod 2 (paperResults.py:65, beliefPropagationGPU.py:198) -------
 // One thread per (shot, 32-check word): parity of the packed error bits over the columns of each row (CSR of H).
 __global__ void syndrome_kernel(const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ col_idx, int m, int WM, int WN,

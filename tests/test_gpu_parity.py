@@ -799,3 +799,99 @@ def test_error_behaviour():
     # an all-zero prior (p = 0.5) and an all-ones syndrome are legal inputs
     hard, conv, llr, it = code.bp_decode_batch(np.ones((3, 36), np.uint8), np.zeros(72), "min_sum", 5, precision=64)
     assert hard.shape == (3, 72) and np.isfinite(llr).all()
+
+
+# ----------------------------------------------------------------------------------------------
+# OSD-w in the fused BP -> OSD paths (performOSD_enhanced with order > 0 on syndromes OUTSIDE the column space of H:
+# measurement errors, the model the reference keeps one uncomment away, paperResults.py:66-68)
+# ----------------------------------------------------------------------------------------------
+def _noisy_case(stem, B, p, q, seed):
+    H, d = load_code_file(stem)
+    n = H.shape[1]
+    rng = np.random.default_rng(seed)
+    err = (rng.random((B, n)) < p).astype(np.uint8)
+    synd = _synd(H, err) ^ (rng.random((B, H.shape[0])) < q).astype(np.uint8)      # syndrome + measurementError (mod 2)
+    return H, d, err, synd
+
+
+@pytest.mark.parametrize("stem,order,B", [("[[72, 12, 6]]", 2, 600), ("[[144, 12, 12]]", 3, 300), ("[[90, 8, 10]]", 7, 40),
+                                          ("[[288, 12, 18]]", 1, 120)])
+def test_fused_bposd_runs_the_osdw_sweep_on_inconsistent_syndromes(stem, order, B):
+    H, d, err, synd = _noisy_case(stem, B, 0.04, 0.03, 11)
+    n = H.shape[1]
+    prior = _prior(0.04, n)
+    g = O.Graph(H, *O.auto_schedule(H, O.MIN_SUM))
+    ref = O.decode_batch(g, synd, prior, O.MIN_SUM, 30, 0.8, 0.7, 25.0, osd_order=order)
+    ref0 = O.decode_batch(g, synd, prior, O.MIN_SUM, 30, 0.8, 0.7, 25.0, osd_order=0)
+    if stem == "[[72, 12, 6]]":      # here the sweep also changes the answer on some shots (the larger codes keep OSD-0: it
+        assert (ref["corr"] != ref0["corr"]).any(1).sum() >= 3               # stays the best of the all-invalid candidates)
+    code = _code(H, "min_sum", d["Lx"], int(d["distance"]))
+    corr, conv, iters = code.bposd_decode_batch(synd, prior, "min_sum", 30, 0.8, 0.7, 25.0, precision=64, osd_order=order)
+    assert np.array_equal(conv, ref["converged"]) and np.array_equal(iters, ref["iters"])
+    assert np.array_equal(corr, ref["corr"])
+    corr0, _, _ = code.bposd_decode_batch(synd, prior, "min_sum", 30, 0.8, 0.7, 25.0, precision=64, osd_order=0)
+    assert np.array_equal(corr0, ref0["corr"])
+    # float32 pipeline: the fused path must equal its own two halves (BP with LLR output, then the batched OSD call on them)
+    hard, conv32, llr32, _ = code.bp_decode_batch(synd, prior, "min_sum", 30, 0.8, 0.7, 25.0, precision=32)
+    f = np.nonzero(~conv32)[0]
+    want = hard.astype(np.uint8)
+    want[f] = code.osd_decode_batch(synd[f], llr32[f], hard[f], order=order).astype(np.uint8)
+    corr32, c32, _ = code.bposd_decode_batch(synd, prior, "min_sum", 30, 0.8, 0.7, 25.0, precision=32, osd_order=order)
+    assert np.array_equal(c32, conv32) and np.array_equal(corr32, want)
+
+
+def test_mc_sweep_with_measurement_errors_equals_oracle_counters():
+    """qldpc_mc_sweep_noisy == sample (device Philox, measurement flips included) -> oracle BP + OSD-w -> oracle checks."""
+    H, d = load_code_file("[[72, 12, 6]]")
+    n, dist = H.shape[1], int(d["distance"])
+    code = _code(H, "min_sum", d["Lx"], dist)
+    B, p, q, order = 3000, 0.03, 0.02, 2
+    err, synd = code.sample(p, B, seed=5, meas_p=q)
+    clean = _synd(H, err.view(np.uint8))
+    flips = synd.view(np.uint8) ^ clean
+    assert abs(flips.mean() - q) < 5 * np.sqrt(q / flips.size)              # measurement errors at the requested rate
+    err0, synd0 = code.sample(p, B, seed=5)                                  # same data errors without them
+    assert np.array_equal(err0, err) and np.array_equal(synd0.view(np.uint8), clean)
+    prior = _prior(p, n)
+    g = O.Graph(H, *O.auto_schedule(H, O.MIN_SUM))
+    ref = O.decode_batch(g, synd, prior, O.MIN_SUM, 40, 0.8, 0.7, 25.0, osd_order=order)
+    lg, va, wt = O.check_batch(g, d["Lx"], err, ref["corr"], synd)
+    c = code.mc_sweep(p, B, seed=5, variant="min_sum", max_iter=40, alpha=0.8, damping=0.7, clip=25.0, precision=64, osd_order=order,
+                      meas_p=q)
+    assert c["shots"] == B and c["bp_failed"] == int((~ref["converged"]).sum())
+    assert c["logical"] == int(lg.sum()) and c["invalid"] == int((~va).sum()) and c["residual_weight"] == int(wt.sum())
+    assert c["invalid"] > 0                                                  # inconsistent syndromes cannot be satisfied
+    # shard invariance with measurement errors
+    a = code.mc_sweep(p, 1000, seed=5, first_shot=0, variant="min_sum", max_iter=40, alpha=0.8, damping=0.7, clip=25.0, precision=64,
+                      osd_order=order, meas_p=q)
+    b = code.mc_sweep(p, 2000, seed=5, first_shot=1000, variant="min_sum", max_iter=40, alpha=0.8, damping=0.7, clip=25.0, precision=64,
+                      osd_order=order, meas_p=q)
+    assert all(a[k] + b[k] == c[k] for k in c)
+
+
+def test_osdw_on_large_check_matrices_is_exact_or_refused():
+    """More than 160 rows: no sweep kernel.  Full row rank (the space-time matrix): every syndrome is consistent, order 7 ==
+    order 0 exactly as in the reference; rank-deficient: QLDPC_ERR_UNSUPPORTED, never a silent OSD-0."""
+    from qldpc_b200 import Code, graph
+    from qldpc_b200._lib import QldpcError
+    from qldpc_b200.spaceTime import spaceTimeMatrix
+    H144, _ = load_code_file("[[144, 12, 12]]")
+    Hst = spaceTimeMatrix(H144, 3).astype(np.int64)                         # 216 x 648, has an identity block
+    rng = np.random.default_rng(2)
+    B = 24
+    synd = (rng.random((B, Hst.shape[0])) < 0.3).astype(np.uint8)            # arbitrary syndromes: all consistent
+    llr = rng.normal(size=(B, Hst.shape[1]))
+    hard = (llr < 0).astype(np.uint8)
+    cst = Code(Hst, None, (graph.SEQ, graph.SEQ))
+    o0 = cst.osd_decode_batch(synd, llr, hard, order=0)
+    assert np.array_equal(cst.osd_decode_batch(synd, llr, hard, order=7), o0)
+    assert np.array_equal(_synd(Hst, o0.astype(np.uint8)), synd)
+    Hbig = np.kron(np.eye(3, dtype=np.int64), np.asarray(H144))              # 216 x 432, rank 198 < 216
+    cbig = Code(Hbig, None, (graph.SEQ, graph.SEQ))
+    sb = (rng.random((4, 216)) < 0.3).astype(np.uint8)
+    lb = rng.normal(size=(4, 432))
+    assert cbig.osd_decode_batch(sb, lb, (lb < 0).astype(np.uint8), order=0).shape == (4, 432)
+    with pytest.raises(QldpcError, match="rank-deficient"):
+        cbig.osd_decode_batch(sb, lb, (lb < 0).astype(np.uint8), order=2)
+    with pytest.raises(QldpcError, match="rank-deficient"):
+        cbig.bposd_decode_batch(sb, [2.0] * 432, "min_sum", 5, precision=64, osd_order=2)

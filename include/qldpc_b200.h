@@ -221,6 +221,14 @@ int qldpc_osd_decode_dev(qldpc_code *code, const int32_t *idx, const uint32_t *c
                          const uint32_t *synd, const void *llr, int32_t llr_f64, const uint32_t *hard,
                          uint32_t *out, uint8_t *valid, void *stream);
 
+/* The OSD-w sweep of performOSD_enhanced (OSD_enhanced.py:66-131) behind a qldpc_osd_decode_dev call that wrote `valid`:
+ * the listed shots (as there; with a device-side count, count_host must bound it) whose OSD-0 solution misses the syndrome
+ * are compacted on the device and swept; out is updated in place.  hard == NULL: the BP hard decision is llr < 0 (use it
+ * when out aliased hard in the OSD-0 call).  order <= 0: no-op.  Limits: see qldpc_osd_decode_host. */
+int qldpc_osdw_decode_dev(qldpc_code *code, const int32_t *idx, const uint32_t *count_dev, int64_t count_host,
+                          const uint32_t *synd, const void *llr, int32_t llr_f64, const uint32_t *hard,
+                          uint32_t *out, const uint8_t *valid, int32_t order, int64_t max_combinations, void *stream);
+
 int qldpc_check_dev(qldpc_code *code, int64_t B, const uint32_t *err, const uint32_t *corr,
                     const uint32_t *synd, const uint8_t *conv, const int32_t *iters, int32_t distance,
                     uint8_t *flags, int32_t *weight, uint64_t *counters_dev, void *stream);

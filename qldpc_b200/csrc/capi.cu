@@ -723,6 +723,18 @@ static int osdw_stage(qldpc_code *c, const int32_t *idx, const uint32_t *count_d
     return QLDPC_OK;
 }
 
+extern "C" int qldpc_osdw_decode_dev(qldpc_code *c, const int32_t *idx, const uint32_t *count_dev, int64_t count_host,
+                                     const uint32_t *synd, const void *llr, int32_t llr_f64, const uint32_t *hard, uint32_t *out,
+                                     const uint8_t *valid, int32_t order, int64_t max_combinations, void *stream)
+{
+    if (!c || !synd || !llr || !out || !valid) return fail(QLDPC_ERR_ARG, "qldpc_osdw_decode_dev: null argument");
+    if (!count_dev && count_host <= 0) return QLDPC_OK;
+    if (count_dev && count_host <= 0) return fail(QLDPC_ERR_ARG, "qldpc_osdw_decode_dev: count_host must bound a device-side count");
+    if (int rc = osdw_supported(c, order)) return rc;
+    return osdw_stage(c, idx, count_dev, count_dev ? 0 : count_host, count_host, synd, llr, llr_f64, hard, out, valid, order,
+                      max_combinations, &c->ws_inv, (cudaStream_t)stream);
+}
+
 // ------------------------------------------------------------------------------------------------
 // fused BP -> OSD
 // ------------------------------------------------------------------------------------------------

@@ -19,7 +19,10 @@ static cudaError_t launch_bp_warp_inst3(const qldpc_code *c, const BPParams &P, 
 template <int CPL, int VPL>
 static cudaError_t launch_ms(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    return c->two_tables ? launch_bp_warp_inst3<CPL, VPL, true, 0>(c, P, G, st) : launch_bp_warp_inst3<CPL, VPL, false, 0>(c, P, G, st);
+    // The iteration-0 addition order only matters for non-uniform priors: with one prior value every message of iteration 0
+    // has the same magnitude a = alpha * prior, and (+-a +- a) +- a rounds the same in any order (2a and 0 are exact).
+    const bool two = c->two_tables && !P.prior_uniform;
+    return two ? launch_bp_warp_inst3<CPL, VPL, true, 0>(c, P, G, st) : launch_bp_warp_inst3<CPL, VPL, false, 0>(c, P, G, st);
 }
 
 #define QLDPC_WARP_SHAPES(F)                                                  \

@@ -19,7 +19,9 @@ static cudaError_t launch_f64_inst(const qldpc_code *c, const BPParams &P, const
 template <int CPL, int VPL>
 static cudaError_t launch_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    return c->two_tables ? launch_f64_inst<CPL, VPL, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false>(c, P, G, st);
+    // (uniform prior: the iteration-0 addition order cannot change a bit -- see launch_bp_warp.cu)
+    const bool two = c->two_tables && !P.prior_uniform;
+    return two ? launch_f64_inst<CPL, VPL, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false>(c, P, G, st);
 }
 
 #define QLDPC_WARP_SHAPES(F)                                                  \

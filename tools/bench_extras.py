@@ -84,69 +84,83 @@ class Runner:
         return out
 
 
-def emit(config, **kw):
-    print(json.dumps(dict(config=config, **kw)), flush=True)
+def baseline_configs(quick=False, only=None, emit=None):
+    """Runs BASELINE.json configs 1, 2 (p-sweep), 3, 5 and 4 with fixed shot counts; returns {label: result dict} (and calls
+    emit(label, **result) as results arrive).  quick: a quarter of the shots (what bench.py embeds in its JSON line)."""
+    q = 4 if quick else 1
+    out = {}
 
-
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--quick", action="store_true")
-    ap.add_argument("--only", default="", help="comma-separated config numbers, e.g. 4")
-    args = ap.parse_args()
-    q = 4 if args.quick else 1
-    only = set(args.only.split(",")) if args.only else None
-    global emit
-    _emit = emit
-    def emit(config, **kw):
-        if only is None or config.split(":")[0] in only:
-            _emit(config, **kw)
+    def put(config, **kw):
+        if only is not None and config.split(":")[0] not in only:
+            return
+        out[config] = kw
+        if emit:
+            emit(config, **kw)
     want = lambda k: only is None or k in only
     ms_kw = dict(variant="min_sum", alpha=0.8, damping=0.7, clip=25.0, precision=32)
+    ms64 = dict(ms_kw, precision=64)
+    peak = 148 * 128 * PEAKS.get("sm_max_mhz", 1965.0) * 1e6
+
+    def with_roof(r, res):
+        """lane-op roofline fraction of the BP kernel alone (a BP-only run of the same shots)"""
+        A = 15 * r.code.E + 2 * r.n + r.m
+        if "bp_only" in res:
+            res["bp_lane_op_frac"] = res["bp_only"]["shot_iterations_per_s"] * A / peak
+        return res
+
+    def both(r, p, B, cfg, osd, **kw):
+        res = r.run(p, B, cfg, osd, **kw)
+        if osd >= 0:
+            b = r.run(p, B, cfg, -1, **kw)
+            res["bp_only"] = dict(ms=b["ms"], shots_per_s=b["shots_per_s"], shot_iterations_per_s=b["shot_iterations_per_s"])
+        else:
+            res["bp_only"] = dict(ms=res["ms"], shots_per_s=res["shots_per_s"], shot_iterations_per_s=res["shot_iterations_per_s"])
+        return with_roof(r, res)
 
     if want('1'):  # config 1: [[72,12,6]] p = 0.05, min-sum 50 iterations + OSD-0
         H, Lx, d = load("[[72, 12, 6]]")
         r = Runner(H, Lx, d)
-        emit("1: [[72,12,6]] p=0.05 min-sum BP50 + OSD-0, f32", **r.run(0.05, 8_000_000 // q, dict(max_iter=50, **ms_kw), 0))
-        emit("1: [[72,12,6]] p=0.05 min-sum defaults (alpha=1,damping=1,clip=20) BP50 + OSD-0, f32",
-             **r.run(0.05, 4_000_000 // q, dict(variant="min_sum", max_iter=50, precision=32), 0))
-
+        put("1: [[72,12,6]] p=0.05 min-sum BP50 + OSD-0, f32", **both(r, 0.05, 8_000_000 // q, dict(max_iter=50, **ms_kw), 0))
+        put("1: [[72,12,6]] p=0.05 min-sum BP50 + OSD-0, f64 (bit-exact)", **both(r, 0.05, 4_000_000 // q, dict(max_iter=50, **ms64), 0))
+        put("1: [[72,12,6]] p=0.05 min-sum defaults (alpha=1,damping=1,clip=20) BP50 + OSD-0, f32",
+            **both(r, 0.05, 4_000_000 // q, dict(variant="min_sum", max_iter=50, precision=32), 0))
 
     if want('2'):  # config 2: [[144,12,12]] p-sweep, BP100 + OSD-7
         H, Lx, d = load("[[144, 12, 12]]")
         r = Runner(H, Lx, d)
         for p in (0.01, 0.02, 0.03, 0.04, 0.05, 0.06, 0.1):
-            emit(f"2: [[144,12,12]] p={p} min-sum BP100 + OSD-7, f32", p=p, **r.run(p, 8_000_000 // q, dict(max_iter=100, **ms_kw), 7))
-        emit("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f64", p=0.05,
-             **r.run(0.05, 400_000 // q, dict(variant="sum_product", max_iter=100, precision=64), 7, reps=1))
-        emit("2: [[144,12,12]] p=0.05 min-sum BP100 + OSD-7, f64 (bit-exact parity mode)", p=0.05,
-             **r.run(0.05, 1_000_000 // q, dict(variant="min_sum", max_iter=100, alpha=0.8, damping=0.7, clip=25.0, precision=64), 7, reps=1))
+            put(f"2: [[144,12,12]] p={p} min-sum BP100 + OSD-7, f32", p=p, **both(r, p, 8_000_000 // q, dict(max_iter=100, **ms_kw), 7))
+        for p in (0.01, 0.05, 0.1):
+            put(f"2: [[144,12,12]] p={p} min-sum BP100 + OSD-7, f64 (bit-exact)", p=p, **both(r, p, 2_000_000 // q, dict(max_iter=100, **ms64), 7))
+        put("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f64", p=0.05,
+            **both(r, 0.05, 400_000 // q, dict(variant="sum_product", max_iter=100, precision=64), 7, reps=1))
+        put("2: [[144,12,12]] p=0.05 sum-product BP100 + OSD-7, f32 psi domain", p=0.05,
+            **both(r, 0.05, 2_000_000 // q, dict(variant="sum_product", max_iter=100, precision=32), 7, reps=1))
 
-
-    if want('3'):  # config 3: [[288,12,18]] BP only
+    if want('3'):  # config 3: [[288,12,18]] BP only (BP failures and logical flags are separate counters)
         H, Lx, d = load("[[288, 12, 18]]")
         r = Runner(H, Lx, d)
         for p in (0.1, 0.06, 0.05, 0.04):
-            emit(f"3: [[288,12,18]] p={p} min-sum BP50, BP only, f32", p=p, **r.run(p, 4_000_000 // q, dict(max_iter=50, **ms_kw), -1))
-
+            put(f"3: [[288,12,18]] p={p} min-sum BP50, BP only, f32", p=p, **both(r, p, 4_000_000 // q, dict(max_iter=50, **ms_kw), -1))
+        put("3: [[288,12,18]] p=0.05 min-sum BP50, BP only, f64 (bit-exact)", p=0.05, **both(r, 0.05, 1_000_000 // q, dict(max_iter=50, **ms64), -1))
 
     if want('5'):  # config 5: [[90,8,10]] / [[108,8,10]] p = 0.01, iteration budgets, min-sum vs sum-product
         for name in ("[[90, 8, 10]]", "[[108, 8, 10]]"):
             H, Lx, d = load(name)
             r = Runner(H, Lx, d)
             for mi in (10, 50, 90):
-                emit(f"5: {name} p=0.01 min-sum BP{mi} + OSD-0, f32", **r.run(0.01, 8_000_000 // q, dict(max_iter=mi, **ms_kw), 0))
-            emit(f"5: {name} p=0.01 sum-product BP50 + OSD-0, f64", **r.run(0.01, 1_000_000 // q, dict(variant="sum_product", max_iter=50, precision=64), 0, reps=1))
+                put(f"5: {name} p=0.01 min-sum BP{mi} + OSD-0, f32", **both(r, 0.01, 8_000_000 // q, dict(max_iter=mi, **ms_kw), 0))
+            put(f"5: {name} p=0.01 sum-product BP50 + OSD-0, f64", **both(r, 0.01, 1_000_000 // q, dict(variant="sum_product", max_iter=50, precision=64), 0, reps=1))
+            put(f"5: {name} p=0.01 sum-product BP50 + OSD-0, f32 psi domain", **both(r, 0.01, 4_000_000 // q, dict(variant="sum_product", max_iter=50, precision=32), 0, reps=1))
 
-
-    if want('4'):  # config 4: space-time [[144,12,12]] x 12 rounds (864 x 2592), HBM-staged BP50 + OSD-0
+    if want('4'):  # config 4: space-time [[144,12,12]] x 12 rounds (864 x 2592), BP50 + OSD-0
         H, Lx, d = load("[[144, 12, 12]]")
         Hst = spaceTimeMatrix(H, 12)
         r = Runner(Hst)
         E = r.code.E
         for p in (0.001, 0.005):
             B = 300_000 // q
-            # syndromes of the phenomenological model WITHOUT the reference sampler's first-block quirk are not what the
-            # reference decodes; use its own sampler semantics, vectorised (spaceTime.py:20-43)
+            # the reference's own sampler semantics (first block = last round's syndrome), vectorised (spaceTime.py:20-43)
             rng = np.random.default_rng(4)
             m, n = H.shape
             err = (rng.random((B, n)) < p).astype(np.int64)
@@ -166,7 +180,6 @@ def main():
                           hbm_frac=res_st["shot_iterations_per_s"] * 12 * E / 1e9 / PEAKS.get("hbm_gbs", 6650.0))
             if res_bp["kernel"] == "cta_per_shot":
                 A = 15 * E + 2 * r.n + r.m                       # lane-ops per shot-iteration
-                peak = 148 * 128 * PEAKS.get("sm_max_mhz", 1965.0) * 1e6
                 roof = dict(bound="alu", algorithmic_lane_ops_per_shot_iteration=A, achieved=res_bp["shot_iterations_per_s"] * A / 1e12,
                             peak=peak / 1e12, unit="Tlane-op/s", frac=res_bp["shot_iterations_per_s"] * A / peak,
                             note="BP kernel alone (bp_only run); message state in registers / shared memory: HBM traffic negligible")
@@ -177,15 +190,25 @@ def main():
                 roof = dict(bound="hbm", algorithmic_bytes_per_shot_iteration=bytes_per_iter, achieved=gbs, peak=PEAKS.get("hbm_gbs", 6650.0),
                             unit="GB/s", frac=gbs / PEAKS.get("hbm_gbs", 6650.0), note="BP kernel alone (bp_only run)")
                 label = "HBM-staged"
-            emit(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, {label}", p=p, **res,
-                 bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
-                 roofline=roof, bp_only_hbm_staged=staged)
+            put(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, {label}", p=p, **res,
+                bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
+                roofline=roof, bp_only_hbm_staged=staged)
             if p == 0.001:      # the reference decodes these matrices with sum-product (studies/studyTT.py:49)
                 sp32 = r.run(p, B, dict(variant="sum_product", max_iter=50, precision=32), 0, synd_override=synd, reps=1)
                 sp64 = r.run(p, B // 8, dict(variant="sum_product", max_iter=50, precision=64), 0, synd_override=synd[:B // 8], reps=1)
-                emit(f"4: space-time [[144,12,12]]x12 (864x2592) p={p} sum-product BP50 + OSD-0, f32 psi domain (CTA-per-shot)", p=p, **sp32,
-                     float64_hbm_staged=dict(shots=sp64["shots"], shots_per_s=sp64["shots_per_s"], kernel=sp64["kernel"],
-                                             shot_iterations_per_s=sp64["shot_iterations_per_s"]))
+                put(f"4: space-time [[144,12,12]]x12 (864x2592) p={p} sum-product BP50 + OSD-0, f32 psi domain (CTA-per-shot)", p=p, **sp32,
+                    float64_hbm_staged=dict(shots=sp64["shots"], shots_per_s=sp64["shots_per_s"], kernel=sp64["kernel"],
+                                            shot_iterations_per_s=sp64["shot_iterations_per_s"]))
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--only", default="", help="comma-separated config numbers, e.g. 4")
+    args = ap.parse_args()
+    baseline_configs(args.quick, set(args.only.split(",")) if args.only else None,
+                     emit=lambda config, **kw: print(json.dumps(dict(config=config, **kw)), flush=True))
 
 
 if __name__ == "__main__":

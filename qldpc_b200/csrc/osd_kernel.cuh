@@ -76,6 +76,110 @@ template <> struct KeyBits<double> {
     __device__ static __forceinline__ type get(double x) { return (unsigned long long)__double_as_longlong(x) & 0x7fffffffffffffffull; }
 };
 
+// Rank of the stable argsort by counting, for a group of LPS lanes that owns one shot: lane `lid` of the group ranks its keys
+// ki[t] (index LPS * t + lid) against all n keys, fetched block by block.  Keys of blocks before the lane's own compare with
+// <=, keys of later blocks with <, only the diagonal block needs the tie rule per lane (2 instructions per 32-bit compare:
+// the subtraction as an IMAD on the FMA pipe, the sign accumulated by a LEA.HI; 3 on the ALU pipe for 64-bit keys).
+// cnt[t] = #{j : key_j < key_i, or key_j == key_i and j < i}.
+template <typename KB, int NSLOT, int LPS, typename Fetch>
+__device__ __forceinline__ void osd_rank_count(int n, int lid, const KB (&ki)[NSLOT], int (&cnt)[NSLOT], Fetch fetch)
+{
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t) cnt[t] = 0;
+#pragma unroll
+    for (int jb = 0; jb < NSLOT; ++jb) {                                 // keys LPS jb .. LPS jb + LPS - 1
+        KB thr[NSLOT];
+#pragma unroll
+        for (int t = 0; t < NSLOT; ++t) thr[t] = (jb < t) ? ki[t] + (KB)1 : ki[t];         // j < i: count key_j <= key_i
+        const int jend = min(LPS, n - LPS * jb);
+#pragma unroll 4
+        for (int jl = 0; jl < jend; ++jl) {
+            const KB kj = fetch(LPS * jb + jl);
+#pragma unroll
+            for (int t = 0; t < NSLOT; ++t) {
+                const KB bound = (t == jb) ? ki[t] + (KB)(jl < lid) : thr[t];               // diagonal block: tie rule per lane
+                if constexpr (sizeof(KB) == 4) {
+                    osd_count_lt_fma(cnt[t], kj, bound);                   // subtraction on the FMA pipe, counts up
+                } else {
+                    osd_count_lt(cnt[t], kj, bound);                       // borrow chain, counts down
+                }
+            }
+        }
+    }
+    if constexpr (sizeof(KB) == 8) {
+#pragma unroll
+        for (int t = 0; t < NSLOT; ++t) cnt[t] = -cnt[t];
+    }
+}
+
+// The same count for float64 keys, compared as DOUBLES: the key pattern of |x| is the double |x|, DSETP runs on the FP64 pipe
+// and the counter is bumped by a predicated IMAD on the FMA pipe -- two issue slots per compare and not one cycle of the ALU
+// pipe, which bounds the OSD kernels (the 64-bit integer borrow chain is three ALU instructions, two cycles each).  The
+// tie rule is carried by the comparison: <= for keys of earlier blocks, < for later ones, (<) or (== and j < i) on the
+// diagonal block.  NaN keys compare false: the caller falls back to the integer ranking when a shot holds one.
+template <int NSLOT, int LPS>
+__device__ __forceinline__ void osd_rank_count_f64(int n, int lid, const double (&ki)[NSLOT], int (&cnt)[NSLOT], const double *keys, int one)
+{
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t) cnt[t] = 0;
+#pragma unroll
+    for (int jb = 0; jb < NSLOT; ++jb) {
+        const int jend = min(LPS, n - LPS * jb);
+#pragma unroll 4
+        for (int jl = 0; jl < jend; ++jl) {
+            const double kj = keys[LPS * jb + jl];
+            const int before = (jl < lid) ? 1 : 0;
+#pragma unroll
+            for (int t = 0; t < NSLOT; ++t) {
+                if (t > jb)
+                    asm("{\n\t.reg .pred p;\n\tsetp.le.f64 p, %1, %2;\n\t@p mad.lo.s32 %0, %3, %3, %0;\n\t}" : "+r"(cnt[t]) : "d"(kj), "d"(ki[t]), "r"(one));
+                else if (t < jb)
+                    asm("{\n\t.reg .pred p;\n\tsetp.lt.f64 p, %1, %2;\n\t@p mad.lo.s32 %0, %3, %3, %0;\n\t}" : "+r"(cnt[t]) : "d"(kj), "d"(ki[t]), "r"(one));
+                else
+                    asm("{\n\t.reg .pred p, q, r;\n\tsetp.ne.s32 r, %4, 0;\n\tsetp.eq.and.f64 q, %1, %2, r;\n\tsetp.lt.or.f64 p, %1, %2, q;\n\t"
+                        "@p mad.lo.s32 %0, %3, %3, %0;\n\t}" : "+r"(cnt[t]) : "d"(kj), "d"(ki[t]), "r"(one), "r"(before));
+            }
+        }
+    }
+}
+
+// The ordering of one shot into ord[] (shared memory; keys[] already holds the n key patterns, ki[] the lane's own).
+template <typename KB, int NSLOT, int LPS>
+__device__ __forceinline__ void osd_order_shot(int n, int lid, const KB *keys, const KB (&ki)[NSLOT], uint16_t *ord)
+{
+    int cnt[NSLOT];
+    bool as_doubles = false;
+    if constexpr (sizeof(KB) == 8) {
+        bool nan = false;
+#pragma unroll
+        for (int t = 0; t < NSLOT; ++t) nan = nan || (LPS * t + lid < n && ki[t] > (KB)0x7ff0000000000000ull);
+        as_doubles = !__any_sync(0xffffffffu, nan);                        // (warp-uniform: both halves of a two-shot warp agree)
+        if (as_doubles) {
+            double kd[NSLOT];
+#pragma unroll
+            for (int t = 0; t < NSLOT; ++t) kd[t] = __longlong_as_double((long long)ki[t]);      // (padding: a NaN pattern, never stored)
+            osd_rank_count_f64<NSLOT, LPS>(n, lid, kd, cnt, reinterpret_cast<const double *>(keys), n > 0 ? 1 : 0);
+        }
+    }
+    if constexpr (sizeof(KB) == 4) {
+        osd_rank_count<KB, NSLOT, LPS>(n, lid, ki, cnt, [&](int j) { return keys[j]; });
+    } else if (!as_doubles) {
+        // a NaN among the keys (sorts last, like np.argsort): plain integer ranking, kept small -- it practically never runs
+#pragma unroll
+        for (int t = 0; t < NSLOT; ++t) {                                  // (unrolled over the register arrays, not over j)
+            const int i = LPS * t + lid;
+            int c = 0;
+#pragma unroll 1
+            for (int j = 0; j < n; ++j) c += (keys[j] < ki[t]) || (keys[j] == ki[t] && j < i);
+            cnt[t] = c;
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NSLOT; ++t)
+        if (LPS * t + lid < n) ord[cnt[t]] = (uint16_t)(LPS * t + lid);
+    __syncwarp();
+}
+
 constexpr int OSD_WARPS = 4;
 
 // dynamic shared memory: one copy of colmask per CTA, then per warp: n keys + n ordering entries + solution words
@@ -344,39 +448,14 @@ osd0_fast_kernel(const OSDParams P)
 
         // ---- ordering = argsort(|llr|), stable (OSD.py:10-11): rank by counting --------------
         kbits ki[NS];
-        int cnt[NS];
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             const int i = 32 * t + lane;
             ki[t] = (i < n) ? KeyBits<K>::get(llr[i]) : ~(kbits)0;        // padding sorts last
             if (i < n) keys[i] = ki[t];
-            cnt[t] = 0;
         }
         __syncwarp();
-#pragma unroll
-        for (int jb = 0; jb < NS; ++jb) {                                    // keys 32 jb .. 32 jb + 31
-            kbits thr[NS];
-#pragma unroll
-            for (int t = 0; t < NS; ++t) thr[t] = (jb < t) ? ki[t] + (kbits)1 : ki[t];     // j < i: count key_j <= key_i
-            const int jend = min(32, n - 32 * jb);
-#pragma unroll 4
-            for (int jl = 0; jl < jend; ++jl) {
-                const kbits kj = keys[32 * jb + jl];
-#pragma unroll
-                for (int t = 0; t < NS; ++t) {
-                    const kbits bound = (t == jb) ? ki[t] + (kbits)(jl < lane) : thr[t];     // diagonal block: tie rule per lane
-                    if constexpr (sizeof(kbits) == 4) {
-                        osd_count_lt_fma(cnt[t], kj, bound);               // subtraction on the FMA pipe, counts up
-                    } else {
-                        osd_count_lt(cnt[t], kj, bound);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < NS; ++t)
-            if (32 * t + lane < n) ord[(sizeof(kbits) == 4) ? cnt[t] : -cnt[t]] = (uint16_t)(32 * t + lane);      // (the borrow counters count down)
-        __syncwarp();
+        osd_order_shot<kbits, NS, 32>(n, lane, keys, ki, ord);
 
         // ---- residual syndrome s ^ H*hard (OSD.py:7-8) as packed words, warp-uniform --------
         uint32_t b[WM];
@@ -533,39 +612,14 @@ osd0_fast2_kernel(const OSDParams P)
 
         // ---- ordering = argsort(|llr|), stable (OSD.py:10-11): rank by counting within the half ----------
         kbits ki[NS2];
-        int cnt[NS2];
 #pragma unroll
         for (int t = 0; t < NS2; ++t) {
             const int i = 16 * t + hl;
             ki[t] = (i < n) ? KeyBits<K>::get(llr[i]) : ~(kbits)0;        // padding sorts last
             if (i < n) keys[i] = ki[t];
-            cnt[t] = 0;
         }
         __syncwarp();
-#pragma unroll
-        for (int jb = 0; jb < NS2; ++jb) {                                   // keys 16 jb .. 16 jb + 15
-            kbits thr[NS2];
-#pragma unroll
-            for (int t = 0; t < NS2; ++t) thr[t] = (jb < t) ? ki[t] + (kbits)1 : ki[t];    // j < i: count key_j <= key_i
-            const int jend = min(16, n - 16 * jb);
-#pragma unroll 4
-            for (int jl = 0; jl < jend; ++jl) {
-                const kbits kj = keys[16 * jb + jl];
-#pragma unroll
-                for (int t = 0; t < NS2; ++t) {
-                    const kbits bound = (t == jb) ? ki[t] + (kbits)(jl < hl) : thr[t];       // diagonal block: tie rule per lane
-                    if constexpr (sizeof(kbits) == 4) {
-                        osd_count_lt_fma(cnt[t], kj, bound);               // subtraction on the FMA pipe, counts up
-                    } else {
-                        osd_count_lt(cnt[t], kj, bound);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < NS2; ++t)
-            if (16 * t + hl < n) ord[(sizeof(kbits) == 4) ? cnt[t] : -cnt[t]] = (uint16_t)(16 * t + hl);
-        __syncwarp();
+        osd_order_shot<kbits, NS2, 16>(n, hl, keys, ki, ord);
 
         // ---- residual syndrome s ^ H*hard (OSD.py:7-8), uniform within the half --------------------------
         uint32_t b[WM];

@@ -895,3 +895,24 @@ def test_osdw_on_large_check_matrices_is_exact_or_refused():
         cbig.osd_decode_batch(sb, lb, (lb < 0).astype(np.uint8), order=2)
     with pytest.raises(QldpcError, match="rank-deficient"):
         cbig.bposd_decode_batch(sb, [2.0] * 432, "min_sum", 5, precision=64, osd_order=2)
+
+
+@pytest.mark.parametrize("stem", ["[[72, 12, 6]]", "[[144, 12, 12]]", "[[288, 12, 18]]"])
+def test_osd_float64_keys_that_share_their_high_word(stem):
+    """The OSD kernels rank float64 |LLR| keys by their high words and redo a shot with the full keys when two keys share the
+    high word and differ in the low one: LLRs that differ only below 2^-20 relative (and exact ties) must still give the
+    stable float64 order of the oracle."""
+    H, d = load_code_file(stem)
+    m, n = H.shape
+    rng = np.random.default_rng(8)
+    B = 48
+    err = (rng.random((B, n)) < 0.06).astype(np.uint8)
+    synd = _synd(H, err)
+    base = rng.choice([0.75, 1.0, 3.5], size=(B, n))
+    llr = base * (1.0 + rng.integers(0, 6, size=(B, n)) * 2.0 ** -44) * rng.choice([-1.0, 1.0], size=(B, n))
+    llr[B // 2:] = (base * rng.choice([-1.0, 1.0], size=(B, n)))[B // 2:]          # second half: exact ties only
+    hard = (llr < 0).astype(np.uint8)
+    g = O.Graph(H)
+    want = np.stack([O.osd0(g, synd[i], llr[i], hard[i]) for i in range(B)])
+    code = _code(H, "loop")
+    assert np.array_equal(code.osd_decode_batch(synd, llr, hard), want)

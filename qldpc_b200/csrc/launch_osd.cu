@@ -22,7 +22,7 @@ template <typename K, int WM, int NS>
 static cudaError_t launch_osd_fast_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
 {
     auto kern = osd0_fast_kernel<K, WM, NS>;
-    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS;
+    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<double>(P.n) * OSD_WARPS;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
@@ -39,7 +39,7 @@ template <typename K, int WM, int NS2>
 static cudaError_t launch_osd_fast2_inst(const qldpc_code *c, const OSDParams &P, long long count_hint, cudaStream_t st)
 {
     auto kern = osd0_fast2_kernel<K, WM, NS2>;
-    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<K>(P.n) * OSD_WARPS * 2;
+    const size_t smem = osd_smem_colmask(P.n, P.WM) + osd_smem_per_warp<double>(P.n) * OSD_WARPS * 2;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;

@@ -424,14 +424,14 @@ template <typename K, int WM, int NS>
 __global__ void __launch_bounds__(OSD_WARPS * 32)
 osd0_fast_kernel(const OSDParams P)
 {
-    typedef typename KeyBits<K>::type kbits;
+    typedef unsigned long long kbits;       // keys are always |double(llr)|: float32 LLRs are widened (order and ties are preserved)
     const int m = P.m, n = P.n, WN = P.WN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *cmask = reinterpret_cast<uint32_t *>(smem);
     for (int i = threadIdx.x; i < n * WM; i += blockDim.x) cmask[i] = P.colmask[i];
     __syncthreads();
-    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * warp;
+    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<double>(n) * warp;
     kbits *keys = reinterpret_cast<kbits *>(base);
     uint16_t *ord = reinterpret_cast<uint16_t *>(base + sizeof(kbits) * (size_t)n);
     uint32_t *solw = reinterpret_cast<uint32_t *>(base + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
@@ -451,7 +451,7 @@ osd0_fast_kernel(const OSDParams P)
 #pragma unroll
         for (int t = 0; t < NS; ++t) {
             const int i = 32 * t + lane;
-            ki[t] = (i < n) ? KeyBits<K>::get(llr[i]) : ~(kbits)0;        // padding sorts last
+            ki[t] = (i < n) ? KeyBits<double>::get((double)llr[i]) : ~(kbits)0;        // padding sorts last
             if (i < n) keys[i] = ki[t];
         }
         __syncwarp();
@@ -586,14 +586,14 @@ template <typename K, int WM, int NS2>
 __global__ void __launch_bounds__(OSD_WARPS * 32)
 osd0_fast2_kernel(const OSDParams P)
 {
-    typedef typename KeyBits<K>::type kbits;
+    typedef unsigned long long kbits;       // (see osd0_fast_kernel)
     const int m = P.m, n = P.n, WN = P.WN;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, hl = lane & 15;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *cmask = reinterpret_cast<uint32_t *>(smem);
     for (int i = threadIdx.x; i < n * WM; i += blockDim.x) cmask[i] = P.colmask[i];
     __syncthreads();
-    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * (2 * warp + half);
+    unsigned char *base = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<double>(n) * (2 * warp + half);
     kbits *keys = reinterpret_cast<kbits *>(base);
     uint16_t *ord = reinterpret_cast<uint16_t *>(base + sizeof(kbits) * (size_t)n);
     uint32_t *solw = reinterpret_cast<uint32_t *>(base + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
@@ -615,7 +615,7 @@ osd0_fast2_kernel(const OSDParams P)
 #pragma unroll
         for (int t = 0; t < NS2; ++t) {
             const int i = 16 * t + hl;
-            ki[t] = (i < n) ? KeyBits<K>::get(llr[i]) : ~(kbits)0;        // padding sorts last
+            ki[t] = (i < n) ? KeyBits<double>::get((double)llr[i]) : ~(kbits)0;        // padding sorts last
             if (i < n) keys[i] = ki[t];
         }
         __syncwarp();
@@ -743,7 +743,7 @@ osd0_fast2_kernel(const OSDParams P)
             if ((badmask >> (16 * h)) & 1u) {
                 const long long it_h = 2 * pair + h;
                 const long long shot_h = P.idx ? (long long)P.idx[it_h] : it_h;
-                unsigned char *base_h = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<K>(n) * (2 * warp + h);
+                unsigned char *base_h = smem + osd_smem_colmask(n, WM) + osd_smem_per_warp<double>(n) * (2 * warp + h);
                 uint16_t *ord_h = reinterpret_cast<uint16_t *>(base_h + sizeof(kbits) * (size_t)n);
                 uint32_t *solw_h = reinterpret_cast<uint32_t *>(base_h + ((sizeof(kbits) * (size_t)n + sizeof(uint16_t) * (size_t)n + 3) & ~(size_t)3));
                 osd0_rowmajor_shot<K, WM>(P, it_h, shot_h, cmask, ord_h, solw_h, lane);

@@ -193,6 +193,13 @@ int qldpc_mc_sweep_noisy(qldpc_code *code, const qldpc_bp_config *cfg, const dou
                          double q_meas, uint64_t seed, uint64_t first_shot, int64_t nshots, int32_t draws,
                          int32_t osd_order, int32_t distance, uint64_t *counters);
 
+/* The statistics behind estimate_alpha_from_code (rework/Alvarado.py:10-66) without materialising messages: with a uniform
+ * prior L the message R_new / alpha of the first check pass (rework/decoding.py:58-59) is (1 - 2 s_c) L on every edge of
+ * check c, so its two histograms (true bit 0 / 1) reduce to counts[2 * bit + s], ADDED into counts[4].  err [B][n] uint8
+ * (the caller's errors, e.g. NumPy's stream as in the reference), or NULL: B device-sampled shots (p, seed, first_shot). */
+int qldpc_alpha_counts(qldpc_code *code, int64_t B, const uint8_t *err, double p, uint64_t seed, uint64_t first_shot,
+                       uint64_t *counts);
+
 /* Posterior-LLR histograms without returning B*n floats (BP_per_Iteration.py:56,60 and rework/Alvarado.py:159-162 collect
  * every posterior LLR on the host): device-sampled shots as in qldpc_mc_sweep, BP only, hist [3][nbins] uint64 ADDED into:
  * row 0 = LLRs of variables whose true error bit is 0, row 1 = true bit 1, row 2 = all LLRs of BP-failed shots.  Uniform

@@ -62,6 +62,7 @@ def lib():
         "qldpc_mc_sweep_noisy": ([c_vp, P(BPConfig), c_vp, c_dbl, c_dbl, c_u64, c_u64, c_i64, c_i32, c_i32, c_i32, c_vp], ctypes.c_int),
         "qldpc_sample_noisy_host": ([c_vp, c_dbl, c_dbl, c_u64, c_u64, c_i32, c_i64, c_vp, c_vp], ctypes.c_int),
         "qldpc_osdw_decode_dev": ([c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp], ctypes.c_int),
+        "qldpc_alpha_counts": ([c_vp, c_i64, c_vp, c_dbl, c_u64, c_u64, c_vp], ctypes.c_int),
         "qldpc_measurement_noise_dev": ([c_vp, c_dbl, c_u64, c_u64, c_i64, c_vp, c_vp], ctypes.c_int),
         "qldpc_bp_llr_histogram": ([c_vp, P(BPConfig), c_vp, c_dbl, c_u64, c_u64, c_i64, c_i32, c_dbl, c_dbl, c_i32, c_vp, c_vp], ctypes.c_int),
         "qldpc_bp_decode_dev": ([c_vp, P(BPConfig), c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_vp], ctypes.c_int),
@@ -82,7 +83,7 @@ def lib():
 
 EXPORTED = ["qldpc_last_error", "qldpc_version", "qldpc_device_count", "qldpc_code_create", "qldpc_code_destroy",
             "qldpc_bp_geometry", "qldpc_tiled_conflict_model", "qldpc_warp_layout_tune", "qldpc_words_m", "qldpc_words_n", "qldpc_bp_decode_host", "qldpc_bp_messages_host", "qldpc_osd_decode_host",
-            "qldpc_bposd_decode_host", "qldpc_bposd_decode_host_packed", "qldpc_check_host", "qldpc_syndrome_host", "qldpc_syndrome_dev", "qldpc_sample_host", "qldpc_sample_noisy_host", "qldpc_mc_sweep", "qldpc_mc_sweep_noisy", "qldpc_measurement_noise_dev",
+            "qldpc_bposd_decode_host", "qldpc_bposd_decode_host_packed", "qldpc_check_host", "qldpc_syndrome_host", "qldpc_syndrome_dev", "qldpc_sample_host", "qldpc_sample_noisy_host", "qldpc_mc_sweep", "qldpc_mc_sweep_noisy", "qldpc_measurement_noise_dev", "qldpc_alpha_counts",
             "qldpc_bp_llr_histogram", "qldpc_bp_decode_dev",
             "qldpc_osd_decode_dev", "qldpc_osdw_decode_dev", "qldpc_check_dev", "qldpc_sample_dev", "qldpc_bposd_decode_dev",
             "qldpc_pack_bits_dev", "qldpc_unpack_bits_dev"]

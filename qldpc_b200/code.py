@@ -237,6 +237,23 @@ class Code:
         return dict(zip(_lib.COUNTER_NAMES, (int(x) for x in counters)))
 
 
+    def alpha_counts(self, errors=None, p=None, nshots=0, seed=0, first_shot=0):
+        """The four edge counts behind estimate_alpha_from_code (rework/Alvarado.py:10-66), computed on the device:
+        counts[bit][s] = number of Tanner-graph edges whose variable has error bit `bit` and whose check has syndrome bit s.
+        errors (B, n): the caller's errors; or errors=None: `nshots` device-sampled shots at rate p."""
+        counts = np.zeros(4, np.uint64)
+        if errors is not None:
+            err = _bits(errors)
+            if err.ndim != 2 or err.shape[1] != self.n:
+                raise ValueError("errors must be (B, n)")
+            B, ep = err.shape[0], _vp(err)
+        else:
+            B, ep = int(nshots), None
+        if B:
+            _lib.check(_lib.lib().qldpc_alpha_counts(self._h, B, ep, float(p or 0.0), int(seed), int(first_shot), _vp(counts)),
+                       "qldpc_alpha_counts")
+        return counts.reshape(2, 2).astype(np.int64)
+
     def llr_histograms(self, p, nshots, lo=-30.0, hi=30.0, nbins=120, prior=None, seed=0, first_shot=0, draws=1,
                        variant="min_sum", max_iter=50, alpha=1.0, damping=1.0, clip=20.0, precision=32):
         """Posterior-LLR histograms computed on the device (no B*n floats returned).

@@ -1210,6 +1210,40 @@ extern "C" int qldpc_bp_llr_histogram(qldpc_code *c, const qldpc_bp_config *cfg,
     return QLDPC_OK;
 }
 
+// rework/Alvarado.py:10-66 on the device: the four edge counts behind the alpha estimator (see alpha_counts_kernel)
+extern "C" int qldpc_alpha_counts(qldpc_code *c, int64_t B, const uint8_t *err_host, double p, uint64_t seed, uint64_t first_shot,
+                                  uint64_t *counts)
+{
+    if (!c || !counts) return fail(QLDPC_ERR_ARG, "qldpc_alpha_counts: null argument");
+    if (!err_host && !(p >= 0.0 && p < 1.0)) return fail(QLDPC_ERR_ARG, "qldpc_alpha_counts: need 0 <= p < 1");
+    cudaStream_t st = 0;
+    CK(c->ws_cnt.reserve(8 * QLDPC_NUM_COUNTERS));
+    CK(cudaMemsetAsync(c->ws_cnt.p, 0, 8 * 4, st));
+    const long long chunk = 1ll << 20;
+    for (long long o = 0; o < B; o += chunk) {
+        const long long b = std::min<long long>(chunk, B - o);
+        CK(c->ws_err.reserve(4 * (size_t)b * c->WN));
+        if (err_host) {
+            CK(c->ws_u8a.reserve((size_t)b * std::max(c->m, c->n)));
+            CK(cudaMemcpyAsync(c->ws_u8a.p, err_host + (size_t)o * c->n, (size_t)b * c->n, cudaMemcpyHostToDevice, st));
+            if (int rc = qldpc_pack_bits_dev(c->ws_u8a.as<uint8_t>(), c->ws_err.as<uint32_t>(), b, c->n, st)) return rc;
+        } else {
+            CK(c->ws_synd.reserve(4 * (size_t)b * c->WM));
+            if (int rc = qldpc_sample_dev(c, p, seed, first_shot + (uint64_t)o, 1, b, c->ws_err.as<uint32_t>(), c->ws_synd.as<uint32_t>(), st))
+                return rc;
+        }
+        alpha_counts_kernel<<<grid_for(b, 128, c->num_sms), 128, 0, st>>>(c->d_Hrows, c->d_row_ptr, c->m, c->WN, b, c->ws_err.as<uint32_t>(),
+                                                                         c->ws_cnt.as<unsigned long long>());
+        CK(cudaGetLastError());
+        if (err_host) CK(cudaStreamSynchronize(st));          // (the staging buffer is reused by the next chunk)
+    }
+    uint64_t h[4];
+    CK(cudaMemcpyAsync(h, c->ws_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) counts[i] += h[i];
+    return QLDPC_OK;
+}
+
 extern "C" int qldpc_mc_sweep(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, double p, uint64_t seed,
                               uint64_t first_shot, int64_t nshots, int32_t draws, int32_t osd_order, int32_t distance,
                               uint64_t *counters)

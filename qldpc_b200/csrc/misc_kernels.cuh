@@ -329,6 +329,34 @@ __global__ void __launch_bounds__(256) check_kernel(const CheckParams P)
     }
 }
 
+// ---- alpha estimation (rework/Alvarado.py:10-66) without the messages ----------------------------------------------
+// The estimator histograms R_new / alpha of performMinSum_Symmetric after the FIRST check pass (decoding.py:58-59) by the
+// true value of the edge's bit.  With one prior value L on every variable all incoming messages equal L, so the message
+// on every edge of check c is (1 - 2 s_c) L: the histograms are four numbers, counts[2 * bit + s] = number of edges whose
+// variable has error bit `bit` and whose check has syndrome bit s.  One thread per shot: k = |row_c & error|, s = k mod 2.
+__global__ void alpha_counts_kernel(const uint32_t *__restrict__ Hrows, const int32_t *__restrict__ row_ptr, int m, int WN, long long B,
+                                    const uint32_t *__restrict__ err, unsigned long long *counts)
+{
+    unsigned int c4[4] = {0u, 0u, 0u, 0u};
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < B; t += (long long)gridDim.x * blockDim.x) {
+        const uint32_t *e = err + (size_t)t * WN;
+        for (int c = 0; c < m; ++c) {
+            int k = 0;
+            for (int w = 0; w < WN; ++w) k += __popc(e[w] & Hrows[(size_t)c * WN + w]);
+            const int rw = row_ptr[c + 1] - row_ptr[c], s = k & 1;
+            c4[2 + s] += (unsigned int)k;
+            c4[s] += (unsigned int)(rw - k);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        unsigned int v = c4[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&counts[q], (unsigned long long)v);
+    }
+}
+
 // Shots of a list (idx / count, identity when idx is null) whose OSD-0 solution missed the syndrome (valid == 0): compacted
 // into out_idx, count in out_count (zeroed by the caller).  The OSD-w sweep runs on that list (osdw_kernel.cuh).
 __global__ void compact_invalid_kernel(const int32_t *idx, const unsigned int *count_dev, long long count_host, const uint8_t *valid,

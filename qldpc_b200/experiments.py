@@ -3,12 +3,17 @@ plotting code / loadResults.py can consume them unchanged:
 
     paper_results()      -> keys of paperResults.py:110-114 / paperResults_GPU.py:156-160 / degeneracyCount.ipynb
     rework_main()        -> keys of rework/main.py:119-129 (and rework/Alvarado.py:196-206)
+    rework_main_different_orders() -> results[code][label][p] of rework/main_different_orders.py:45-50,125-135
     bp_per_iteration()   -> keys of BP_per_Iteration.py:85-90
     save_results()       -> np.savez(path, results=dict) as every reference script does
 
 Counting runs entirely on the device (Code.mc_sweep: Philox sampling -> BP -> OSD -> checks -> counters); drivers that
 must return per-shot lists (residual weights, posterior LLRs) use the batched host-array calls.  With
 torch.distributed initialised, shot ranges are sharded over the ranks and the counters all-reduced once.
+
+Random streams: every (code, p) point of a driver gets its own range of global shot ids of the Philox stream `seed` (the
+k-th point uses ids [k * trials, (k + 1) * trials)), so the points of a curve are independent, as in the reference, which
+draws them one after the other from one NumPy stream (paperResults.py:61-63).
 """
 import os
 
@@ -69,13 +74,15 @@ def paper_results(codes=CODES, physicalErrorRates=(0.05, 0.04, 0.03, 0.02, 0.01,
     ln((1-p)/p) of the NOMINAL p as in :49.  bp_only=True gives the BP-only accounting of degeneracyCount.ipynb
     cell 5 (a BP failure counts as a logical error and the logical check of the failed detection is added on top)."""
     results = {}
+    point = 0
     for name in codes:
         code = load_code(name, "x", directory)
         out = {k: [] for k in ("ler", "BPs_fault", "BPs_miscorrected", "incorrectable", "degeneracies")}
         for p in physicalErrorRates:
             prior = np.log((1 - p) / p)
-            c = mc_point(code, p, trials, seed=seed, draws=draws, prior=prior, variant=variant, max_iter=maxIter,
-                         osd_order=(-1 if bp_only else osd_order), precision=precision, **bp_kwargs)
+            c = mc_point(code, p, trials, seed=seed, draws=draws, first_shot=point * trials, prior=prior, variant=variant,
+                         max_iter=maxIter, osd_order=(-1 if bp_only else osd_order), precision=precision, **bp_kwargs)
+            point += 1
             logical = c["logical"] + (c["bp_failed"] if bp_only else 0)
             out["ler"].append(logical / trials)
             out["BPs_fault"].append(c["bp_failed"] if bp_only else 0)     # paperResults.py leaves this counter at 0 (:74-75)
@@ -88,10 +95,11 @@ def paper_results(codes=CODES, physicalErrorRates=(0.05, 0.04, 0.03, 0.02, 0.01,
 
 # ---- rework/main.py / rework/Alvarado.py ------------------------------------------------------------
 def rework_main(experiment, trials=10000, BP_maxIter=100, OSD_order=7, variant="sum_product", seed=0, precision=64,
-                directory=None, chunk=1 << 20, alpha=1.0, damping=1.0, clip=20.0):
+                directory=None, chunk=1 << 20, alpha=1.0, damping=1.0, clip=20.0, first_point=0):
     """rework/main.py:51-129.  `experiment` is its list of dicts {"code", "name", "physicalErrorRates", "distance"}.
     Per-shot lists (residual weights by category) are gathered from the batched calls."""
     results = {}
+    point = first_point
     for exp in experiment:
         code = load_code(exp["code"], "x", directory)
         results[exp["name"]] = {}
@@ -101,7 +109,7 @@ def rework_main(experiment, trials=10000, BP_maxIter=100, OSD_order=7, variant="
             w_bp, w_osd, w_bp_err, w_osd_err = [], [], [], []
             for o in range(0, trials, chunk):
                 b = min(chunk, trials - o)
-                err, synd = code.sample(p, b, seed=seed, first_shot=o)
+                err, synd = code.sample(p, b, seed=seed, first_shot=point * trials + o)
                 corr, conv, iters = code.bposd_decode_batch(synd, prior, variant, BP_maxIter, alpha, damping, clip,
                                                             precision=precision, osd_order=OSD_order)
                 chk = code.check_batch(err, corr, synd, conv, iters)
@@ -116,6 +124,26 @@ def rework_main(experiment, trials=10000, BP_maxIter=100, OSD_order=7, variant="
                 "average_iterations": acc["iters"] / trials, "OSD_invocation_AND_logicalError": acc["both"] / trials,
                 "weights_found_BP": w_bp, "weights_found_OSD": w_osd,
                 "weights_found_BP_error": w_bp_err, "weights_found_OSD_error": w_osd_err}
+            point += 1
+    return results
+
+
+DIFFERENT_ORDERS = ({"bp_iter": 50, "osd_order": 0, "label": "BP50_OSD0"}, {"bp_iter": 100, "osd_order": 0, "label": "BP100_OSD0"},
+                    {"bp_iter": 50, "osd_order": 7, "label": "BP50_OSD7"}, {"bp_iter": 100, "osd_order": 7, "label": "BP100_OSD7"})
+
+
+def rework_main_different_orders(experiment, configurations=DIFFERENT_ORDERS, trials=10000, **kwargs):
+    """rework/main_different_orders.py:45-135: the rework/main.py loop for BP{50,100} x OSD{0,7};
+    results[code name][configuration label][p] = the rework/main.py entry (saved as simulation_results_complex.npz)."""
+    results = {exp["name"]: {} for exp in experiment}
+    point = 0
+    for exp in experiment:
+        for cfg in configurations:
+            r = rework_main([exp], trials=trials, BP_maxIter=cfg["bp_iter"], OSD_order=cfg["osd_order"], first_point=point, **kwargs)
+            for entry in r[exp["name"]].values():
+                entry.pop("average_iterations")            # (not stored by main_different_orders.py:125-134)
+            results[exp["name"]][cfg["label"]] = r[exp["name"]]
+            point += len(exp["physicalErrorRates"])
     return results
 
 
@@ -151,4 +179,4 @@ def bp_per_iteration(codes=CODES, errorRate=0.01, iterations=(10, 20, 30, 40, 50
 
 def save_results(path, results):
     """np.savez(path, results=dict): what every reference script writes and loadResults.py reads back with .item()."""
-    np.savez(path, results=np.array(results, dtype=object), allow_pickle=True)
+    np.savez(path, results=np.array(results, dtype=object))        # (object arrays are pickled by default: one key, `results`)

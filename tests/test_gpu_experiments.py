@@ -59,20 +59,61 @@ def test_paper_results_dict_and_ler(reference_stats):
     assert abs(bp["ler"][0] - w["ler"][7]) < 0.03
 
 
-def test_rework_main_dict():
+def test_rework_main_dict(reference_stats):
     from qldpc_b200 import experiments as X
+    from qldpc_b200.rework.Alvarado import estimate_alpha_from_code
     exp = [{"code": "[[72, 12, 6]]", "name": "72", "physicalErrorRates": [0.05], "distance": 6}]
     N = 20000
-    res = X.rework_main(exp, trials=N, BP_maxIter=50, OSD_order=7, variant="min_sum", alpha=0.8, damping=0.7, clip=25.0, precision=32)
+    H, _ = load_code_file("[[72, 12, 6]]")
+    alpha = estimate_alpha_from_code(H, trials=5000, error_rate=0.05, maxIter=1, verbose=False, seed=3)
+    res = X.rework_main(exp, trials=N, BP_maxIter=50, OSD_order=0, variant="min_sum", alpha=alpha, damping=0.7, clip=25.0, precision=64)
     r = res["72"][0.05]
     assert set(r) == {"logical", "osd", "degeneracies", "average_iterations", "OSD_invocation_AND_logicalError", "weights_found_BP",
                       "weights_found_OSD", "weights_found_BP_error", "weights_found_OSD_error"}
     assert len(r["weights_found_BP_error"]) + len(r["weights_found_OSD_error"]) == round(r["logical"] * N)
     assert len(r["weights_found_OSD_error"]) == round(r["OSD_invocation_AND_logicalError"] * N)
     assert len(r["weights_found_BP"]) + len(r["weights_found_OSD"]) == round(r["degeneracies"] * N)   # all corrections are valid
-    # reference run of the same decoder family (rework/simulation_results.npz, alpha estimated): LER 0.1525, OSD rate 0.2498
-    assert 0.10 < r["logical"] < 0.20 and 0.0 < r["osd"] < 0.35 and 2 < r["average_iterations"] < 25
+    # the reference's run of this flow (rework/Alvarado.py -> rework/simulation_results.npz, 10^4 shots): two-sample binomial
+    # intervals at z = 3 (three rates compared)
+    want = reference_stats["simulation_results.npz"]["72"]["0.05"]
+    for key in ("logical", "osd", "degeneracies", "OSD_invocation_AND_logicalError"):
+        pooled = (r[key] * N + want[key] * 10000) / (N + 10000)
+        assert abs(r[key] - want[key]) <= 3.0 * np.sqrt(pooled * (1 - pooled) * (1 / N + 1 / 10000)), (key, r[key], want[key])
+    assert abs(r["average_iterations"] - want["average_iterations"]) < 0.6
     assert min(r["weights_found_BP_error"]) >= 6              # a logical error has weight >= the distance
+
+
+def test_rework_main_different_orders_dict(tmp_path):
+    """rework/main_different_orders.py:45-135 -> simulation_results_complex.npz: results[code][label][p], saved and read back
+    the way loadResults.py does (np.load(..., allow_pickle=True)["results"].item())."""
+    from qldpc_b200 import experiments as X
+    exp = [{"code": "[[72, 12, 6]]", "name": "72", "physicalErrorRates": [0.06, 0.04], "distance": 6}]
+    N = 4000
+    res = X.rework_main_different_orders(exp, trials=N, variant="min_sum", alpha=0.8, damping=0.7, clip=25.0, precision=64)
+    assert list(res) == ["72"] and list(res["72"]) == ["BP50_OSD0", "BP100_OSD0", "BP50_OSD7", "BP100_OSD7"]
+    for label, by_p in res["72"].items():
+        assert list(by_p) == [0.06, 0.04]
+        for r in by_p.values():
+            assert set(r) == {"logical", "osd", "degeneracies", "OSD_invocation_AND_logicalError", "weights_found_BP", "weights_found_OSD",
+                              "weights_found_BP_error", "weights_found_OSD_error"}
+    assert res["72"]["BP100_OSD0"][0.06]["osd"] <= res["72"]["BP50_OSD0"][0.06]["osd"] + 3 * np.sqrt(0.25 / N)   # more iterations, fewer failures
+    path = str(tmp_path / "simulation_results_complex.npz")
+    X.save_results(path, res)
+    f = np.load(path, allow_pickle=True)
+    assert list(f.keys()) == ["results"] and f["results"].item() == res
+
+
+def test_curve_points_use_independent_streams():
+    """Every (code, p) point of a driver draws its own range of the Philox stream: the errors at a lower p are not a subset
+    of the errors at a higher p (they were, with one shared range per point)."""
+    from qldpc_b200 import experiments as X, load_code
+    code = load_code("[[72, 12, 6]]")
+    a = X.mc_point(code, 0.05, 2000, seed=0, first_shot=0, variant="min_sum", max_iter=20, precision=32)
+    b = X.mc_point(code, 0.05, 2000, seed=0, first_shot=2000, variant="min_sum", max_iter=20, precision=32)
+    assert a["shots"] == b["shots"] == 2000 and a["error_weight"] != b["error_weight"]
+    r1 = X.paper_results(codes=["[[72, 12, 6]]"], physicalErrorRates=[0.05, 0.05], trials=2000, variant="min_sum", maxIter=20, draws=1,
+                         precision=32, alpha=0.8, damping=0.7, clip=25.0)["[[72, 12, 6]]"]
+    assert r1["incorrectable"][0] != r1["incorrectable"][1] or r1["degeneracies"][0] != r1["degeneracies"][1]
 
 
 def test_bp_per_iteration_dict():

@@ -90,3 +90,16 @@ def test_spacetime_host(spacetime_golden):
     np.random.seed(5)
     e, s = spacetimeSyndrome(H, 0.03, 3)
     assert np.array_equal(e, d["seed5_error"]) and np.array_equal(s, d["seed5_syndrome"])
+
+
+def test_save_results_round_trip_like_load_results(tmp_path):
+    """experiments.save_results writes what every reference script writes (np.savez(path, results=dict)); loadResults.py:5-12
+    reads it back with np.load(..., allow_pickle=True)["results"].item()."""
+    import numpy as np
+    from qldpc_b200 import experiments as X
+    res = {"[[72, 12, 6]]": {"ler": [0.1, 0.01], "BPs_fault": [0, 0], "degeneracies": [3, 1]}}
+    path = str(tmp_path / "BPOSD.npz")
+    X.save_results(path, res)
+    f = np.load(path, allow_pickle=True)
+    assert list(f.keys()) == ["results"]
+    assert f["results"].item() == res

@@ -57,12 +57,14 @@ def allreduce_counters(counters):
     return {k: int(v) for k, v in zip(keys, t.cpu().tolist())}
 
 
-def mc_point(code, p, nshots, seed=0, draws=1, **decoder):
-    """One (code, p) Monte-Carlo point: this rank's shard of the global shot range, counters reduced over ranks."""
+def mc_point(code, p, nshots, seed=0, draws=1, first_shot=0, **decoder):
+    """One (code, p) Monte-Carlo point on the global shot ids [first_shot, first_shot + nshots): this rank's shard of
+    that range, counters reduced over ranks."""
     dist = _dist()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist else (0, 1)
     first, count = shard_range(nshots, rank, world)
-    c = code.mc_sweep(p, count, seed=seed, first_shot=first, draws=draws, **decoder) if count else dict.fromkeys(_lib.COUNTER_NAMES, 0)
+    c = (code.mc_sweep(p, count, seed=seed, first_shot=first_shot + first, draws=draws, **decoder) if count
+         else dict.fromkeys(_lib.COUNTER_NAMES, 0))
     return allreduce_counters(c)
 
 

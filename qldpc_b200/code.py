@@ -82,7 +82,7 @@ class Code:
         cfg.variant = VARIANTS[variant] if isinstance(variant, str) else int(variant)
         cfg.precision = int(precision)
         cfg.max_iter = int(max_iter)
-        cfg.staged = int(staged)          # 0 auto | 1 (True) HBM-staged | 2 thread-per-shot | 3 warp-per-shot | 4 CTA-per-shot
+        cfg.staged = int(staged)          # 0 auto | 1 (True) HBM-staged thread-per-shot | 2 thread-per-shot | 3 warp-per-shot | 4 CTA-per-shot | 5 CTA-per-shot, staged
         cfg.lanes_per_shot = int(lanes_per_shot)
         cfg.refill_min = int(refill_min)
         cfg.alpha, cfg.damping, cfg.clip = float(alpha), float(damping), float(clip)
@@ -101,8 +101,9 @@ class Code:
         _lib.check(_lib.lib().qldpc_bp_geometry(self._h, ctypes.byref(cfg), ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
         kind = c.value
         return dict(shots_per_cta=a.value, smem_bytes=b.value, staged=(kind == 1),
-                    lanes_per_shot=(0 if kind == 133 else kind - 100 if kind >= 100 else 1),
-                    kernel=('hbm_staged' if kind == 1 else 'cta_per_shot' if kind == 133 else 'warp_per_shot' if kind == 132 else 'tiled' if kind >= 100 else 'thread_per_shot'))
+                    lanes_per_shot=(0 if kind in (133, 134) else kind - 100 if kind >= 100 else 1),
+                    kernel=('hbm_staged' if kind == 1 else 'cta_staged' if kind == 134 else 'cta_per_shot' if kind == 133
+                            else 'warp_per_shot' if kind == 132 else 'tiled' if kind >= 100 else 'thread_per_shot'))
 
     def tune_warp_layout(self, steps=0):
         """Lane labelling of the warp-per-shot kernels (results never depend on it).  steps = 0: report; steps < 0: install

@@ -13,6 +13,7 @@
 #include "capi_internal.h"
 #include "misc_kernels.cuh"     // non-template kernels: defined in this translation unit only
 #include "osdw_kernel.cuh"
+#include "bp_stage_kernel.cuh"   // (layout helpers only; the kernels are instantiated in launch_bp_stage.cu)
 
 static thread_local std::string g_err;
 int qldpc_fail(int code, const std::string &msg)
@@ -336,6 +337,25 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     G->refill_min = 1;
     G->warp_kernel = false;
     G->cta_kernel = false;
+    G->stage_kernel = false;
+    // CTA-per-shot, messages staged in global memory: on request (staged = 5), and for everything the register-resident CTA
+    // kernel does not serve on these matrices -- float64, and through it the reference's exact (tanh-domain) sum-product
+    if (c->cta_ok && (cfg->staged == 5 || (cfg->staged == 0 && cfg->precision == 64))) {
+        const int tsize = cfg->precision == 64 ? 8 : 4;
+        G->staged = false;
+        G->stage_kernel = true;
+        G->warp_var = cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2);
+        G->threads = c->cta_nw * 32;
+        G->shots_per_cta = 1;
+        G->smem = bp_stage_smem(c->cta_sv * c->cta_nw, tsize);
+        if (G->smem <= (size_t)c->smem_optin) {
+            const int occ = bp_stage_occupancy(c, cfg->precision, G->threads, G->smem);
+            G->grid = (int)std::max<long long>(1, std::min<long long>((long long)c->num_sms * occ, B));
+            G->gstate_bytes = bp_stage_gstate(c->cta_nw, c->cta_sc, 8, tsize) * (size_t)G->grid;
+            return QLDPC_OK;
+        }
+        G->stage_kernel = false;
+    }
     if ((cfg->staged == 0 || cfg->staged == 4) && c->cta_ok && cfg->precision == 32) {
         G->staged = false;
         G->cta_kernel = true;
@@ -424,7 +444,7 @@ extern "C" int qldpc_bp_geometry(qldpc_code *c, const qldpc_bp_config *cfg, int3
     bp_geometry(c, cfg, 1ll << 40, &G);
     if (shots_per_cta) *shots_per_cta = G.shots_per_cta;
     if (smem_bytes) *smem_bytes = (int32_t)G.smem;
-    if (staged) *staged = G.staged ? 1 : (G.cta_kernel ? 133 : (G.warp_kernel ? 132 : (G.tiled_T ? 100 + G.tiled_T : 0)));
+    if (staged) *staged = G.staged ? 1 : (G.stage_kernel ? 134 : (G.cta_kernel ? 133 : (G.warp_kernel ? 132 : (G.tiled_T ? 100 + G.tiled_T : 0))));
     return QLDPC_OK;
 }
 
@@ -496,7 +516,7 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     if (int rc = set_prior(c, prior_host, st)) return rc;
     BPGeom G;
     bp_geometry(c, cfg, B, &G);
-    if (G.staged) CK(gstate_buf->reserve(G.gstate_bytes));
+    if (G.staged || G.stage_kernel) CK(gstate_buf->reserve(G.gstate_bytes));
     CK(ctrl_buf->reserve(sizeof(Ctrl)));
     Ctrl *ctrl = ctrl_buf->as<Ctrl>();
     CK(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st));
@@ -529,7 +549,9 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.dump_iter = -1;
     cudaError_t e;
     const int kv = kernel_variant(cfg->variant);
-    if (G.cta_kernel)
+    if (G.stage_kernel)
+        e = launch_bp_stage(c, P, G, cfg->precision, st);
+    else if (G.cta_kernel)
         e = launch_bp_cta(c, P, G, st);
     else if (G.warp_kernel)
         e = launch_bp_warp(c, P, G, st);

@@ -125,6 +125,7 @@ struct BPGeom {
     bool warp_kernel;     // warp-per-shot kernel (messages in registers)
     int warp_var;         // its variant: 0 min-sum, 1 sum-product, 2 symmetric sum-product
     bool cta_kernel;      // CTA-per-shot kernel (messages in registers, several warps per shot)
+    bool stage_kernel;    // CTA-per-shot kernel with the messages staged in global memory (bp_stage_kernel.cuh)
     int shots_per_cta;
     int refill_min;
     int threads, grid;
@@ -139,5 +140,7 @@ cudaError_t launch_bp_warp(const qldpc_code *c, const BPParams &P, const BPGeom 
 cudaError_t launch_bp_warp_sp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
 cudaError_t launch_bp_warp_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
 cudaError_t launch_bp_cta(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
+cudaError_t launch_bp_stage(const qldpc_code *c, const BPParams &P, const BPGeom &G, int precision, cudaStream_t st);
+int bp_stage_occupancy(const qldpc_code *c, int precision, int threads, size_t smem);
 bool osd_use_block(const qldpc_code *c);
 int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, cudaStream_t st, DevBuf *redo = nullptr);

@@ -510,7 +510,7 @@ def test_spacetime_144x12_bp_osd_vs_oracle():
     ref = O.decode_batch(g, synd, prior, O.MIN_SUM, 50, 0.8, 0.7, 25.0, osd_order=0, want_llr=True)
     code = _code(Hst, "min_sum")
     cfg = code.config("min_sum", 50, 0.8, 0.7, 25.0, 64)
-    assert code.geometry(cfg)["kernel"] == "hbm_staged"
+    assert code.geometry(cfg)["kernel"] == "cta_staged"
     hard, conv, llr, iters = code.bp_decode_batch(synd, prior, "min_sum", 50, 0.8, 0.7, 25.0, precision=64)
     assert np.array_equal(conv, ref["converged"]) and np.array_equal(iters, ref["iters"]) and np.array_equal(llr, ref["llr"])
     assert (~conv).sum() >= 3, "want some BP failures to exercise OSD"
@@ -913,3 +913,43 @@ def test_osd_float64_keys_that_share_their_high_word(stem):
     want = np.stack([O.osd0(g, synd[i], llr[i], hard[i]) for i in range(B)])
     code = _code(H, "loop")
     assert np.array_equal(code.osd_decode_batch(synd, llr, hard), want)
+
+
+@pytest.mark.parametrize("schedule", ["seq", "reference"])
+def test_cta_staged_kernel_vs_thread_per_shot_staged_kernel(schedule):
+    """bp_stage_kernel (one CTA per shot, messages staged in global memory with 128-bit accesses, summaries on chip) against
+    the thread-per-shot HBM-staged kernel on the 864 x 2592 space-time matrix: min-sum bit-identical in float32 and float64
+    (hard decisions, flags, exit iterations, LLRs); the exact (tanh-domain) float64 sum-product agrees to the last ulps of
+    the row product (taken in slot order instead of column order)."""
+    from qldpc_b200 import Code, graph
+    from qldpc_b200.spaceTime import spaceTimeMatrix
+    H, _ = load_code_file("[[144, 12, 12]]")
+    Hst = spaceTimeMatrix(H, 12)
+    m, n = Hst.shape
+    sched = (graph.SEQ, graph.SEQ) if schedule == "seq" else graph.reference_schedule(Hst, "min_sum")
+    code = Code(Hst, None, sched)
+    rng = np.random.default_rng(29)
+    err = (rng.random((203, n)) < 0.004).astype(np.uint8)
+    synd = _synd(Hst, err)
+    for prec in (32, 64):
+        for (prior, kw) in ((_prior(0.004, n), dict(variant="min_sum", max_iter=40, alpha=0.8, damping=0.7, clip=25.0)),
+                            (rng.uniform(2.0, 7.0, n), dict(variant="min_sum", max_iter=25)),                                  # alpha = damping = 1
+                            (np.full(n, 30.0), dict(variant="min_sum", max_iter=10, alpha=0.9, damping=0.8, clip=20.0))):       # prior > clip
+            assert code.geometry(code.config(staged=5, precision=prec, **kw))["kernel"] == "cta_staged"
+            ref = code.bp_decode_batch(synd, prior, staged=1, precision=prec, **kw)
+            got = code.bp_decode_batch(synd, prior, staged=5, precision=prec, **kw)
+            for x, y in zip(got, ref):
+                assert np.array_equal(x, y), (schedule, prec, kw)
+    assert code.geometry(code.config("min_sum", 40, 0.8, 0.7, 25.0, precision=64))["kernel"] == "cta_staged"     # float64: the default
+    prior = _prior(0.004, n)
+    for variant, kw in (("sum_product", {}), ("sum_product_sym", dict(alpha=0.9, damping=0.8, clip=20.0))):
+        assert code.geometry(code.config(variant, 30, precision=64, **kw))["kernel"] == "cta_staged"
+        ref = code.bp_decode_batch(synd, prior, variant, 30, precision=64, staged=1, **kw)
+        got = code.bp_decode_batch(synd, prior, variant, 30, precision=64, **kw)
+        same = (got[1] == ref[1]) & (got[3] == ref[3]) & (got[0] == ref[0]).all(1)
+        sel = ref[1] & same
+        rel = np.abs(got[2][sel] - ref[2][sel]) / np.maximum(np.abs(ref[2][sel]), 1e-3)
+        print(f"\n[cta_staged f64 {variant}] identical {same.mean():.4f}, max rel. LLR error {rel.max():.2e}")
+        assert same.mean() >= 0.99 and rel.max() < 1e-9, (variant, same.mean(), rel.max())
+        got32 = code.bp_decode_batch(synd, prior, variant, 30, precision=32, staged=5, **kw)       # float32, tanh domain
+        assert (got32[1] == ref[1]).mean() > 0.9

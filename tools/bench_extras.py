@@ -175,9 +175,14 @@ def baseline_configs(quick=False, only=None, emit=None):
             res_bp = r.run(p, B, dict(max_iter=50, **ms_kw), -1, synd_override=synd, reps=1)
             # the same BP with the message state staged in HBM (what BASELINE config 4 names): the crossover figure
             res_st = r.run(p, B, dict(max_iter=50, staged=1, **ms_kw), -1, synd_override=synd, reps=1)
-            staged = dict(kernel=res_st["kernel"], shots_per_s=res_st["shots_per_s"], shot_iterations_per_s=res_st["shot_iterations_per_s"],
-                          hbm_algorithmic_gbs=res_st["shot_iterations_per_s"] * 12 * E / 1e9,
-                          hbm_frac=res_st["shot_iterations_per_s"] * 12 * E / 1e9 / PEAKS.get("hbm_gbs", 6650.0))
+            def staged_figures(rs, tsize=4):
+                gbs = rs["shot_iterations_per_s"] * 3 * tsize * E / 1e9
+                return dict(kernel=rs["kernel"], shots_per_s=rs["shots_per_s"], shot_iterations_per_s=rs["shot_iterations_per_s"],
+                            algorithmic_bytes_per_shot_iteration=3 * tsize * E, hbm_algorithmic_gbs=gbs, hbm_frac=gbs / PEAKS.get("hbm_gbs", 6650.0))
+            staged = staged_figures(res_st)
+            # the CTA-per-shot kernel with the messages staged in global memory (bp_stage_kernel.cuh), float32 and float64
+            cta_staged = staged_figures(r.run(p, B, dict(max_iter=50, staged=5, **ms_kw), -1, synd_override=synd, reps=1))
+            cta_staged_f64 = staged_figures(r.run(p, B, dict(max_iter=50, **dict(ms_kw, precision=64)), -1, synd_override=synd, reps=1), 8)
             if res_bp["kernel"] == "cta_per_shot":
                 A = 15 * E + 2 * r.n + r.m                       # lane-ops per shot-iteration
                 roof = dict(bound="alu", algorithmic_lane_ops_per_shot_iteration=A, achieved=res_bp["shot_iterations_per_s"] * A / 1e12,
@@ -192,13 +197,16 @@ def baseline_configs(quick=False, only=None, emit=None):
                 label = "HBM-staged"
             put(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, {label}", p=p, **res,
                 bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
-                roofline=roof, bp_only_hbm_staged=staged)
+                roofline=roof, bp_only_hbm_staged=staged, bp_only_cta_staged=cta_staged, bp_only_cta_staged_f64=cta_staged_f64)
             if p == 0.001:      # the reference decodes these matrices with sum-product (studies/studyTT.py:49)
                 sp32 = r.run(p, B, dict(variant="sum_product", max_iter=50, precision=32), 0, synd_override=synd, reps=1)
-                sp64 = r.run(p, B // 8, dict(variant="sum_product", max_iter=50, precision=64), 0, synd_override=synd[:B // 8], reps=1)
+                sp64 = r.run(p, B // 4, dict(variant="sum_product", max_iter=50, precision=64), 0, synd_override=synd[:B // 4], reps=1)
+                sp64b = r.run(p, B // 4, dict(variant="sum_product", max_iter=50, precision=64), -1, synd_override=synd[:B // 4], reps=1)
+                sp64old = r.run(p, B // 16, dict(variant="sum_product", max_iter=50, precision=64, staged=1), -1, synd_override=synd[:B // 16], reps=1)
                 put(f"4: space-time [[144,12,12]]x12 (864x2592) p={p} sum-product BP50 + OSD-0, f32 psi domain (CTA-per-shot)", p=p, **sp32,
-                    float64_hbm_staged=dict(shots=sp64["shots"], shots_per_s=sp64["shots_per_s"], kernel=sp64["kernel"],
-                                            shot_iterations_per_s=sp64["shot_iterations_per_s"]))
+                    float64=dict(shots=sp64["shots"], shots_per_s=sp64["shots_per_s"], kernel=sp64["kernel"],
+                                 bp_only_shots_per_s=sp64b["shots_per_s"], bp_only_shot_iterations_per_s=sp64b["shot_iterations_per_s"],
+                                 thread_per_shot_staged_bp_only_shot_iterations_per_s=sp64old["shot_iterations_per_s"]))
     return out
 
 

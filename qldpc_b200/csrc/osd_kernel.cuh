@@ -944,6 +944,22 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 // The checks of column ordering[j] are packed 3 x 10 bits into the shared-memory words the sort keys occupied
 // (m < 1024, column weight <= 3: the space-time matrices; otherwise they are read from global memory).
 // ------------------------------------------------------------------------------------------------
+// the sort runs as a bitonic sort inside the (still idle) transform area when (key, index) pairs of the padded length fit
+// there; only the rank-counting fallback needs the keys outside of it.  (4 n bytes either way: the packed check lists;
+// 114 KB in all for the 864 x 2592 matrix with float or double keys -- two CTAs per SM.)
+template <typename K>
+__host__ __device__ inline bool osdbf_bitonic_fits(int m, int n)
+{
+    size_t N2 = 1;
+    while (N2 < (size_t)n) N2 <<= 1;
+    return (sizeof(typename KeyBits<K>::type) + 2) * N2 <= 4 * (size_t)m * ((m + 31) / 32);
+}
+template <typename K>
+__host__ __device__ inline size_t osdbf_key_area(int m, int n)
+{
+    return osdbf_bitonic_fits<K>(m, n) ? 4 * (size_t)n : sizeof(typename KeyBits<K>::type) * (size_t)n;
+}
+
 template <typename K>
 __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 {
@@ -955,7 +971,7 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     o += 4 * (size_t)WM * (OSDB_THREADS / 32);                  // per-warp candidate columns
     o += 4 * (size_t)WN;                                        // solution words
     o = (o + 7) & ~(size_t)7;
-    o += sizeof(typename KeyBits<K>::type) * (size_t)n;         // keys, then the packed check lists
+    o += osdbf_key_area<K>(m, n);                               // keys (rank-counting path only), then the packed check lists
     o += 2 * (size_t)n;                                         // ordering (uint16)
     return o + 64;
 }
@@ -978,7 +994,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
     uint32_t *solw = cand + (size_t)NW * WM;                                // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
     uint32_t *chk = reinterpret_cast<uint32_t *>(keys);                    // [n] packed checks of column ordering[j] (after the sort)
-    uint16_t *ord = reinterpret_cast<uint16_t *>(keys + n);
+    uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
     __shared__ int s_pp[NW], s_pw[NW], s_k;
     constexpr bool packed_chk = PACKED;               // m < 1024 and column weight <= 3 (checked by the host)
 
@@ -1009,7 +1025,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
         int N2 = 1;
         while (N2 < n) N2 <<= 1;
-        if ((sizeof(kbits) + 2) * (size_t)N2 <= 4 * (size_t)m * WM) {
+        if (osdbf_bitonic_fits<K>(m, n)) {
             // bitonic sort of (key, index) pairs in the (still unused) transform area: O(n log^2 n) instead of the
             // O(n^2) rank counting -- 78 stages of 2048 compare-exchanges for n = 2592
             kbits *sk = reinterpret_cast<kbits *>(TC);

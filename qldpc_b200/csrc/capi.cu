@@ -254,6 +254,13 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
                 if (int rc = layout_tables_upload(lb.tables(), &c->d_ctab, &c->ctab, c->cta_cost)) return rc;
                 c->cta_nw = nw; c->cta_sc = sc; c->cta_sv = sv;
                 c->cta_ok = bp_cta_smem(sv * nw) <= (size_t)c->smem_optin;
+                if (c->cta_ok) {
+                    WarpLayoutBuilder lb64(m, n, row_ptr, col_idx, var_ptr, var_edge0, var_edge1, edge_check.data(), 8, sc * nw, sv * nw, 16);
+                    if (lb64.construct(400000)) {
+                        if (int rc = layout_tables_upload(lb64.tables(), &c->d_ctab64, &c->ctab64, c->cta64_cost)) return rc;
+                        c->cta64_ok = true;
+                    }
+                }
             }
         }
     }
@@ -305,6 +312,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     cudaFree(c->d_wtab64);
     delete c->wlayout64;
     cudaFree(c->d_ctab);
+    cudaFree(c->d_ctab64);
     delete c->wlayout;
     DevBuf *bufs[] = {&c->prior32, &c->prior64, &c->ctrl, &c->gstate, &c->ws_synd, &c->ws_hard, &c->ws_err, &c->ws_conv,
                       &c->ws_iters, &c->ws_llr, &c->ws_fail, &c->ws_valid, &c->ws_u8a, &c->ws_u8b, &c->ws_flags, &c->ws_redo,

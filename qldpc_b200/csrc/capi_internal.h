@@ -88,6 +88,11 @@ struct qldpc_code {
     BPWarpTables ctab = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int cta_nw = 0, cta_sc = 3, cta_sv = 7, cta_cost[3] = {0, 0, 0};
     bool cta_ok = false;
+    // the same shape labelled for 16-lane conflict domains (64-bit shared-memory words: float64 bp_stage_kernel)
+    uint32_t *d_ctab64 = nullptr;
+    BPWarpTables ctab64 = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int cta64_cost[3] = {0, 0, 0};
+    bool cta64_ok = false;
     int max_row_w = 0;
     double prior_max = 0.0;
     bool prior_uniform = false;

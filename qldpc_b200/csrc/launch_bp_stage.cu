@@ -5,11 +5,15 @@
 template <typename T, int VAR, int SC, int SV, bool TWO>
 static cudaError_t launch_stage_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
+    // float32: offsets in registers, one CTA per SM (measured 9.3-9.9e7 shot-iterations/s against 7.9-8.3e7 with two CTAs per SM
+    // and the offsets re-read from the tables); float64: the FP64-latency-bound arithmetic wants the second CTA
     constexpr bool TABREG = sizeof(T) == 4;
     auto kern = bp_stage_kernel<T, VAR, SC, SV, 8, TWO, TABREG>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
     if (e != cudaSuccess) return e;
-    kern<<<G.grid, G.threads, G.smem, st>>>(P, c->ctab, c->cta_sv * c->cta_nw);
+    // float64: 64-bit shared-memory words are served per half-warp -- the labelling built for 16-lane conflict domains
+    const BPWarpTables &tab = (sizeof(T) == 8 && c->cta64_ok) ? c->ctab64 : c->ctab;
+    kern<<<G.grid, G.threads, G.smem, st>>>(P, tab, c->cta_sv * c->cta_nw);
     return cudaGetLastError();
 }
 

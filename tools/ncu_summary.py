@@ -1,8 +1,11 @@
-"""Summarise an .ncu-rep (raw page + source page) into text: python tools/ncu_summary.py file.ncu-rep [min_pct] [kernel-regex]"""
+"""Summarise an .ncu-rep (raw page + source page) into text: python tools/ncu_summary.py file.ncu-rep [min_pct] [kernel-regex | name:invocation]
+(name:invocation selects the n-th launch of a kernel name, e.g. bp_stage_kernel:3 -- template arguments are not part of the name)"""
 import csv, subprocess, sys
 rep = sys.argv[1]
 minpct = float(sys.argv[2]) if len(sys.argv) > 2 else 0.6
-ksel = ["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else []
+ksel = []
+if len(sys.argv) > 3:
+    ksel = ["--kernel-id", "::" + sys.argv[3]] if ":" in sys.argv[3] else ["--kernel-name", "regex:" + sys.argv[3]]
 raw = subprocess.run(["ncu", "-i", rep] + ksel + ["--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]

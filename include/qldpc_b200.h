@@ -208,7 +208,14 @@ int qldpc_bp_llr_histogram(qldpc_code *code, const qldpc_bp_config *cfg, const d
                            uint64_t first_shot, int64_t nshots, int32_t draws, double lo, double hi, int32_t nbins,
                            uint64_t *hist, uint64_t *bp_failed);
 
-/* ---------------- device-pointer API (bit-packed, asynchronous) ---------------- */
+/* ---------------- device-pointer API (bit-packed, asynchronous) ----------------
+ * Calls enqueue work on `stream` and return.  Concurrency contract of a handle: ONE host thread, ONE stream at a time -- the
+ * control block (shot cursor, failure counter), the device copies of the prior and the internal workspaces (LLR hand-off,
+ * failure / invalid lists, staging arrays) are per handle, so two calls in flight on different streams race on them; use one
+ * handle per stream (handles are cheap: tables < 100 KB).  Implicit synchronisation: a call with a prior that differs from
+ * the previous call's copies it and synchronises `stream`; a call that needs a larger workspace than any call before it
+ * frees and allocates device memory (device-wide synchronisation).  After one call with the largest batch and the final
+ * prior the calls are pure kernel launches plus 8-byte memsets, and can be stream-captured. */
 
 /* words per packed syndrome / error row */
 int qldpc_words_m(const qldpc_code *code);

@@ -91,8 +91,10 @@ def test_reference_named_wrappers(bp_golden):
 
 @pytest.mark.parametrize("ci", range(6))
 def test_sum_product_f64_vs_reference_golden(bp_golden, ci):
-    """CUDA's tanh/atanh are not NumPy's: compare shots that converge (same iteration required) to
-    1e-4 relative as the north star asks -- in practice ~1e-12 -- and the convergence flag on the rest."""
+    """CUDA's tanh/atanh are not NumPy's (last-ulp differences), so sum-product parity is a tolerance: the north star asks for
+    1e-4 relative.  Measured against the unmodified reference's golden vectors (tools/sp_accuracy_report.py ->
+    profiles/r2_sp_accuracy.json): identical flags, exit iterations and hard decisions on every golden shot, LLRs within 3.2e-9
+    relative.  Held here to 1e-7 on EVERY shot that converges (not only the early ones) and to exact agreement of the rest."""
     d, meta = bp_golden
     case = meta["cases"][ci]
     H, _ = load_code_file(case["code"], case["layout"])
@@ -101,20 +103,19 @@ def test_sum_product_f64_vs_reference_golden(bp_golden, ci):
     prior = _prior(case["p"], H.shape[1])
     code = _code(H, "sum_product")
     hard, conv, llr, iters = code.bp_decode_batch(synd, prior, "sum_product", case["max_iter"], precision=64)
-    early = d[key + "_sp_conv"] & (d[key + "_sp_iter"] <= 20)
-    assert early.sum() >= case["shots"] // 2
-    assert np.array_equal(conv[early], d[key + "_sp_conv"][early])
-    assert np.array_equal(iters[early], d[key + "_sp_iter"][early])
-    assert np.array_equal(hard[early], d[key + "_sp_hard"][early])
-    np.testing.assert_allclose(llr[early], d[key + "_sp_llr"][early], rtol=1e-4)
-    assert (conv == d[key + "_sp_conv"]).mean() >= 0.9
+    assert np.array_equal(conv, d[key + "_sp_conv"]) and np.array_equal(iters, d[key + "_sp_iter"])
+    ok = d[key + "_sp_conv"]
+    assert ok.sum() >= case["shots"] // 2
+    assert np.array_equal(hard[ok], d[key + "_sp_hard"][ok])
+    np.testing.assert_allclose(llr[ok], d[key + "_sp_llr"][ok], rtol=1e-7)
     # damped / scaled / clipped variant (rework/decoding.py:131)
     al, dm, cl = meta["sym_params"]
     codes = _code(H, "sum_product_sym")
     hard, conv, llr, iters = codes.bp_decode_batch(synd, prior, "sum_product_sym", case["max_iter"], al, dm, cl, precision=64)
-    early = d[key + "_sym_conv"] & (d[key + "_sym_iter"] <= 20)
-    assert np.array_equal(iters[early], d[key + "_sym_iter"][early]) and np.array_equal(hard[early], d[key + "_sym_hard"][early])
-    np.testing.assert_allclose(llr[early], d[key + "_sym_llr"][early], rtol=1e-4)
+    ok = d[key + "_sym_conv"]
+    assert np.array_equal(conv, d[key + "_sym_conv"])
+    assert np.array_equal(iters[ok], d[key + "_sym_iter"][ok]) and np.array_equal(hard[ok], d[key + "_sym_hard"][ok])
+    np.testing.assert_allclose(llr[ok], d[key + "_sym_llr"][ok], rtol=1e-7)
 
 
 def test_sum_product_f32_accuracy_is_measured_not_assumed(bp_golden):
@@ -163,9 +164,12 @@ def test_sum_product_f32_psi_domain_kernel_vs_f64():
             same = (got[1] == ref[1]) & (got[3] == ref[3]) & (got[0] == ref[0]).all(1)
             sel = ref[1] & same
             rel = np.abs(got[2][sel] - ref[2][sel]) / np.maximum(np.abs(ref[2][sel]), 1e-3)
-            stats[label] = (same.mean(), np.quantile(rel, 0.99))
-        print(f"\n[f32 {variant}] identical fraction / q99 rel. LLR error: psi {stats['psi']}, tanh {stats['tanh']}")
-        assert stats["psi"][0] >= 0.99 and stats["psi"][1] < 1e-4, stats
+            stats[label] = (same.mean(), np.quantile(rel, 0.99), np.quantile(rel, 0.999), rel.max())
+        print(f"\n[f32 {variant}] identical fraction / q99 / q99.9 / max rel. LLR error: psi {stats['psi']}, tanh {stats['tanh']}")
+        # The bound is a DISTRIBUTION, not a maximum (profiles/r2_sp_accuracy.json, 20 000 shots: q99 4.6e-5, q99.9
+        # 4.8e-3, max 5.8 relative on a posterior near zero after ~40 iterations): float32 trajectories of slowly converging shots
+        # drift like the min-sum ones do.  The float64 kernels carry the 1e-4 bar (test_sum_product_f64_vs_reference_golden).
+        assert stats["psi"][0] >= 0.99 and stats["psi"][1] < 1e-4 and stats["psi"][2] < 2e-2, stats
         assert stats["psi"][0] >= stats["tanh"][0] - 0.002 and stats["psi"][1] <= stats["tanh"][1], stats
 
 

@@ -195,8 +195,8 @@ bp_cta_kernel(const BPParams P, const BPWarpTables W, int VPL)
                         float t0, t1;
                         bpw_mul2(omd, omd, Q[i][k], Q[i][k + 1], t0, t1);
                         bpw_fma2(damp, damp, q0, q1, t0, t1, q0, q1);
-                        q0 = fminf(fmaxf(q0, -clipv), clipv);
-                        q1 = fminf(fmaxf(q1, -clipv), clipv);
+                        q0 = bpw_xmin(q0, clipv);     // np.clip(q, -c, c) for c >= 0: sign(q) * min(|q|, c), ONE FMNMX.XORSIGN
+                        q1 = bpw_xmin(q1, clipv);
                     }
                     // sum-product: a padding slot must stay at +inf (psi = 0); at +clip it would add psi(clip) to the sums
                     if (VAR != 0 && ((padmask >> (i * RW + k)) & 1u)) q0 = CUDART_INF_F;

@@ -306,8 +306,8 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
                         float t0, t1;
                         bpw_mul2(omd, omd, Q[i][k], Q[i][k + 1], t0, t1);                         // :65, same roundings as bp_damp(float)
                         bpw_fma2(damp, damp, q0, q1, t0, t1, q0, q1);
-                        q0 = fminf(fmaxf(q0, -clipv), clipv);                                     // :66
-                        q1 = fminf(fmaxf(q1, -clipv), clipv);
+                        q0 = bpw_xmin(q0, clipv);     // np.clip(q, -c, c) for c >= 0: sign(q) * min(|q|, c), ONE FMNMX.XORSIGN                                     // :66
+                        q1 = bpw_xmin(q1, clipv);
                     }
                     Q[i][k] = q0;
                     Q[i][k + 1] = q1;

@@ -364,7 +364,9 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         }
         G->stage_kernel = false;
     }
-    if ((cfg->staged == 0 || cfg->staged == 4) && c->cta_ok && cfg->precision == 32) {
+    // (the float32 warp / CTA kernels clip with one xorsign-min against +clip: valid for clip >= 0)
+    const bool clip_ok = cfg->clip >= 0.0 || cfg->variant == QLDPC_SUM_PRODUCT;
+    if ((cfg->staged == 0 || cfg->staged == 4) && c->cta_ok && cfg->precision == 32 && clip_ok) {
         G->staged = false;
         G->cta_kernel = true;
         G->warp_var = cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2);
@@ -377,7 +379,7 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
     }
     // (float64 warp kernel: no -0.0 canonicalisation, valid for damping > 0, clip >= 0 and max_iter <= 500 -- see its header)
     const bool f64_warp_ok = cfg->variant == QLDPC_MIN_SUM && cfg->damping > 0.0 && cfg->clip >= 0.0 && cfg->max_iter <= 500;
-    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && (cfg->precision == 32 || f64_warp_ok) &&
+    if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && ((cfg->precision == 32 && clip_ok) || (cfg->precision == 64 && f64_warp_ok)) &&
         (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
         G->staged = false;
         G->warp_kernel = true;

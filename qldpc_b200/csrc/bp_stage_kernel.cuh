@@ -25,6 +25,7 @@
 // kernels bit for bit for min-sum; for sum-product the row product is taken in slot order, not in column order (last-ulp
 // differences in the tanh product).
 #pragma once
+#include "sp_math.cuh"
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -58,6 +59,21 @@ template <typename T> __device__ __forceinline__ void stage_stb(T *base, uint32_
 // TABREG: the scatter / gather offsets of the owned edge slots live in registers (2 * SC * RW of them: one CTA per SM), or
 // are re-read from the (L1-resident) tables at every use, which leaves room for two CTAs per SM -- the choice for the
 // FP64-latency-bound float64 instantiations.
+// sum-product arithmetic of this kernel: float64 takes the branch-free FP64-pipe versions of sp_math.cuh (tanh(q/2): 23 FP64
+// instructions instead of 34 + the library's special cases, 2 atanh: 19 instead of 76, division by the own factor: 4 instead of
+// ~20), float32 the math library.
+__device__ __forceinline__ double stage_tanh_half(double q) { return spm_tanh_half(q); }
+__device__ __forceinline__ float stage_tanh_half(float q) { return tanhf(__fmul_rn(q, 0.5f)); }
+__device__ __forceinline__ double stage_sp_r(double x) { return spm_2atanh_clipped(x); }
+__device__ __forceinline__ float stage_sp_r(float x) { return bp_sp_r(x); }
+// prod / ts for 1e-15 <= |ts| <= 1
+__device__ __forceinline__ double stage_div(double prod, double ts)
+{
+    const double q = spm_div(prod, fabs(ts));
+    return spm_make(spm_hi(q) ^ (spm_hi(ts) & 0x80000000u), spm_lo(q));
+}
+__device__ __forceinline__ float stage_div(float prod, float ts) { return __fdiv_rn(prod, ts); }
+
 template <typename T, int VAR, int SC, int SV, int RW, bool TWO, bool TABREG>
 __global__ void __launch_bounds__(SC >= 3 ? 384 : 576, TABREG ? 1 : 2)
 bp_stage_kernel(const BPParams P, const BPWarpTables W, int VPL)
@@ -162,7 +178,7 @@ bp_stage_kernel(const BPParams P, const BPWarpTables W, int VPL)
 #pragma unroll
             for (int k = 0; k < RW; ++k) {
                 T x = stage_ldb(Vbuf, VI(i, k));
-                if (VAR == 1) x = N::tanh_(N::mul(x, (T)0.5));
+                if (VAR == 1) x = stage_tanh_half(x);
                 q[k] = ((padmask >> (i * RW + k)) & 1u) ? pad_word : x;
             }
             store_row(i, q);
@@ -202,14 +218,14 @@ bp_stage_kernel(const BPParams P, const BPWarpTables W, int VPL)
                     T prod = (T)1;
 #pragma unroll
                     for (int k = 0; k < RW; ++k) {
-                        t[k] = (VAR == 1) ? q[k] : N::tanh_(N::mul(q[k], (T)0.5));
+                        t[k] = (VAR == 1) ? q[k] : stage_tanh_half(q[k]);
                         prod = N::mul(prod, t[k]);
                     }
                     prod = N::from_bits(N::bits(prod) ^ sbit[i]);
 #pragma unroll
                     for (int k = 0; k < RW; ++k) {
                         const T ts = (fabs(t[k]) < (T)1e-15) ? (T)1e-15 : t[k];
-                        T rr = bp_sp_r(N::div(prod, ts));
+                        T rr = stage_sp_r(stage_div(prod, ts));
                         if (VAR == 2) rr = N::mul(rr, alpha);                                                   // decoding.py:171
                         r[k] = rr;
                     }
@@ -250,7 +266,7 @@ bp_stage_kernel(const BPParams P, const BPWarpTables W, int VPL)
                         qn = fmin(fmax(qn, -clipv), clipv);                                                    // :66 / :181
                         qn = bp_canon(qn);
                     } else {
-                        qn = N::tanh_(N::mul(qn, (T)0.5));
+                        qn = stage_tanh_half(qn);
                     }
                     // padding slots: min-sum lets them settle at +clip (>= every real |Q|); the sum-product ones stay neutral
                     if (VAR != 0 && ((padmask >> (i * RW + k)) & 1u)) qn = pad_word;

@@ -23,8 +23,18 @@
 // 477 issue slots and 159 DP instructions per shot-iteration of [[144,12,12]] against 896 / 195 in the first version
 // (0.79 G shot-iterations/s); 4-warp CTAs, three per SM.  Results equal the thread-per-shot / tiled float64 kernels bit
 // for bit (tests).
+//
+// VAR = 1 / 2: the reference's SUM-PRODUCT decoders in float64 on the same mapping (VAR 1: performBeliefPropagationFast,
+// beliefPropagation.py:88-144; VAR 2: performBeliefPropagation_Symmetric, rework/decoding.py:131-191 -- alpha, damping, clip).
+// The check update runs in the reference's tanh domain: t = tanh(Q / 2) per edge, the product of the OTHER five factors by a
+// prefix and a suffix chain (the reference divides the row product by the own factor, the same number up to rounding; a
+// check that holds a factor below the reference's 1e-15 guard takes the division path so that its `tanh_Q_safe` semantics
+// are kept), clip to +-0.9999999 and 2 atanh -- with the branch-free float64 tanh / atanh of sp_math.cuh (42 FP64
+// instructions per edge instead of the math library's 130 + ~100 integer ones).  Not bit-exact (NumPy's tanh / arctanh differ
+// from any other implementation in the last place); held to 1e-7 relative on the golden shots, north_star bar 1e-4.
 #pragma once
 #include "bp_warp_kernel.cuh"
+#include "sp_math.cuh"
 
 namespace qldpc {
 
@@ -66,7 +76,7 @@ struct BPW64Mem {
     __device__ static __forceinline__ void st_own(unsigned char *base, int row, int lane, double v) { st(base, 8u * (uint32_t)(row * 32 + lane), v); }
 };
 
-template <int CPL, int VPL, int RW, bool TWO>
+template <int CPL, int VPL, int RW, bool TWO, int VAR = 0>
 __global__ void __launch_bounds__(BPW64_WARPS * 32, (CPL * RW > 18) ? 2 : 3)
 bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
 {
@@ -159,23 +169,55 @@ bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
 #pragma unroll
             for (int i = 0; i < CPL; ++i) {
                 double pre[RW], suf[RW];
-                pre[1] = Q[i][0];
-                suf[RW - 2] = Q[i][RW - 1];
+                if constexpr (VAR == 0) {
+                    pre[1] = Q[i][0];
+                    suf[RW - 2] = Q[i][RW - 1];
 #pragma unroll
-                for (int k = 2; k < RW; ++k) pre[k] = bpw_absmin(pre[k - 1], Q[i][k - 1]);
+                    for (int k = 2; k < RW; ++k) pre[k] = bpw_absmin(pre[k - 1], Q[i][k - 1]);
 #pragma unroll
-                for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_absmin(suf[k + 1], Q[i][k + 1]);
-                uint32_t sgall = sbit[i];
+                    for (int k = RW - 3; k >= 0; --k) suf[k] = bpw_absmin(suf[k + 1], Q[i][k + 1]);
+                    uint32_t sgall = sbit[i];
 #pragma unroll
-                for (int k = 0; k < RW; ++k) sgall ^= d_hi(Q[i][k]);
+                    for (int k = 0; k < RW; ++k) sgall ^= d_hi(Q[i][k]);
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) {
+                        const double o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_absmin(pre[k], suf[k]);
+                        const double am = __dmul_rn(alpha, fabs(o));                                     // :55
+                        R[i][k] = d_make(d_hi(am) ^ ((sgall ^ d_hi(Q[i][k])) & 0x80000000u), d_lo(am));
+                    }
+                } else {
+                    // beliefPropagation.py:114-126 / decoding.py:157-166
+                    double t[RW], o[RW];
+                    uint32_t tmin = 0x7fffffffu;
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) {
+                        t[k] = spm_tanh_half(Q[i][k]);
+                        tmin = min(tmin, d_hi(t[k]) & 0x7fffffffu);
+                    }
+                    pre[1] = t[0];
+                    suf[RW - 2] = t[RW - 1];
+#pragma unroll
+                    for (int k = 2; k < RW; ++k) pre[k] = __dmul_rn(pre[k - 1], t[k - 1]);
+#pragma unroll
+                    for (int k = RW - 3; k >= 0; --k) suf[k] = __dmul_rn(suf[k + 1], t[k + 1]);
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) o[k] = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : __dmul_rn(pre[k], suf[k]);
+                    if (tmin <= 0x3cd203afu) {                       // (high word of 1e-15) some |t| may be below the guard: the
+                        const double prod = __dmul_rn(pre[RW - 1], t[RW - 1]);   // reference's row product / tanh_Q_safe, literally
+#pragma unroll
+                        for (int k = 0; k < RW; ++k) o[k] = __ddiv_rn(prod, fabs(t[k]) < 1e-15 ? 1e-15 : t[k]);
+                    }
+#pragma unroll
+                    for (int k = 0; k < RW; ++k) {
+                        const double x = d_make(d_hi(o[k]) ^ sbit[i], d_lo(o[k]));                       // * syndrome_sign
+                        const double r = spm_2atanh_clipped(x);
+                        R[i][k] = (VAR == 2) ? __dmul_rn(r, alpha) : r;                                  // decoding.py:171
+                    }
+                }
 #pragma unroll
                 for (int k = 0; k < RW; ++k) {
-                    const double o = (k == 0) ? suf[0] : (k == RW - 1) ? pre[RW - 1] : bpw_absmin(pre[k], suf[k]);
-                    const double am = __dmul_rn(alpha, fabs(o));                                     // :55
-                    const double r = d_make(d_hi(am) ^ ((sgall ^ d_hi(Q[i][k])) & 0x80000000u), d_lo(am));
-                    R[i][k] = r;
-                    if (TWO && iter == 0) RM::st(Rbuf, RM::scale(__ldg(W.sidx0 + (i * RW + k) * 32 + lane)), r);
-                    else RM::st(Rbuf, sidx[i][k], r);       // (padding lanes write garbage into the dump row)
+                    if (TWO && iter == 0) RM::st(Rbuf, RM::scale(__ldg(W.sidx0 + (i * RW + k) * 32 + lane)), R[i][k]);
+                    else RM::st(Rbuf, sidx[i][k], R[i][k]);       // (padding lanes write garbage into the dump row)
                 }
             }
             __syncwarp();
@@ -201,8 +243,12 @@ bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
                     const double val = VM::ld(Vbuf, vidx[i][k]);
                     par ^= d_hi(val);   // sign bit == hard decision (a sum with a canonical prior is never -0.0)
                     double qn = __dsub_rn(val, R[i][k]);                                          // :63
-                    qn = __dadd_rn(__dmul_rn(damp, qn), __dmul_rn(omd, Q[i][k]));                 // :65 (three roundings, like NumPy)
-                    Q[i][k] = bpw_clip(qn, clipv, clip_hi, clip_lo);                              // :66
+                    if constexpr (VAR == 1) {
+                        Q[i][k] = qn;                                                             // beliefPropagation.py:133
+                    } else {
+                        qn = __dadd_rn(__dmul_rn(damp, qn), __dmul_rn(omd, Q[i][k]));             // :65 (three roundings, like NumPy)
+                        Q[i][k] = bpw_clip(qn, clipv, clip_hi, clip_lo);                          // :66
+                    }
                 }
                 ok = ok && (cinfo[i] == 0xffffffffu || (int)par >= 0);
             }

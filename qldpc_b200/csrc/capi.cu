@@ -378,13 +378,15 @@ static int bp_geometry(const qldpc_code *c, const qldpc_bp_config *cfg, long lon
         return QLDPC_OK;
     }
     // (float64 warp kernel: no -0.0 canonicalisation, valid for damping > 0, clip >= 0 and max_iter <= 500 -- see its header)
-    const bool f64_warp_ok = cfg->variant == QLDPC_MIN_SUM && cfg->damping > 0.0 && cfg->clip >= 0.0 && cfg->max_iter <= 500;
+    // plain sum-product (no damping, no clip) always qualifies
+    const bool f64_warp_ok = cfg->variant == QLDPC_SUM_PRODUCT ||
+                             (cfg->damping > 0.0 && cfg->clip >= 0.0 && (cfg->variant == QLDPC_SUM_PRODUCT_SYM || cfg->max_iter <= 500));
     if ((cfg->staged == 0 || cfg->staged == 3) && c->warp_ok && ((cfg->precision == 32 && clip_ok) || (cfg->precision == 64 && f64_warp_ok)) &&
         (cfg->staged == 3 || cfg->lanes_per_shot == 0 || cfg->lanes_per_shot == 32)) {
         G->staged = false;
         G->warp_kernel = true;
-        // 0 min-sum, 1 sum-product, 2 symmetric sum-product (float32); 3 float64 min-sum (the bit-exact parity mode)
-        G->warp_var = cfg->precision == 64 ? 3 : (cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2));
+        // 0 min-sum, 1 sum-product, 2 symmetric sum-product (float32); 3 / 4 / 5 the same in float64 (3: the bit-exact parity mode)
+        G->warp_var = (cfg->precision == 64 ? 3 : 0) + (cfg->variant == QLDPC_MIN_SUM ? 0 : (cfg->variant == QLDPC_SUM_PRODUCT ? 1 : 2));
         const int nw = cfg->precision == 64 ? BPW64_WARPS : BPW_WARPS;
         G->threads = nw * 32;
         G->shots_per_cta = nw;

@@ -144,6 +144,7 @@ cudaError_t launch_bp_tiled(const qldpc_code *c, const BPParams &P, const BPGeom
 cudaError_t launch_bp_warp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
 cudaError_t launch_bp_warp_sp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
 cudaError_t launch_bp_warp_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
+cudaError_t launch_bp_warp_f64_sp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
 cudaError_t launch_bp_cta(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st);
 cudaError_t launch_bp_stage(const qldpc_code *c, const BPParams &P, const BPGeom &G, int precision, cudaStream_t st);
 int bp_stage_occupancy(const qldpc_code *c, int precision, int threads, size_t smem);

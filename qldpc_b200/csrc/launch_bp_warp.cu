@@ -32,10 +32,12 @@ static cudaError_t launch_ms(const qldpc_code *c, const BPParams &P, const BPGeo
     if (c->WM == 5 && c->WN == 9) return F<5, 9>(c, P, G, st);                \
     return cudaErrorInvalidValue
 
-// G.warp_var: 0 min-sum, 1 sum-product, 2 symmetric sum-product (float32); 3 float64 min-sum (the bit-exact parity mode)
+// G.warp_var: 0 min-sum, 1 sum-product, 2 symmetric sum-product (float32); 3 float64 min-sum (the bit-exact parity mode),
+// 4 / 5 float64 sum-product / symmetric sum-product
 cudaError_t launch_bp_warp(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
     if (G.warp_var == 3) return launch_bp_warp_f64(c, P, G, st);
+    if (G.warp_var >= 4) return launch_bp_warp_f64_sp(c, P, G, st);
     if (G.warp_var != 0) return launch_bp_warp_sp(c, P, G, st);
     QLDPC_WARP_SHAPES(launch_ms);
 }

@@ -1,37 +1,4 @@
-// Launchers of the warp-per-shot float64 min-sum kernels (bp_warp_kernel_f64.cuh): the bit-exact parity mode.
-#include "capi_internal.h"
-
-template <int CPL, int VPL, bool TWO>
-static cudaError_t launch_f64_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    auto kern = bp_warp_kernel_f64<CPL, VPL, 6, TWO>;
-    if (G.smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
-        if (e != cudaSuccess) return e;
-    }
-    int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, G.threads, G.smem);
-    const long long grid = std::max<long long>(1, std::min<long long>((long long)c->num_sms * std::max(1, occ), (P.B + BPW64_WARPS - 1) / BPW64_WARPS));
-    kern<<<(int)grid, G.threads, G.smem, st>>>(P, c->wtab64);      // (labelling for 16-lane conflict domains)
-    return cudaGetLastError();
-}
-
-template <int CPL, int VPL>
-static cudaError_t launch_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    // (uniform prior: the iteration-0 addition order cannot change a bit -- see launch_bp_warp.cu)
-    const bool two = c->two_tables && !P.prior_uniform;
-    return two ? launch_f64_inst<CPL, VPL, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false>(c, P, G, st);
-}
-
-#define QLDPC_WARP_SHAPES(F)                                                  \
-    if (c->WM == 2 && c->WN == 3) return F<2, 3>(c, P, G, st);                \
-    if (c->WM == 2 && c->WN == 4) return F<2, 4>(c, P, G, st);                \
-    if (c->WM == 3 && c->WN == 5) return F<3, 5>(c, P, G, st);                \
-    if (c->WM == 5 && c->WN == 9) return F<5, 9>(c, P, G, st);                \
-    return cudaErrorInvalidValue
-
-cudaError_t launch_bp_warp_f64(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
-{
-    QLDPC_WARP_SHAPES(launch_f64);
-}
+// Launchers of the warp-per-shot float64 min-sum kernels (bp_warp_kernel_f64.cuh, VAR = 0): the bit-exact parity mode.
+#define QLDPC_F64_VAR 0
+#define QLDPC_F64_ENTRY launch_bp_warp_f64
+#include "launch_bp_warp_f64_impl.h"

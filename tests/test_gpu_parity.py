@@ -173,6 +173,46 @@ def test_sum_product_f32_psi_domain_kernel_vs_f64():
         assert stats["psi"][0] >= stats["tanh"][0] - 0.002 and stats["psi"][1] <= stats["tanh"][1], stats
 
 
+@pytest.mark.parametrize("stem,p", [("[[72, 12, 6]]", 0.06), ("[[90, 8, 10]]", 0.05), ("[[108, 8, 10]]", 0.05),
+                                    ("[[144, 12, 12]]", 0.05), ("[[288, 12, 18]]", 0.07)])
+def test_sum_product_f64_warp_kernel_vs_tiled_kernel(stem, p):
+    """The warp-per-shot float64 sum-product kernels (bp_warp_kernel_f64, VAR 1 / 2: own tanh / atanh, leave-one-out products)
+    against the tiled float64 kernel (math-library tanh / atanh, the reference's division by the own factor): same flags,
+    exit iterations and hard decisions, LLRs within 1e-9 relative on the shots that converge early and 1e-4 on all -- uniform priors, non-uniform
+    priors (the two-table instantiation on the Fortran-ordered Hx) and a prior of exactly 0, which puts tanh(Q/2) = 0 factors
+    into iteration 0 and sends their checks through the reference's `tanh_Q_safe` division path."""
+    H, _ = load_code_file(stem)
+    n = H.shape[1]
+    rng = np.random.default_rng(7)
+    B = 1501
+    synd = _synd(H, (rng.random((B, n)) < p).astype(np.uint8))
+    pri_nu = np.log((1 - p) / p) * rng.uniform(0.6, 1.4, n)
+    pri_zero = pri_nu.copy()
+    pri_zero[rng.choice(n, 3, replace=False)] = 0.0
+    for variant, kw in (("sum_product", {}), ("sum_product_sym", dict(alpha=0.9, damping=0.8, clip=20.0))):
+        code = _code(H, variant)
+        for prior in (_prior(p, n), pri_nu, pri_zero):
+            assert code.geometry(code.config(variant, 40, precision=64, **kw))["kernel"] == "warp_per_shot"
+            assert code.geometry(code.config(variant, 40, precision=64, lanes_per_shot=8, **kw))["kernel"] == "tiled"
+            got = code.bp_decode_batch(synd, prior, variant, 40, precision=64, **kw)
+            ref = code.bp_decode_batch(synd, prior, variant, 40, precision=64, lanes_per_shot=8, **kw)
+            same = (got[1] == ref[1]) & (got[3] == ref[3]) & (got[0] == ref[0]).all(1)
+            assert same.mean() >= 0.999, (variant, same.mean())
+            sel = same & ref[1]
+            assert sel.sum() > B // 3
+            rel = (np.abs(got[2] - ref[2]) / np.maximum(np.abs(ref[2]), 1e-3)).max(1)
+            early = sel & (ref[3] < 12)
+            worst = int(np.argmax(np.where(sel, rel, 0)))
+            print(f"\n[f64 {variant} warp vs tiled, {stem}] identical {same.mean():.4f}; max rel. LLR error: exit iteration < 12 "
+                  f"{rel[early].max():.2e}, all {rel[sel].max():.2e} (a shot that exits at iteration {ref[3][worst]}), q99.9 {np.quantile(rel[sel], 0.999):.2e}")
+            # Undamped sum-product amplifies a last-place difference by ~2x per iteration on the shots that wander before they
+            # converge (measured maxima by exit iteration: < 5: 2e-11, < 10: 3e-10, < 20: 1e-7, < 30: 1e-6, < 40: 5.5e-5 -- a [[108,8,10]]
+            # shot that exits at iteration 39; flags, iterations and hard decisions identical on every shot): the early shots carry
+            # the tight bar, every shot the north-star one.
+            print("   by exit iteration (<5, <10, <20, <30, <40):", ["%.1e" % rel[sel & (ref[3] >= a) & (ref[3] < b)].max(initial=0) for a, b in ((0, 5), (5, 10), (10, 20), (20, 30), (30, 40))])
+            assert rel[early].max() < 1e-9 and rel[sel].max() < 1e-4 and np.quantile(rel[sel], 0.99) < 1e-6, (variant, rel[sel].max())
+
+
 def test_non_uniform_prior_and_loop_version(bp_golden):
     d, meta = bp_golden
     H, _ = load_code_file("[[72, 12, 6]]")
@@ -954,6 +994,6 @@ def test_cta_staged_kernel_vs_thread_per_shot_staged_kernel(schedule):
         sel = ref[1] & same
         rel = np.abs(got[2][sel] - ref[2][sel]) / np.maximum(np.abs(ref[2][sel]), 1e-3)
         print(f"\n[cta_staged f64 {variant}] identical {same.mean():.4f}, max rel. LLR error {rel.max():.2e}")
-        assert same.mean() >= 0.99 and rel.max() < 1e-9, (variant, same.mean(), rel.max())
+        assert same.mean() >= 0.99 and rel.max() < 1e-7, (variant, same.mean(), rel.max())      # (own tanh / atanh vs the math library)
         got32 = code.bp_decode_batch(synd, prior, variant, 30, precision=32, staged=5, **kw)       # float32, tanh domain
         assert (got32[1] == ref[1]).mean() > 0.9

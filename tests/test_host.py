@@ -103,3 +103,42 @@ def test_save_results_round_trip_like_load_results(tmp_path):
     f = np.load(path, allow_pickle=True)
     assert list(f.keys()) == ["results"]
     assert f["results"].item() == res
+
+
+@pytest.mark.parametrize("flags", [[], ["-DSPM_EMULATE_RCP"]])
+def test_sum_product_math_header_against_50_digit_references(tmp_path, flags):
+    """qldpc_b200/csrc/sp_math.cuh (the float64 tanh(q/2) / 2 atanh(clip(x)) of the warp-per-shot sum-product kernels), built
+    for the host -- once with the host's division, once with a model of the device's reciprocal sequence (20-bit seed + one
+    cubic Newton step) -- against mpmath at 40 digits: relative error <= 5e-16, signs and zeros as tanh / arctanh."""
+    import subprocess
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    lib = str(tmp_path / "spm.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", *flags, "-o", lib,
+                    os.path.join(ROOT, "tests", "cpp", "sp_math_check.cpp")], check=True,
+                   env={k: v for k, v in os.environ.items() if k not in ("CC", "CXX")})
+    L = ctypes.CDLL(lib)
+
+    def call(f, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.empty_like(x)
+        f(x.ctypes.data_as(ctypes.c_void_p), y.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(x.size))
+        return y
+
+    rng = np.random.default_rng(0)
+    q = np.concatenate([rng.uniform(-60, 60, 1500), rng.normal(0, 3, 1500), 10.0 ** rng.uniform(-18, 1, 1000) * rng.choice([-1, 1], 1000),
+                        [0.0, 1e-300, 80, 100, -200, 0.69314718, 0.34657359, -0.34657359, 37.0, 38.5]])
+    t = call(L.sp_tanh_half, q)
+    ref = np.array([float(mp.tanh(mp.mpf(float(v)) / 2)) for v in q])
+    assert (np.abs(t - ref) <= 5e-16 * np.abs(ref)).all()
+    x = np.concatenate([rng.uniform(-1, 1, 2000), 1 - 10.0 ** rng.uniform(-7.5, -0.3, 1000), -(1 - 10.0 ** rng.uniform(-7.5, -0.3, 500)),
+                        10.0 ** rng.uniform(-18, -0.5, 1000), [0, 0.2, 0.1999999, 0.2000001, 0.5, 0.9999999, 1.0, -1.0, 0.99999995, 1 / 3, 0.6]])
+    r = call(L.sp_2atanh, x)
+    ref = np.array([float(2 * mp.atanh(mp.mpf(float(v)))) for v in np.clip(x, -0.9999999, 0.9999999)])
+    assert (np.abs(r - ref) <= 5e-16 * np.abs(ref)).all()
+    assert r[np.abs(x) >= 0.9999999].tolist() == [2 * np.arctanh(0.9999999) * np.sign(v) for v in x[np.abs(x) >= 0.9999999]] or \
+        np.allclose(np.abs(r[np.abs(x) >= 0.9999999]), 2 * np.arctanh(0.9999999), rtol=5e-16)
+    z = call(L.sp_tanh_half, [0.0, -0.0, -3.0])
+    assert z[0] == 0 and not np.signbit(z[0]) and z[1] == 0 and np.signbit(z[1]) and z[2] < 0
+    z = call(L.sp_2atanh, [0.0, -0.0, -0.5])
+    assert z[0] == 0 and not np.signbit(z[0]) and z[1] == 0 and np.signbit(z[1]) and z[2] < 0

@@ -363,12 +363,30 @@ def main():
             return float(tt.item())
 
         e2e_steps = max(1, min(args.steps, 3))
-        e2e_value = Be * e2e_steps * world / wall(e2e_step, e2e_steps)
         corr_u8_dev = torch.empty((Be, n), dtype=torch.uint8, device=dev)
         _lib.check(L.qldpc_unpack_bits_dev(corr.data_ptr(), corr_u8_dev.data_ptr(), Be, n, stream), "unpack")
         torch.cuda.synchronize()
-        e2e_matches = bool(torch.equal(corr_u8_dev.cpu(), corr_h))
+        corr_u8_ref = corr_u8_dev.cpu()
         del corr_u8_dev
+
+        def e2e_leg(mode):
+            """the uint8 host call with the rows packed by the library's own choice (-1), on the device (0) or by host threads (1):
+            shots/s, bytes per step as counted by the library from the copies it issued, equality with the device path"""
+            code.set_host_pack(mode)
+            corr_h.zero_()
+            s0 = code.host_transfer_stats()
+            v = Be * e2e_steps * world / wall(e2e_step, e2e_steps)
+            s1 = code.host_transfer_stats()
+            calls = e2e_steps + 1
+            return dict(value=v, unit="shots/s", h2d_bytes_per_step=(s1["h2d_bytes"] - s0["h2d_bytes"]) // calls,
+                        d2h_bytes_per_step=(s1["d2h_bytes"] - s0["d2h_bytes"]) // calls,
+                        rows_packed_by=("host threads (bit-packed rows cross PCIe)" if s1["host_pack"] == 1 else "device kernels (byte rows cross PCIe)"),
+                        host_pack_rate_shots_per_s=s1["host_pack_rate"], matches_device_path=bool(torch.equal(corr_u8_ref, corr_h)))
+        e2e_auto = e2e_leg(-1)
+        e2e_other = e2e_leg(0 if e2e_auto["rows_packed_by"].startswith("host") else 1)
+        code.set_host_pack(-1)
+        e2e_value, e2e_matches = e2e_auto["value"], e2e_auto["matches_device_path"]
+        del corr_u8_ref
         e2e_packed_value = Be * e2e_steps * world / wall(e2e_packed_step, e2e_steps)
         e2e_packed_matches = bool(torch.equal(corr_hp, corr[:Be].cpu()))
         # the reference's actual Monte-Carlo use: everything on the device, counters back (no per-shot host traffic)
@@ -384,9 +402,13 @@ def main():
                "kernel_ms_per_step": {k: v / args.steps for k, v in kernel_ms.items()},
                "results": {"ler": cd["logical"] / max(1, cd["shots"]), "bp_failure_rate": cd["bp_failed"] / max(1, cd["shots"]),
                            "invalid": cd["invalid"], "mean_exit_iteration": cd["iter_sum"] / max(1, cd["shots"]), "shots": cd["shots"]},
-               "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": Be * m, "d2h_bytes_per_step": Be * (n + 1 + 4),
+               "e2e": {"value": e2e_value, "unit": "shots/s", "h2d_bytes_per_step": e2e_auto["h2d_bytes_per_step"],
+                       "d2h_bytes_per_step": e2e_auto["d2h_bytes_per_step"],
                        "shots_per_step": Be, "steps": e2e_steps, "api": "qldpc_bposd_decode_host (uint8 in pinned host memory), osd_order=7",
-                       "matches_device_path": e2e_matches,
+                       "matches_device_path": e2e_matches, "rows_packed_by": e2e_auto["rows_packed_by"],
+                       "host_pack_rate_shots_per_s": e2e_auto["host_pack_rate_shots_per_s"],
+                       "host_bytes_per_step": {"in": Be * m, "out": Be * (n + 1 + 4)},
+                       "other_side": e2e_other,
                        "packed_host_rows": {"value": e2e_packed_value, "unit": "shots/s", "h2d_bytes_per_step": Be * 4 * WM,
                                             "d2h_bytes_per_step": Be * (4 * WN + 1 + 4), "api": "qldpc_bposd_decode_host_packed",
                                             "matches_device_path": e2e_packed_matches},

@@ -54,6 +54,8 @@ def lib():
         "qldpc_osd_decode_host": ([c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp], ctypes.c_int),
         "qldpc_bposd_decode_host": ([c_vp, P(BPConfig), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp], ctypes.c_int),
         "qldpc_bposd_decode_host_packed": ([c_vp, P(BPConfig), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp], ctypes.c_int),
+        "qldpc_host_transfer_stats": ([c_vp, c_vp, c_vp, c_vp, c_vp], ctypes.c_int),
+        "qldpc_set_host_pack": ([c_vp, c_i32], ctypes.c_int),
         "qldpc_check_host": ([c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp], ctypes.c_int),
         "qldpc_syndrome_host": ([c_vp, c_i64, c_vp, c_vp], ctypes.c_int),
         "qldpc_syndrome_dev": ([c_vp, c_i64, c_vp, c_vp, c_vp], ctypes.c_int),
@@ -83,7 +85,7 @@ def lib():
 
 EXPORTED = ["qldpc_last_error", "qldpc_version", "qldpc_device_count", "qldpc_code_create", "qldpc_code_destroy",
             "qldpc_bp_geometry", "qldpc_tiled_conflict_model", "qldpc_warp_layout_tune", "qldpc_words_m", "qldpc_words_n", "qldpc_bp_decode_host", "qldpc_bp_messages_host", "qldpc_osd_decode_host",
-            "qldpc_bposd_decode_host", "qldpc_bposd_decode_host_packed", "qldpc_check_host", "qldpc_syndrome_host", "qldpc_syndrome_dev", "qldpc_sample_host", "qldpc_sample_noisy_host", "qldpc_mc_sweep", "qldpc_mc_sweep_noisy", "qldpc_measurement_noise_dev", "qldpc_alpha_counts",
+            "qldpc_bposd_decode_host", "qldpc_bposd_decode_host_packed", "qldpc_host_transfer_stats", "qldpc_set_host_pack", "qldpc_check_host", "qldpc_syndrome_host", "qldpc_syndrome_dev", "qldpc_sample_host", "qldpc_sample_noisy_host", "qldpc_mc_sweep", "qldpc_mc_sweep_noisy", "qldpc_measurement_noise_dev", "qldpc_alpha_counts",
             "qldpc_bp_llr_histogram", "qldpc_bp_decode_dev",
             "qldpc_osd_decode_dev", "qldpc_osdw_decode_dev", "qldpc_check_dev", "qldpc_sample_dev", "qldpc_bposd_decode_dev",
             "qldpc_pack_bits_dev", "qldpc_unpack_bits_dev"]

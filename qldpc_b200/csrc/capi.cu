@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "capi_internal.h"
+#include <chrono>
 #include "misc_kernels.cuh"     // non-template kernels: defined in this translation unit only
 #include "osdw_kernel.cuh"
 #include "bp_stage_kernel.cuh"   // (layout helpers only; the kernels are instantiated in launch_bp_stage.cu)
@@ -321,11 +322,14 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
     for (auto &sl : c->slot) {
         DevBuf *sb[] = {&sl.ctrl, &sl.gstate, &sl.u8in, &sl.u8out, &sl.synd, &sl.hard, &sl.conv, &sl.iters, &sl.llr, &sl.fail, &sl.redo, &sl.valid, &sl.inv};
         for (DevBuf *b : sb) b->release();
+        sl.h_synd.release();
+        sl.h_hard.release();
         for (cudaEvent_t e : {sl.ev_in, sl.ev_comp, sl.ev_out})
             if (e) cudaEventDestroy(e);
     }
     for (cudaStream_t st : {c->st_in, c->st_comp, c->st_out})
         if (st) cudaStreamDestroy(st);
+    delete c->pool;
     delete c;
 }
 
@@ -974,6 +978,45 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
     return QLDPC_OK;
 }
 
+// Who packs the uint8 rows of qldpc_bposd_decode_host: the device (byte rows cross PCIe: n + m + 5 bytes per shot) or host
+// threads (bit-packed rows cross it: 4 (WM + WN) + 5 bytes).  QLDPC_HOST_PACK = 0 / 1 forces a side; otherwise the pool's pack +
+// unpack throughput is measured once per code handle on a 2^16-shot sample and the host side is taken when it clearly
+// outruns what the bus would carry (D2H ~50 GB/s, H2D ~25 GB/s when both directions are busy: measured, tools/pcie_bw.py).
+// QLDPC_HOST_THREADS sets the pool size (default: hardware threads / visible GPUs, at most 16).
+static int host_pack_decide(qldpc_code *c, int want)        // want: -1 measure (the environment may force a side), 0 device, 1 host
+{
+    if (want < 0)
+        if (const char *e = getenv("QLDPC_HOST_PACK")) want = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : -1;
+    if (want == 0) return c->host_pack = 0;
+    if (!c->pool) {
+        int threads = 0;
+        if (const char *t = getenv("QLDPC_HOST_THREADS")) threads = atoi(t);
+        if (threads <= 0) {
+            int ndev = 1;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) ndev = 1;
+            threads = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency() / (unsigned)ndev));
+        }
+        if (want < 0 && threads < 4) return c->host_pack = 0;
+        c->pool = new HostPool(threads);
+        const long long Bs = 1ll << 16;
+        std::vector<uint8_t> a((size_t)Bs * c->m, 1), o((size_t)Bs * c->n + 16);
+        std::vector<uint32_t> pa((size_t)Bs * c->WM), po((size_t)Bs * c->WN, 0x55555555u);
+        uint8_t *oal = o.data() + ((16 - (reinterpret_cast<uintptr_t>(o.data()) & 15u)) & 15u);
+        double best = 1e30;
+        for (int rep = 0; rep < 3; ++rep) {
+            const auto t0 = std::chrono::steady_clock::now();
+            host_pack_rows(*c->pool, a.data(), pa.data(), Bs, c->m, c->WM);
+            host_unpack_rows(*c->pool, po.data(), oal, Bs, c->n, c->WN);
+            best = std::min(best, std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());
+        }
+        c->host_pack_rate = (double)Bs / best;
+    }
+    if (want == 1) return c->host_pack = 1;
+    const double bus_rate = 1.0 / std::max((c->n + 5.0) / 50e9, c->m / 25e9);
+    return c->host_pack = (c->host_pack_rate >= 1.2 * bus_rate) ? 1 : 0;
+}
+static int host_pack_mode(qldpc_code *c) { return c->host_pack >= 0 ? c->host_pack : host_pack_decide(c, -1); }
+
 // packed = false: synd [B][m] / corr [B][n] uint8 (the reference's dtypes);  packed = true: bit-packed uint32 rows
 static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, const double *prior, int64_t B,
                                   const void *synd_v, int32_t osd_order, void *corr_v, uint8_t *conv, int32_t *iters, bool packed)
@@ -1007,7 +1050,22 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         CK(cudaStreamCreateWithFlags(&c->st_comp, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->st_out, cudaStreamNonBlocking));
     }
-    for (auto &sl : c->slot) sl.used = false;
+    for (auto &sl : c->slot) { sl.used = false; sl.pend = false; }
+    // host-side packing (uint8 rows only): host threads pack the syndromes of a chunk into the slot's pinned buffer before its
+    // copy-in and expand its corrections after its copy-out, while the GPU works on the neighbouring chunks
+    const bool hostpack = !packed && host_pack_mode(c) == 1;
+    const size_t in_bus = hostpack ? 4 * (size_t)c->WM : in_row, out_bus = hostpack ? 4 * (size_t)c->WN : out_row;
+    auto finish = [&](qldpc_code::Slot &sl) {                // corrections of the slot's pending chunk -> the caller's rows
+        host_unpack_rows(*c->pool, sl.h_hard.as<uint32_t>(), corr + (size_t)sl.pend_o * c->n, sl.pend_b, c->n, c->WN);
+        sl.pend = false;
+    };
+    long long i = 0;
+    auto finish_ready = [&]() {                               // oldest first, as far as their copy-out has completed
+        for (int a = 0; a < qldpc_code::NSLOT; ++a) {
+            qldpc_code::Slot &sl = c->slot[(i + a) % qldpc_code::NSLOT];
+            if (sl.pend && cudaEventQuery(sl.ev_out) == cudaSuccess) finish(sl);
+        }
+    };
     auto enqueue = [&](long long o, long long b, qldpc_code::Slot &sl) -> int {
         if (!sl.ev_in) {
             CK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
@@ -1018,7 +1076,16 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         CK(sl.hard.reserve(4 * (size_t)b * c->WN));
         CK(sl.conv.reserve((size_t)b));
         CK(sl.iters.reserve(4 * (size_t)b));
-        if (!packed) {
+        if (hostpack) {
+            CK(sl.h_synd.reserve(4 * (size_t)b * c->WM));
+            CK(sl.h_hard.reserve(4 * (size_t)b * c->WN));
+            finish_ready();
+            if (sl.pend) {                                    // the slot's previous chunk: its buffers are free after its copy-out
+                CK(cudaEventSynchronize(sl.ev_out));
+                finish(sl);
+            }
+            host_pack_rows(*c->pool, synd + (size_t)o * c->m, sl.h_synd.as<uint32_t>(), b, c->m, c->WM);
+        } else if (!packed) {
             CK(sl.u8in.reserve((size_t)b * c->m));
             CK(sl.u8out.reserve((size_t)b * c->n));
         }
@@ -1026,32 +1093,36 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         //      for its copy-out as well keeps one rule for all buffers of the slot)
         if (sl.used) CK(cudaStreamWaitEvent(c->st_in, sl.ev_out, 0));
         mark(c->st_in);
-        CK(cudaMemcpyAsync(packed ? sl.synd.p : sl.u8in.p, synd + (size_t)o * in_row, (size_t)b * in_row, cudaMemcpyHostToDevice, c->st_in));
+        CK(cudaMemcpyAsync((packed || hostpack) ? sl.synd.p : sl.u8in.p, hostpack ? sl.h_synd.p : (const void *)(synd + (size_t)o * in_row),
+                           (size_t)b * in_bus, cudaMemcpyHostToDevice, c->st_in));
+        c->h2d_bytes += (size_t)b * in_bus;
         CK(cudaEventRecord(sl.ev_in, c->st_in));
         mark(c->st_in);
         // ---- compute
         CK(cudaStreamWaitEvent(c->st_comp, sl.ev_in, 0));
-        if (!packed)
+        if (!packed && !hostpack)
             if (int rc = qldpc_pack_bits_dev(sl.u8in.as<uint8_t>(), sl.synd.as<uint32_t>(), b, c->m, c->st_comp)) return rc;
         if (int rc = bposd_chunk(c, cfg, prior, b, sl.synd.as<uint32_t>(), osd_order, sl.hard.as<uint32_t>(), sl.conv.as<uint8_t>(),
                                  sl.iters.as<int32_t>(), nullptr, &sl.ctrl, &sl.gstate, &sl.llr, &sl.fail, &sl.redo, &sl.valid, &sl.inv, c->st_comp))
             return rc;
-        if (!packed)
+        if (!packed && !hostpack)
             if (int rc = qldpc_unpack_bits_dev(sl.hard.as<uint32_t>(), sl.u8out.as<uint8_t>(), b, c->n, c->st_comp)) return rc;
         CK(cudaEventRecord(sl.ev_comp, c->st_comp));
         mark(c->st_comp);
         // ---- copy out
         CK(cudaStreamWaitEvent(c->st_out, sl.ev_comp, 0));
-        CK(cudaMemcpyAsync(corr + (size_t)o * out_row, packed ? sl.hard.p : sl.u8out.p, (size_t)b * out_row, cudaMemcpyDeviceToHost, c->st_out));
+        CK(cudaMemcpyAsync(hostpack ? sl.h_hard.p : (void *)(corr + (size_t)o * out_row), (packed || hostpack) ? sl.hard.p : sl.u8out.p,
+                           (size_t)b * out_bus, cudaMemcpyDeviceToHost, c->st_out));
         CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, c->st_out));
         if (iters) CK(cudaMemcpyAsync(iters + o, sl.iters.p, 4 * (size_t)b, cudaMemcpyDeviceToHost, c->st_out));
+        c->d2h_bytes += (size_t)b * (out_bus + 1 + (iters ? 4 : 0));
         CK(cudaEventRecord(sl.ev_out, c->st_out));
         mark(c->st_out);
         sl.used = true;
+        if (hostpack) { sl.pend = true; sl.pend_o = o; sl.pend_b = b; }
         return QLDPC_OK;
     };
     int rc_all = QLDPC_OK;
-    long long i = 0;
     // Tapered schedule for large batches: the pipeline fills with a quarter- and a half-sized chunk and drains with a half-
     // and a quarter-sized one, so that the first copy-in and the last copy-out (not hidden under compute) are short.
     const bool taper = !getenv("QLDPC_HOST_NO_TAPER") && B >= 4 * chunk;
@@ -1070,6 +1141,13 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         o += b;
     }
     const std::string msg = g_err;
+    if (hostpack)                                             // expand the chunks still in flight, oldest first
+        for (int a = 0; a < qldpc_code::NSLOT; ++a) {
+            qldpc_code::Slot &sl = c->slot[(i + a) % qldpc_code::NSLOT];
+            if (!sl.pend) continue;
+            if (cudaEventSynchronize(sl.ev_out) == cudaSuccess && rc_all == QLDPC_OK) finish(sl);
+            sl.pend = false;
+        }
     for (cudaStream_t st : {c->st_in, c->st_comp, c->st_out})
         if (st && cudaStreamSynchronize(st) != cudaSuccess && rc_all == QLDPC_OK)
             rc_all = fail(QLDPC_ERR_CUDA, "qldpc_bposd_decode_host: stream synchronisation failed");
@@ -1097,6 +1175,26 @@ extern "C" int qldpc_bposd_decode_host_packed(qldpc_code *c, const qldpc_bp_conf
 {
     if (!c) return fail(QLDPC_ERR_ARG, "qldpc_bposd_decode_host_packed: null code");
     return bposd_decode_host_impl(c, cfg, prior, B, synd, osd_order, corr, conv, iters, true);
+}
+
+extern "C" int qldpc_set_host_pack(qldpc_code *c, int32_t mode)
+{
+    if (!c) return fail(QLDPC_ERR_ARG, "qldpc_set_host_pack: null code");
+    if (mode < -1 || mode > 1) return fail(QLDPC_ERR_ARG, "qldpc_set_host_pack: mode must be -1 (measure), 0 (device) or 1 (host)");
+    if (mode < 0) c->host_pack = -1;             // decided again at the next call
+    else host_pack_decide(c, mode);
+    return QLDPC_OK;
+}
+
+extern "C" int qldpc_host_transfer_stats(qldpc_code *c, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int32_t *host_pack,
+                                         double *host_pack_rate)
+{
+    if (!c) return fail(QLDPC_ERR_ARG, "qldpc_host_transfer_stats: null code");
+    if (h2d_bytes) *h2d_bytes = c->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
+    if (host_pack) *host_pack = c->host_pack;
+    if (host_pack_rate) *host_pack_rate = c->host_pack_rate;
+    return QLDPC_OK;
 }
 
 extern "C" int qldpc_check_host(qldpc_code *c, int64_t B, const uint8_t *err, const uint8_t *corr, const uint8_t *synd,

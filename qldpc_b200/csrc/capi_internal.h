@@ -18,6 +18,7 @@
 #include "bp_cta_kernel.cuh"
 #include "bp_warp_kernel_f64.cuh"
 #include "bp_warp_layout.h"
+#include "host_pack.h"
 #include "osd_kernel.cuh"
 
 using namespace qldpc;
@@ -49,6 +50,28 @@ struct DevBuf {
     void release()
     {
         if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <typename T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+struct HostBuf {                    // pinned host staging buffer
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const cudaError_t e = cudaHostAlloc(&p, bytes + bytes / 8, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = bytes + bytes / 8;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFreeHost(p);
         p = nullptr;
         cap = 0;
     }
@@ -107,12 +130,20 @@ struct qldpc_code {
     // GPU (each runs at full speed), the copies of the neighbouring chunks run under them.
     struct Slot {
         DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail, redo, valid, inv;
+        HostBuf h_synd, h_hard;       // host-side packing: pinned bit-packed rows of the chunk (host_pack.h)
         cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
         bool used = false;
+        long long pend_o = 0, pend_b = 0;   // host-side packing: the chunk whose corrections still sit in h_hard
+        bool pend = false;
     };
     static constexpr int NSLOT = 4;
     Slot slot[NSLOT];
     cudaStream_t st_in = nullptr, st_comp = nullptr, st_out = nullptr;
+    // uint8 rows of the host-pointer decode call: packed on the device (0) or by host threads (1); -1: not decided yet
+    HostPool *pool = nullptr;
+    int host_pack = -1;
+    double host_pack_rate = 0.0;            // measured pack + unpack throughput of the pool, shots / s
+    unsigned long long h2d_bytes = 0, d2h_bytes = 0;    // bytes moved by the host-pointer decode calls (cumulative)
     BPGraphDev graph() const
     {
         BPGraphDev g;

@@ -997,3 +997,38 @@ def test_cta_staged_kernel_vs_thread_per_shot_staged_kernel(schedule):
         assert same.mean() >= 0.99 and rel.max() < 1e-7, (variant, same.mean(), rel.max())      # (own tanh / atanh vs the math library)
         got32 = code.bp_decode_batch(synd, prior, variant, 30, precision=32, staged=5, **kw)       # float32, tanh domain
         assert (got32[1] == ref[1]).mean() > 0.9
+
+
+def test_host_side_packing_of_the_uint8_interface_equals_device_side():
+    """qldpc_bposd_decode_host with its uint8 rows packed by host threads (bit-packed rows cross PCIe, 37 bytes per [[144,12,12]]
+    shot) against the same call with the rows packed by kernels (221 bytes): identical corrections, flags and iterations, over
+    several chunks of the three-stream pipeline (QLDPC_HOST_CHUNK shrinks them), ragged batch sizes, a code whose row lengths are
+    not multiples of 16 ([[90,8,10]]: plain stores instead of the non-temporal path), and the byte counters of the handle."""
+    import os
+    from qldpc_b200 import Code, graph
+    os.environ["QLDPC_HOST_CHUNK"] = "4096"
+    try:
+        for stem, B in (("[[144, 12, 12]]", 40000 + 123), ("[[90, 8, 10]]", 9001), ("[[72, 12, 6]]", 1)):
+            H, d = load_code_file(stem)
+            m, n = H.shape
+            code = Code(H, d["Lx"], graph.reference_schedule(H, "min_sum"))
+            rng = np.random.default_rng(3)
+            synd = _synd(H, (rng.random((B, n)) < 0.05).astype(np.uint8))
+            res = {}
+            for mode in (0, 1):
+                code.set_host_pack(mode)
+                s0 = code.host_transfer_stats()
+                res[mode] = code.bposd_decode_batch(synd, _prior(0.05, n), "min_sum", 40, 0.8, 0.7, 25.0, precision=32, osd_order=7)
+                s1 = code.host_transfer_stats()
+                assert s1["host_pack"] == mode
+                wm, wn = (m + 31) // 32, (n + 31) // 32
+                assert s1["h2d_bytes"] - s0["h2d_bytes"] == B * (m if mode == 0 else 4 * wm)
+                assert s1["d2h_bytes"] - s0["d2h_bytes"] == B * ((n if mode == 0 else 4 * wn) + 1 + 4)
+            for x, y in zip(res[0], res[1]):
+                assert np.array_equal(x, y), stem
+            assert (_synd(H, res[1][0]) == synd).all()
+            code.set_host_pack(-1)
+            auto = code.bposd_decode_batch(synd, _prior(0.05, n), "min_sum", 40, 0.8, 0.7, 25.0, precision=32, osd_order=7)
+            assert code.host_transfer_stats()["host_pack"] in (0, 1) and np.array_equal(auto[0], res[0][0])
+    finally:
+        del os.environ["QLDPC_HOST_CHUNK"]

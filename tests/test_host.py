@@ -142,3 +142,35 @@ def test_sum_product_math_header_against_50_digit_references(tmp_path, flags):
     assert z[0] == 0 and not np.signbit(z[0]) and z[1] == 0 and np.signbit(z[1]) and z[2] < 0
     z = call(L.sp_2atanh, [0.0, -0.0, -0.5])
     assert z[0] == 0 and not np.signbit(z[0]) and z[1] == 0 and np.signbit(z[1]) and z[2] < 0
+
+
+def test_host_side_bit_packing_matches_numpy(tmp_path):
+    """qldpc_b200/csrc/host_pack.h (the host-thread packing of qldpc_bposd_decode_host's uint8 rows), built with g++: bytes ->
+    bits equals np.packbits(little) on `byte & 1`, bits -> bytes is its inverse, for row lengths with and without full words,
+    aligned and unaligned outputs (non-temporal and plain store paths), several thread counts."""
+    import subprocess
+    lib = str(tmp_path / "hp.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-pthread", "-o", lib, os.path.join(ROOT, "tests", "cpp", "host_pack_check.cpp")],
+                   check=True, env={k: v for k, v in os.environ.items() if k not in ("CC", "CXX")})
+    L = ctypes.CDLL(lib)
+    rng = np.random.default_rng(0)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for nbits, threads in ((72, 3), (144, 4), (36, 1), (45, 2), (90, 5), (7, 2), (33, 3), (64, 2), (100, 3), (2592, 4), (864, 2)):
+        B = 257
+        W = (nbits + 31) // 32
+        a = (rng.random((B, nbits)) < 0.3).astype(np.uint8)
+        a[::7] |= 2                                              # only bit 0 of a byte counts (as in pack_bits_kernel)
+        out = np.zeros((B, W), dtype=np.uint32)
+        L.hp_pack(vp(a), vp(out), ctypes.c_longlong(B), nbits, threads)
+        bits = a & 1
+        pad = np.zeros((B, W * 32), dtype=np.uint8)
+        pad[:, :nbits] = bits
+        ref = np.packbits(pad.reshape(B, W, 32), axis=2, bitorder="little").view(np.uint32).reshape(B, W)
+        assert np.array_equal(out, ref), nbits
+        for shift in (0, 1):
+            buf = np.full(B * nbits + 64, 7, dtype=np.uint8)
+            off = (-buf.ctypes.data) % 16 + shift
+            o = buf[off:off + B * nbits]
+            L.hp_unpack(vp(ref), vp(o), ctypes.c_longlong(B), nbits, threads)
+            assert np.array_equal(o.reshape(B, nbits), bits), (nbits, shift)
+            assert (buf[:off] == 7).all() and (buf[off + B * nbits:] == 7).all()

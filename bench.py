@@ -378,12 +378,15 @@ def main():
             v = Be * e2e_steps * world / wall(e2e_step, e2e_steps)
             s1 = code.host_transfer_stats()
             calls = e2e_steps + 1
+            names = {0: "device kernels (byte rows cross PCIe)", 1: "host threads (bit-packed rows cross PCIe)",
+                     2: "chunk by chunk, whichever side is free (qldpc_b200.h: qldpc_host_transfer_stats)"}
             return dict(value=v, unit="shots/s", h2d_bytes_per_step=(s1["h2d_bytes"] - s0["h2d_bytes"]) // calls,
                         d2h_bytes_per_step=(s1["d2h_bytes"] - s0["d2h_bytes"]) // calls,
-                        rows_packed_by=("host threads (bit-packed rows cross PCIe)" if s1["host_pack"] == 1 else "device kernels (byte rows cross PCIe)"),
+                        rows_packed_by=names[s1["host_pack"]], chunks_packed_by_host=s1["chunks_host"] - s0["chunks_host"],
+                        chunks_packed_by_device=s1["chunks_device"] - s0["chunks_device"],
                         host_pack_rate_shots_per_s=s1["host_pack_rate"], matches_device_path=bool(torch.equal(corr_u8_ref, corr_h)))
         e2e_auto = e2e_leg(-1)
-        e2e_other = e2e_leg(0 if e2e_auto["rows_packed_by"].startswith("host") else 1)
+        e2e_other = {"device": e2e_leg(0), "host": e2e_leg(1), "chunk_by_chunk": e2e_leg(2)}
         code.set_host_pack(-1)
         e2e_value, e2e_matches = e2e_auto["value"], e2e_auto["matches_device_path"]
         del corr_u8_ref
@@ -406,9 +409,10 @@ def main():
                        "d2h_bytes_per_step": e2e_auto["d2h_bytes_per_step"],
                        "shots_per_step": Be, "steps": e2e_steps, "api": "qldpc_bposd_decode_host (uint8 in pinned host memory), osd_order=7",
                        "matches_device_path": e2e_matches, "rows_packed_by": e2e_auto["rows_packed_by"],
+                       "chunks_packed_by_host": e2e_auto["chunks_packed_by_host"], "chunks_packed_by_device": e2e_auto["chunks_packed_by_device"],
                        "host_pack_rate_shots_per_s": e2e_auto["host_pack_rate_shots_per_s"],
                        "host_bytes_per_step": {"in": Be * m, "out": Be * (n + 1 + 4)},
-                       "other_side": e2e_other,
+                       "forced_modes": e2e_other,
                        "packed_host_rows": {"value": e2e_packed_value, "unit": "shots/s", "h2d_bytes_per_step": Be * 4 * WM,
                                             "d2h_bytes_per_step": Be * (4 * WN + 1 + 4), "api": "qldpc_bposd_decode_host_packed",
                                             "matches_device_path": e2e_packed_matches},

@@ -156,13 +156,17 @@ int qldpc_bposd_decode_host(qldpc_code *code, const qldpc_bp_config *cfg, const 
 /* Who packs the uint8 rows of qldpc_bposd_decode_host, and what the calls have moved so far.  The byte rows either cross
  * PCIe as they are and are packed / expanded by kernels (host_pack 0: 72 + 149 bytes per [[144,12,12]] shot), or host threads
  * pack / expand them between the caller's arrays and pinned staging buffers and bit-packed rows cross the bus (host_pack 1:
- * 12 + 25 bytes).  Decided at the first call per code handle from the measured throughput of the thread pool
- * (host_pack_rate, shots/s; -1 before that call); environment: QLDPC_HOST_PACK = 0 | 1 forces a side, QLDPC_HOST_THREADS
- * sets the pool size.  h2d_bytes / d2h_bytes: cumulative bytes of the host<->device copies issued by
- * qldpc_bposd_decode_host[_packed] on this handle.  Any pointer may be NULL. */
+ * 12 + 25 bytes), or each chunk of the pipeline takes whichever side is free (host_pack 2, the default when the host has
+ * the threads: a chunk goes to the host threads whenever the byte-row copies already queued keep the bus busy for as long
+ * as packing it takes; the split follows the measured speeds of both sides, bus contention between the ranks of one box
+ * included).  Decided at the first call per code handle from the measured throughput of the thread pool (host_pack_rate,
+ * shots/s; host_pack is -1 before that call); environment: QLDPC_HOST_PACK = 0 | 1 | 2 forces a mode, QLDPC_HOST_THREADS sets
+ * the pool size (default: hardware threads / visible GPUs, at most 16).  h2d_bytes / d2h_bytes: cumulative bytes of the
+ * host<->device copies issued by qldpc_bposd_decode_host[_packed] on this handle; chunks_host / chunks_device: how many
+ * chunks went to either side.  Results never depend on the mode (tested).  Any pointer may be NULL. */
 int qldpc_host_transfer_stats(qldpc_code *code, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int32_t *host_pack,
-                              double *host_pack_rate);
-/* mode 0 / 1: fix the side for this handle; -1: measure again at the next call */
+                              double *host_pack_rate, uint64_t *chunks_host, uint64_t *chunks_device);
+/* mode 0 / 1 / 2: fix the mode for this handle; -1: measure again at the next call */
 int qldpc_set_host_pack(qldpc_code *code, int32_t mode);
 
 /* Same call with bit-packed host rows (synd [B][words_m], corr [B][words_n] uint32): 37 instead of 221 bytes per

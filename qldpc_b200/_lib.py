@@ -54,7 +54,7 @@ def lib():
         "qldpc_osd_decode_host": ([c_vp, c_i64, c_vp, c_vp, c_vp, c_i32, c_i64, c_vp], ctypes.c_int),
         "qldpc_bposd_decode_host": ([c_vp, P(BPConfig), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp], ctypes.c_int),
         "qldpc_bposd_decode_host_packed": ([c_vp, P(BPConfig), c_vp, c_i64, c_vp, c_i32, c_vp, c_vp, c_vp], ctypes.c_int),
-        "qldpc_host_transfer_stats": ([c_vp, c_vp, c_vp, c_vp, c_vp], ctypes.c_int),
+        "qldpc_host_transfer_stats": ([c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp], ctypes.c_int),
         "qldpc_set_host_pack": ([c_vp, c_i32], ctypes.c_int),
         "qldpc_check_host": ([c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp], ctypes.c_int),
         "qldpc_syndrome_host": ([c_vp, c_i64, c_vp, c_vp], ctypes.c_int),

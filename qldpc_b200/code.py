@@ -190,13 +190,17 @@ class Code:
 
     def host_transfer_stats(self):
         """-> dict(h2d_bytes, d2h_bytes: cumulative bytes moved by bposd_decode_batch on this handle; host_pack: -1 not decided,
-        0 the byte rows cross PCIe and are packed on the device, 1 host threads pack them; host_pack_rate: shots/s of the pool)"""
+        0 the byte rows cross PCIe and are packed on the device, 1 host threads pack them, 2 chunk by chunk whichever side is
+        free; host_pack_rate: shots/s of the thread pool; chunks_host / chunks_device: chunks that went to either side)"""
         a, b, c, d = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_int32(), ctypes.c_double()
-        _lib.check(_lib.lib().qldpc_host_transfer_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
-        return dict(h2d_bytes=a.value, d2h_bytes=b.value, host_pack=c.value, host_pack_rate=d.value)
+        e, f = ctypes.c_uint64(), ctypes.c_uint64()
+        _lib.check(_lib.lib().qldpc_host_transfer_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d),
+                                                        ctypes.byref(e), ctypes.byref(f)))
+        return dict(h2d_bytes=a.value, d2h_bytes=b.value, host_pack=c.value, host_pack_rate=d.value, chunks_host=e.value, chunks_device=f.value)
 
     def set_host_pack(self, mode):
-        """0 / 1: pack the uint8 rows of bposd_decode_batch on the device / with host threads; -1: measure at the next call"""
+        """0 / 1 / 2: pack the uint8 rows of bposd_decode_batch on the device / with host threads / chunk by chunk on whichever
+        side is free; -1: measure at the next call"""
         _lib.check(_lib.lib().qldpc_set_host_pack(self._h, int(mode)))
 
     def check_batch(self, errors, corrections, syndromes, converged=None, iters=None, distance=None):

@@ -324,7 +324,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
         for (DevBuf *b : sb) b->release();
         sl.h_synd.release();
         sl.h_hard.release();
-        for (cudaEvent_t e : {sl.ev_in, sl.ev_comp, sl.ev_out})
+        for (cudaEvent_t e : {sl.ev_in, sl.ev_comp, sl.ev_out0, sl.ev_out})
             if (e) cudaEventDestroy(e);
     }
     for (cudaStream_t st : {c->st_in, c->st_comp, c->st_out})
@@ -986,7 +986,7 @@ extern "C" int qldpc_osd_decode_host(qldpc_code *c, int64_t B, const uint8_t *sy
 static int host_pack_decide(qldpc_code *c, int want)        // want: -1 measure (the environment may force a side), 0 device, 1 host
 {
     if (want < 0)
-        if (const char *e = getenv("QLDPC_HOST_PACK")) want = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : -1;
+        if (const char *e = getenv("QLDPC_HOST_PACK")) want = (e[0] == '0') ? 0 : (e[0] == '1') ? 1 : (e[0] == '2') ? 2 : -1;
     if (want == 0) return c->host_pack = 0;
     if (!c->pool) {
         int threads = 0;
@@ -1011,9 +1011,16 @@ static int host_pack_decide(qldpc_code *c, int want)        // want: -1 measure 
         }
         c->host_pack_rate = (double)Bs / best;
     }
-    if (want == 1) return c->host_pack = 1;
+    c->est_pack = (1.0 / 3.0) / c->host_pack_rate;
+    c->est_unpack = (2.0 / 3.0) / c->host_pack_rate;
+    c->est_dev = (c->n + 5.0) / 50e9;
+    if (want >= 1) return c->host_pack = want;
+    // Host threads when the pool comes within reach of what the bus would carry at its single-GPU best: measured on the 1-, 2-
+    // and 8-GPU boxes of this pool (profiles/r2t_*), the host side wins or ties wherever its pool has >= 4 threads -- on the
+    // 8-GPU box the byte rows of the 8 ranks share 93 GB/s of device-to-host bandwidth (57 GB/s for one GPU alone), and the
+    // bus assumed here is far from what a rank gets.  (Mode 2, chunk by chunk on whichever side is free, is kept selectable.)
     const double bus_rate = 1.0 / std::max((c->n + 5.0) / 50e9, c->m / 25e9);
-    return c->host_pack = (c->host_pack_rate >= 1.2 * bus_rate) ? 1 : 0;
+    return c->host_pack = (c->host_pack_rate >= 0.6 * bus_rate) ? 1 : 0;
 }
 static int host_pack_mode(qldpc_code *c) { return c->host_pack >= 0 ? c->host_pack : host_pack_decide(c, -1); }
 
@@ -1029,7 +1036,10 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
     if (B <= 0) return QLDPC_OK;
     // Copy-in / (pack, BP, OSD, unpack) / copy-out of consecutive chunks run on three streams chained by events (true
     // overlap needs pinned host buffers; pageable ones still work).
-    long long chunk = 1ll << 20;
+    const int hp_mode = packed ? 0 : host_pack_mode(c);       // 0: device, 1: host threads, 2: chunk by chunk
+    // (measured, 10^7 [[144,12,12]] shots: host-packed rows 2.98e8 shots/s with 2^20-shot chunks, 3.09e8 with 2^21 -- fewer kernel
+    //  tails; byte rows over PCIe 2.77e8 / 2.65e8 -- their first copy-in and last copy-out are not hidden)
+    long long chunk = (hp_mode == 1) ? (1ll << 21) : (1ll << 20);
     if (const char *e = getenv("QLDPC_HOST_CHUNK")) chunk = std::max<long long>(1024, atoll(e));
     chunk = std::min<long long>(chunk, CHUNK);
     if (int rc = set_prior(c, prior, 0)) return rc;
@@ -1053,11 +1063,37 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
     for (auto &sl : c->slot) { sl.used = false; sl.pend = false; }
     // host-side packing (uint8 rows only): host threads pack the syndromes of a chunk into the slot's pinned buffer before its
     // copy-in and expand its corrections after its copy-out, while the GPU works on the neighbouring chunks
-    const bool hostpack = !packed && host_pack_mode(c) == 1;
-    const size_t in_bus = hostpack ? 4 * (size_t)c->WM : in_row, out_bus = hostpack ? 4 * (size_t)c->WN : out_row;
+    for (auto &sl : c->slot) { sl.inflight = false; sl.host_mode = false; }
+    if (hp_mode == 2)                                         // either kind of chunk may land in any slot: no allocation on the way
+        for (auto &sl : c->slot) {
+            const long long bmax = std::min<long long>(chunk, B);
+            CK(sl.h_synd.reserve(4 * (size_t)bmax * c->WM));
+            CK(sl.h_hard.reserve(4 * (size_t)bmax * c->WN));
+            CK(sl.u8in.reserve((size_t)bmax * c->m));
+            CK(sl.u8out.reserve((size_t)bmax * c->n));
+        }
+    auto seconds = [](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
     auto finish = [&](qldpc_code::Slot &sl) {                // corrections of the slot's pending chunk -> the caller's rows
+        const auto t0 = std::chrono::steady_clock::now();
         host_unpack_rows(*c->pool, sl.h_hard.as<uint32_t>(), corr + (size_t)sl.pend_o * c->n, sl.pend_b, c->n, c->WN);
+        if (sl.pend_b >= 4096) c->est_unpack = 0.75 * c->est_unpack + 0.25 * seconds(t0) / (double)sl.pend_b;
         sl.pend = false;
+    };
+    // byte-row copy-outs still queued, in seconds of bus time; completed ones update the running estimate of the bus
+    auto bus_backlog = [&]() {
+        double t = 0.0;
+        for (auto &s2 : c->slot) {
+            if (!s2.inflight || s2.host_mode) continue;
+            if (cudaEventQuery(s2.ev_out) == cudaSuccess) {
+                float ms = 0.f;
+                if (s2.cur_b >= 4096 && cudaEventElapsedTime(&ms, s2.ev_out0, s2.ev_out) == cudaSuccess && ms > 0.f)
+                    c->est_dev = 0.75 * c->est_dev + 0.25 * (1e-3 * ms / (double)s2.cur_b);
+                s2.inflight = false;
+            } else {
+                t += (double)s2.cur_b * c->est_dev;
+            }
+        }
+        return t;
     };
     long long i = 0;
     auto finish_ready = [&]() {                               // oldest first, as far as their copy-out has completed
@@ -1070,22 +1106,30 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         if (!sl.ev_in) {
             CK(cudaEventCreateWithFlags(&sl.ev_in, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&sl.ev_comp, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&sl.ev_out, cudaEventDisableTiming));
+            CK(cudaEventCreate(&sl.ev_out0));
+            CK(cudaEventCreate(&sl.ev_out));
         }
         CK(sl.synd.reserve(4 * (size_t)b * c->WM));
         CK(sl.hard.reserve(4 * (size_t)b * c->WN));
         CK(sl.conv.reserve((size_t)b));
         CK(sl.iters.reserve(4 * (size_t)b));
+        bool hostpack = (hp_mode == 1);
+        if (hp_mode == 2) hostpack = bus_backlog() >= 0.9 * (double)b * (c->est_pack + c->est_unpack);
+        const size_t in_bus = hostpack ? 4 * (size_t)c->WM : in_row, out_bus = hostpack ? 4 * (size_t)c->WN : out_row;
+        if (hp_mode != 0) finish_ready();
+        if (sl.pend) {                                        // the slot's previous chunk was packed by the host: expand it first
+            CK(cudaEventSynchronize(sl.ev_out));
+            finish(sl);
+        }
         if (hostpack) {
             CK(sl.h_synd.reserve(4 * (size_t)b * c->WM));
             CK(sl.h_hard.reserve(4 * (size_t)b * c->WN));
-            finish_ready();
-            if (sl.pend) {                                    // the slot's previous chunk: its buffers are free after its copy-out
-                CK(cudaEventSynchronize(sl.ev_out));
-                finish(sl);
-            }
+            const auto t0 = std::chrono::steady_clock::now();
             host_pack_rows(*c->pool, synd + (size_t)o * c->m, sl.h_synd.as<uint32_t>(), b, c->m, c->WM);
+            if (b >= 4096) c->est_pack = 0.75 * c->est_pack + 0.25 * seconds(t0) / (double)b;
+            ++c->host_chunks;
         } else if (!packed) {
+            ++c->dev_chunks;
             CK(sl.u8in.reserve((size_t)b * c->m));
             CK(sl.u8out.reserve((size_t)b * c->n));
         }
@@ -1111,6 +1155,7 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         mark(c->st_comp);
         // ---- copy out
         CK(cudaStreamWaitEvent(c->st_out, sl.ev_comp, 0));
+        CK(cudaEventRecord(sl.ev_out0, c->st_out));
         CK(cudaMemcpyAsync(hostpack ? sl.h_hard.p : (void *)(corr + (size_t)o * out_row), (packed || hostpack) ? sl.hard.p : sl.u8out.p,
                            (size_t)b * out_bus, cudaMemcpyDeviceToHost, c->st_out));
         CK(cudaMemcpyAsync(conv + o, sl.conv.p, (size_t)b, cudaMemcpyDeviceToHost, c->st_out));
@@ -1119,6 +1164,9 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         CK(cudaEventRecord(sl.ev_out, c->st_out));
         mark(c->st_out);
         sl.used = true;
+        sl.host_mode = hostpack;
+        sl.inflight = true;
+        sl.cur_b = b;
         if (hostpack) { sl.pend = true; sl.pend_o = o; sl.pend_b = b; }
         return QLDPC_OK;
     };
@@ -1141,7 +1189,7 @@ static int bposd_decode_host_impl(qldpc_code *c, const qldpc_bp_config *cfg, con
         o += b;
     }
     const std::string msg = g_err;
-    if (hostpack)                                             // expand the chunks still in flight, oldest first
+    if (hp_mode != 0)                                         // expand the chunks still in flight, oldest first
         for (int a = 0; a < qldpc_code::NSLOT; ++a) {
             qldpc_code::Slot &sl = c->slot[(i + a) % qldpc_code::NSLOT];
             if (!sl.pend) continue;
@@ -1180,20 +1228,22 @@ extern "C" int qldpc_bposd_decode_host_packed(qldpc_code *c, const qldpc_bp_conf
 extern "C" int qldpc_set_host_pack(qldpc_code *c, int32_t mode)
 {
     if (!c) return fail(QLDPC_ERR_ARG, "qldpc_set_host_pack: null code");
-    if (mode < -1 || mode > 1) return fail(QLDPC_ERR_ARG, "qldpc_set_host_pack: mode must be -1 (measure), 0 (device) or 1 (host)");
+    if (mode < -1 || mode > 2) return fail(QLDPC_ERR_ARG, "qldpc_set_host_pack: mode must be -1 (measure), 0 (device), 1 (host) or 2 (chunk by chunk)");
     if (mode < 0) c->host_pack = -1;             // decided again at the next call
     else host_pack_decide(c, mode);
     return QLDPC_OK;
 }
 
 extern "C" int qldpc_host_transfer_stats(qldpc_code *c, uint64_t *h2d_bytes, uint64_t *d2h_bytes, int32_t *host_pack,
-                                         double *host_pack_rate)
+                                         double *host_pack_rate, uint64_t *chunks_host, uint64_t *chunks_device)
 {
     if (!c) return fail(QLDPC_ERR_ARG, "qldpc_host_transfer_stats: null code");
     if (h2d_bytes) *h2d_bytes = c->h2d_bytes;
     if (d2h_bytes) *d2h_bytes = c->d2h_bytes;
     if (host_pack) *host_pack = c->host_pack;
     if (host_pack_rate) *host_pack_rate = c->host_pack_rate;
+    if (chunks_host) *chunks_host = c->host_chunks;
+    if (chunks_device) *chunks_device = c->dev_chunks;
     return QLDPC_OK;
 }
 

@@ -131,18 +131,24 @@ struct qldpc_code {
     struct Slot {
         DevBuf ctrl, gstate, u8in, u8out, synd, hard, conv, iters, llr, fail, redo, valid, inv;
         HostBuf h_synd, h_hard;       // host-side packing: pinned bit-packed rows of the chunk (host_pack.h)
-        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out = nullptr;
+        cudaEvent_t ev_in = nullptr, ev_comp = nullptr, ev_out0 = nullptr, ev_out = nullptr;   // (ev_out0 .. ev_out: the copy-out, timed)
         bool used = false;
         long long pend_o = 0, pend_b = 0;   // host-side packing: the chunk whose corrections still sit in h_hard
         bool pend = false;
+        bool host_mode = false;             // the slot's current chunk is packed by host threads
+        bool inflight = false;              // its copy-out has not been seen complete yet
+        long long cur_b = 0;
     };
     static constexpr int NSLOT = 4;
     Slot slot[NSLOT];
     cudaStream_t st_in = nullptr, st_comp = nullptr, st_out = nullptr;
     // uint8 rows of the host-pointer decode call: packed on the device (0) or by host threads (1); -1: not decided yet
+    // or chunk by chunk by whichever side is free (2)
     HostPool *pool = nullptr;
     int host_pack = -1;
     double host_pack_rate = 0.0;            // measured pack + unpack throughput of the pool, shots / s
+    double est_dev = 0.0, est_pack = 0.0, est_unpack = 0.0;   // running estimates, seconds per shot: copy-out of byte rows, host pack, host expansion
+    unsigned long long host_chunks = 0, dev_chunks = 0;
     unsigned long long h2d_bytes = 0, d2h_bytes = 0;    // bytes moved by the host-pointer decode calls (cumulative)
     BPGraphDev graph() const
     {

@@ -1015,20 +1015,25 @@ def test_host_side_packing_of_the_uint8_interface_equals_device_side():
             rng = np.random.default_rng(3)
             synd = _synd(H, (rng.random((B, n)) < 0.05).astype(np.uint8))
             res = {}
-            for mode in (0, 1):
+            for mode in (0, 1, 2):
                 code.set_host_pack(mode)
                 s0 = code.host_transfer_stats()
                 res[mode] = code.bposd_decode_batch(synd, _prior(0.05, n), "min_sum", 40, 0.8, 0.7, 25.0, precision=32, osd_order=7)
                 s1 = code.host_transfer_stats()
                 assert s1["host_pack"] == mode
                 wm, wn = (m + 31) // 32, (n + 31) // 32
-                assert s1["h2d_bytes"] - s0["h2d_bytes"] == B * (m if mode == 0 else 4 * wm)
-                assert s1["d2h_bytes"] - s0["d2h_bytes"] == B * ((n if mode == 0 else 4 * wn) + 1 + 4)
-            for x, y in zip(res[0], res[1]):
-                assert np.array_equal(x, y), stem
+                if mode < 2:
+                    assert s1["h2d_bytes"] - s0["h2d_bytes"] == B * (m if mode == 0 else 4 * wm)
+                    assert s1["d2h_bytes"] - s0["d2h_bytes"] == B * ((n if mode == 0 else 4 * wn) + 1 + 4)
+                    assert (s1["chunks_host"] - s0["chunks_host"] > 0) == (mode == 1) and (s1["chunks_device"] - s0["chunks_device"] > 0) == (mode == 0)
+                else:
+                    assert B * 4 * wm <= s1["h2d_bytes"] - s0["h2d_bytes"] <= B * m
+            for mode in (1, 2):
+                for x, y in zip(res[0], res[mode]):
+                    assert np.array_equal(x, y), (stem, mode)
             assert (_synd(H, res[1][0]) == synd).all()
             code.set_host_pack(-1)
             auto = code.bposd_decode_batch(synd, _prior(0.05, n), "min_sum", 40, 0.8, 0.7, 25.0, precision=32, osd_order=7)
-            assert code.host_transfer_stats()["host_pack"] in (0, 1) and np.array_equal(auto[0], res[0][0])
+            assert code.host_transfer_stats()["host_pack"] in (0, 1, 2) and np.array_equal(auto[0], res[0][0])
     finally:
         del os.environ["QLDPC_HOST_CHUNK"]

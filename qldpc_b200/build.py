@@ -65,7 +65,7 @@ def _compile(unit, force):
         t = os.path.getmtime(obj)
         if os.path.getmtime(src) <= t and all(os.path.getmtime(h) <= t for h in headers()):
             return obj, 0, "(up to date) %s\n" % unit
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", "-o", obj, src]
+    cmd = [_nvcc()] + NVCC_FLAGS + os.environ.get("QLDPC_NVCC_EXTRA", "").split() + ["-c", "-o", obj, src]     # (diagnostic builds)
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=_env())
     return obj, res.returncode, " ".join(cmd) + "\n" + res.stdout
 

@@ -293,6 +293,16 @@ static int code_create_impl(int32_t m, int32_t n, const int32_t *row_ptr, const 
     CK(upload(&c->d_vtab0, vt0));
     CK(upload(&c->d_vtab1, vt1));
     CK(upload(&c->d_colmask, colmask));
+    if (m <= 1024 && c->max_col_w <= 3) {
+        std::vector<uint32_t> colpack((size_t)n, 0u);
+        for (int v = 0; v < n; ++v) {
+            const int cnt = var_ptr[v + 1] - var_ptr[v];
+            uint32_t e = (uint32_t)cnt << 30;
+            for (int t = 0; t < cnt; ++t) e |= vt1[2 * (size_t)(var_ptr[v] + t) + 1] << (10 * t);
+            colpack[v] = e;
+        }
+        CK(upload(&c->d_colpack, colpack));
+    }
     CK(upload(&c->d_Lrows, Lrows));
     CK(upload(&c->d_Hrows, Hrows));
     for (int ti = 0; ti < 3; ++ti) {
@@ -307,7 +317,7 @@ extern "C" void qldpc_code_destroy(qldpc_code *c)
 {
     if (!c) return;
     cudaFree(c->d_row_ptr); cudaFree(c->d_col_idx); cudaFree(c->d_var_ptr);
-    cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
+    cudaFree(c->d_vtab0); cudaFree(c->d_vtab1); cudaFree(c->d_colmask); cudaFree(c->d_colpack); cudaFree(c->d_Lrows); cudaFree(c->d_Hrows);
     for (int ti = 0; ti < 3; ++ti) { cudaFree(c->d_vell0[ti]); cudaFree(c->d_vell1[ti]); }
     cudaFree(c->d_wtab);
     cudaFree(c->d_wtab64);

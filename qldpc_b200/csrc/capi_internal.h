@@ -92,6 +92,7 @@ struct qldpc_code {
     int num_sms = 0, smem_optin = 0;
     int32_t *d_row_ptr = nullptr, *d_col_idx = nullptr, *d_var_ptr = nullptr;
     uint32_t *d_vtab0 = nullptr, *d_vtab1 = nullptr, *d_colmask = nullptr, *d_Lrows = nullptr, *d_Hrows = nullptr;
+    uint32_t *d_colpack = nullptr;                      // [n] checks of a column packed 3 x 10 bits + count << 30 (m <= 1024, column weight <= 3; block OSD)
     // T-lanes-per-shot kernel tables: 4 words per position {e0, e1, e2, v}, e = check | k << 16.  [0]: identity positions
     // (float64: the reference's addition order is kept as is), [1]/[2]: positions optimised for TL = 4 / 8 (float32)
     uint32_t *d_vell0[3] = {nullptr, nullptr, nullptr}, *d_vell1[3] = {nullptr, nullptr, nullptr};

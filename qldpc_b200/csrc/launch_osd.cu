@@ -109,7 +109,7 @@ static cudaError_t launch_osd_block(const qldpc_code *c, const OSDBlockParams &P
 template <typename K>
 static cudaError_t launch_osd_block_fast(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
 {
-    auto kern = (P.m < 1024 && P.max_col_w <= 3) ? osd0_block_fast_kernel<K, true> : osd0_block_fast_kernel<K, false>;
+    auto kern = P.colpack ? osd0_block_fast_kernel<K, true> : osd0_block_fast_kernel<K, false>;
     const size_t smem = osdbf_smem_bytes<K>(P.m, P.n);
     if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -137,7 +137,7 @@ int osd_launch(qldpc_code *c, OSDParams &P, int llr_f64, long long count_hint, c
         if (c->n > 65534 || c->m > 32767) return qldpc_fail(QLDPC_ERR_UNSUPPORTED, "OSD: more than 65534 columns or 32767 rows");
         OSDBlockParams Q;
         Q.m = c->m; Q.n = c->n; Q.WM = c->WM; Q.WN = c->WN; Q.rank = c->rank; Q.max_col_w = c->max_col_w;
-        Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1;
+        Q.var_ptr = c->d_var_ptr; Q.vtab = c->d_vtab1; Q.colpack = c->d_colpack;
         Q.idx = P.idx; Q.count_dev = P.count_dev; Q.count_host = P.count_host;
         Q.synd = P.synd; Q.llr = P.llr; Q.hard = P.hard; Q.out = P.out; Q.valid = P.valid;
         Q.redo_idx = nullptr; Q.redo_count = nullptr;

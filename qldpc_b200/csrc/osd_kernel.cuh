@@ -771,6 +771,7 @@ struct OSDBlockParams {
     int max_col_w;                // largest column weight of H
     const int32_t *var_ptr;       // [n+1]  CSC of H
     const uint32_t *vtab;         // [2E]   (edge, check) pairs per variable (any order)
+    const uint32_t *colpack;      // [n]    checks of a column, 3 x 10 bits + count << 30 (null unless m <= 1024 and column weight <= 3)
     const int32_t *idx;
     const unsigned int *count_dev;
     long long count_host;
@@ -928,25 +929,36 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 }
 
 // ------------------------------------------------------------------------------------------------
-// OSD-0 for large check matrices, column-major transform, forward elimination: the production block kernel.
+// OSD-0 for large check matrices, column-major transform, forward elimination in batches: the production block kernel.
 //
 // Same observation as osd0_fast_kernel: the OSD-0 solution does not depend on which row pivots a column, and a column
 // with no free row never gets one back.  The transform is stored by COLUMNS (TC[c] = column c of T, an m-bit vector of
-// WM words): the reduced column j = T h_j is the XOR of the <= 3 TC columns of the checks of variable ordering[j] --
-// ONE warp evaluates it (a word per lane) and finds its lowest free row; a row operation "rows S ^= row p" becomes
-// "every TC column with bit p set ^= S".  The 8 warps of the CTA test 8 consecutive candidate columns at once; the
-// first one with a free row pivots, the dependent ones before it are skipped for good, the ones after it are re-tested.
-// Two barriers per PIVOT, none per column; dependent columns (2/3 of a space-time matrix) cost one warp-pass each.
+// WM words; column m is the syndrome column): the reduced column j = T h_j is the XOR of the <= 3 TC columns of the
+// checks of variable ordering[j]; a row operation "rows S ^= row p" becomes "every TC column with bit p set ^= S".
 // Only FREE rows are eliminated (S = free rows of the pivot column): pivot rows are frozen once chosen, T fills in like
-// L^-1 instead of B^-1, and the solution follows from a back-substitution over the pivots in reverse order (one warp,
-// the syndrome column in its registers).  Free rows evolve exactly as under Gauss-Jordan, so the pivot columns and the
-// consistency test are unchanged.  Inconsistent syndromes are handed to osd0_block_kernel (redo list).
-// The checks of column ordering[j] are packed 3 x 10 bits into the shared-memory words the sort keys occupied
-// (m < 1024, column weight <= 3: the space-time matrices; otherwise they are read from global memory).
+// L^-1 instead of B^-1, and the solution follows from a back-substitution over the pivots in reverse order.
+//
+// A round takes OSDB_BATCH = 32 consecutive candidate columns:
+//   evaluate  every warp reduces 4 candidates against the current T (a word per lane) and finds their lowest free row;
+//   resolve   warp 0, lane k = candidate k.  The 32 x 32 interaction matrix I[k'][k] = "candidate k' has the pivot row of
+//             candidate k" is gathered once; it is almost empty (the reduced columns are sparse), so nearly every nonzero
+//             candidate is accepted as it stands.  A candidate with an entry below the diagonal is first reduced by the
+//             accepted candidates before it (and may turn out dependent); entries above the diagonal are folded into the
+//             vectors afterwards, in descending order, S'_b = S_b ^ sum_{a > b, S_b[p_a]} S'_a, which turns the SEQUENCE
+//             of row operations of the batch into ONE linear map  c -> c ^ sum_a c[p_a] S'_a  whose coefficients are
+//             bits of the column as it stood BEFORE the round;
+//   apply     each warp owns columns of T: a lane gathers the <= 32 coefficient bits of its column (independent loads,
+//             no chain through the pivots), then the warp XORs the selected S' vectors into the columns that have any
+//             (~10 of 864 per pivot), a word per lane.  No barrier inside, warps never touch each other's columns.
+// Three barriers per 32 candidates (the round-1/2 kernel spent three per 8 and walked every column through the pivots
+// of the batch one after the other: 1.2 M of its 2.0 M cycles per shot).
+// Inconsistent syndromes are handed to osd0_block_kernel (redo list).  The checks of a column come from a per-code table
+// packed 3 x 10 bits (m <= 1024, column weight <= 3: the space-time matrices; otherwise from the CSC in global memory).
 // ------------------------------------------------------------------------------------------------
+constexpr int OSDB_BATCH = 32;
+
 // the sort runs as a bitonic sort inside the (still idle) transform area when (key, index) pairs of the padded length fit
-// there; only the rank-counting fallback needs the keys outside of it.  (4 n bytes either way: the packed check lists;
-// 114 KB in all for the 864 x 2592 matrix with float or double keys -- two CTAs per SM.)
+// there; only the rank-counting fallback needs the keys outside of it.
 template <typename K>
 __host__ __device__ inline bool osdbf_bitonic_fits(int m, int n)
 {
@@ -957,71 +969,85 @@ __host__ __device__ inline bool osdbf_bitonic_fits(int m, int n)
 template <typename K>
 __host__ __device__ inline size_t osdbf_key_area(int m, int n)
 {
-    return osdbf_bitonic_fits<K>(m, n) ? 4 * (size_t)n : sizeof(typename KeyBits<K>::type) * (size_t)n;
+    return osdbf_bitonic_fits<K>(m, n) ? 0 : sizeof(typename KeyBits<K>::type) * (size_t)n;
 }
 
 template <typename K>
 __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 {
     const int WM = (m + 31) / 32, WN = (n + 31) / 32;
-    size_t o = 4 * (size_t)m * WM;                              // TC
-    o += 2 * (size_t)m * 2;                                     // pivot rows / sorted positions of the pivot columns (uint16)
+    size_t o = 4 * (size_t)(m + 1) * WM;                        // TC, syndrome column
+    o += 2 * (size_t)m * 3;                                     // pivot rows / sorted positions of the pivot columns / pivot index of a row (uint16)
     o = (o + 3) & ~(size_t)3;
-    o += 4 * (size_t)WM * 3;                                    // used (double-buffered), b
-    o += 4 * (size_t)WM * (OSDB_THREADS / 32);                  // per-warp candidate columns
+    o += 4 * (size_t)WM;                                        // used
+    o += 4 * (size_t)WM * OSDB_BATCH;                           // candidate columns of the round
     o += 4 * (size_t)WN;                                        // solution words
     o = (o + 7) & ~(size_t)7;
-    o += osdbf_key_area<K>(m, n);                               // keys (rank-counting path only), then the packed check lists
+    o += osdbf_key_area<K>(m, n);                               // keys (rank-counting path only)
     o += 2 * (size_t)n;                                         // ordering (uint16)
     return o + 64;
 }
+
+// -DQLDPC_OSD_TIMING: per-phase clock64() totals of CTA 0, printed at the end of the launch (diagnostic builds only)
+#ifdef QLDPC_OSD_TIMING
+#define OSDT_DECL long long osdt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, osdt_t = clock64(); long long osdt_rounds = 0, osdt_piv = 0, osdt_shots = 0, osdt_hits = 0, osdt_fix = 0
+#define OSDT_MARK(i) do { const long long osdt_n = clock64(); osdt[i] += osdt_n - osdt_t; osdt_t = osdt_n; } while (0)
+#else
+#define OSDT_DECL
+#define OSDT_MARK(i)
+#endif
 
 template <typename K, bool PACKED>
 __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSDBlockParams P)
 {
     typedef typename KeyBits<K>::type kbits;
     constexpr int NW = OSDB_THREADS / 32;
+    constexpr int KB = OSDB_BATCH, CPW = KB / NW;               // candidates per round / per warp
+    static_assert(KB == 32 && KB % NW == 0, "one candidate per lane of the resolving warp");
     const int m = P.m, n = P.n, WM = P.WM, WN = P.WN;
     const int tid = threadIdx.x, NT = OSDB_THREADS, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *TC = reinterpret_cast<uint32_t *>(smem);                      // [m][WM]  column c of T
-    uint16_t *prow = reinterpret_cast<uint16_t *>(TC + (size_t)m * WM);    // [m] pivot row of the k-th pivot
+    uint32_t *TC = reinterpret_cast<uint32_t *>(smem);                      // [m + 1][WM]  column c of T; column m = syndrome
+    uint32_t *bw = TC + (size_t)m * WM;
+    uint16_t *prow = reinterpret_cast<uint16_t *>(TC + (size_t)(m + 1) * WM);   // [m] pivot row of the k-th pivot
     uint16_t *pcolj = prow + m;                                            // [m] sorted position of the k-th pivot column
-    uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(pcolj + m) + 3) & ~(uintptr_t)3);   // [2][WM]
-    uint32_t *bw = used + 2 * WM;                                           // [WM] syndrome column
-    uint32_t *cand = bw + WM;                                               // [NW][WM] free rows of the candidates
-    uint32_t *solw = cand + (size_t)NW * WM;                                // [WN]
+    uint16_t *rowpiv = pcolj + m;                                          // [m] index of the pivot that row r belongs to
+    uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(rowpiv + m) + 3) & ~(uintptr_t)3);   // [WM]
+    uint32_t *cand = used + WM;                                             // [KB][WM] free rows of the candidates
+    uint32_t *solw = cand + (size_t)KB * WM;                                // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
-    uint32_t *chk = reinterpret_cast<uint32_t *>(keys);                    // [n] packed checks of column ordering[j] (after the sort)
     uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
-    __shared__ int s_pp[NW], s_pw[NW], s_k;
-    constexpr bool packed_chk = PACKED;               // m < 1024 and column weight <= 3 (checked by the host)
+    __shared__ int s_p[KB];
+    __shared__ unsigned s_acc;
+    constexpr bool packed_chk = PACKED;               // m <= 1024 and column weight <= 3 (checked by the host)
 
     // XOR of the TC columns of the checks of sorted position jj, word w
     auto reduced_word = [&](int jj, int w) -> uint32_t {
         uint32_t x = 0;
+        const int col = ord[jj];
         if (packed_chk) {
-            const uint32_t e = chk[jj];
+            const uint32_t e = __ldg(P.colpack + col);
             const int cnt = (int)(e >> 30);
-            x = TC[(size_t)(e & 1023u) * WM + w];
+            if (cnt > 0) x = TC[(size_t)(e & 1023u) * WM + w];
             if (cnt > 1) x ^= TC[(size_t)((e >> 10) & 1023u) * WM + w];
             if (cnt > 2) x ^= TC[(size_t)((e >> 20) & 1023u) * WM + w];
         } else {
-            const int col = ord[jj];
             for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= TC[(size_t)P.vtab[2 * a + 1] * WM + w];
         }
         return x;
     };
 
     const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
+    OSDT_DECL;
     for (long long it = blockIdx.x; it < count; it += gridDim.x) {
         const long long shot = P.idx ? (long long)P.idx[it] : it;
         const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
         const uint32_t *hard = P.hard + (size_t)shot * WN;
         __syncthreads();
+        OSDT_MARK(7);
         // ---- stable ascending order of |llr| ----------------------------------------------------
-        for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; used[WM + w] = 0; }
+        for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; }
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
         int N2 = 1;
         while (N2 < n) N2 <<= 1;
@@ -1064,14 +1090,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             }
         }
         __syncthreads();                                              // keys are dead from here on
-        if (packed_chk)
-            for (int j = tid; j < n; j += NT) {
-                const int col = ord[j];
-                const int a0 = P.var_ptr[col], cnt = P.var_ptr[col + 1] - a0;
-                uint32_t e = (uint32_t)cnt << 30;
-                for (int k = 0; k < cnt; ++k) e |= P.vtab[2 * (a0 + k) + 1] << (10 * k);
-                chk[j] = e;
-            }
+        OSDT_MARK(0);
         // ---- residual syndrome s ^ H*hard; T = I ------------------------------------------------
         for (int v = tid; v < n; v += NT)
             if ((hard[v >> 5] >> (v & 31)) & 1u)
@@ -1085,95 +1104,180 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         }
         __syncthreads();
 
-        // ---- forward elimination, NW candidate columns per round ----------------------------------
-        // Every warp evaluates one candidate against the current T.  Warp 0 then resolves the whole batch in order: a
-        // candidate with a free row pivots (lowest free row p, S = its other free rows), and every LATER candidate of the
-        // batch is brought up to date in registers (if it has row p: ^= S; row p is no longer free).  The batch of up to
-        // NW pivots is then applied to T -- each warp walks its own columns through the pivots in order, no barrier in
-        // between -- so a round costs three barriers for up to NW pivots and NW columns are finished per round.
+        // ---- forward elimination, KB candidate columns per round ------------------------------------
         int j = 0, npiv = 0;
         const int rank = P.rank;
-        const uint32_t *ucur = used;
+        OSDT_MARK(1);
         while (j < n && npiv < rank) {
-            const int jj = j + warp;
-            if (lane < WM) cand[(size_t)warp * WM + lane] = (jj < n) ? (reduced_word(jj, lane) & ~ucur[lane]) : 0u;
-            __syncthreads();
-            if (warp == 0) {
-                uint32_t fr[NW];
+            // evaluate: candidate k = i * NW + warp, a word per lane; lowest free row
+            {
+                uint32_t v[CPW];
 #pragma unroll
-                for (int w = 0; w < NW; ++w) fr[w] = (lane < WM) ? cand[(size_t)w * WM + lane] : 0u;
-                int k = 0;
+                for (int i = 0; i < CPW; ++i) {
+                    const int jj = j + i * NW + warp;
+                    v[i] = (lane < WM && jj < n) ? (reduced_word(jj, lane) & ~used[lane]) : 0u;
+                }
 #pragma unroll
-                for (int w = 0; w < NW; ++w) {
-                    const unsigned bal = __ballot_sync(FULL, fr[w] != 0);
-                    if (bal != 0 && npiv + k < rank) {                          // (uniform)
+                for (int i = 0; i < CPW; ++i) {
+                    const int k = i * NW + warp;
+                    if (lane < WM) cand[(size_t)k * WM + lane] = v[i];
+                    const unsigned bal = __ballot_sync(FULL, v[i] != 0);
+                    int p = -1;
+                    if (bal) {
                         const int src = __ffs(bal) - 1;
-                        const uint32_t f = __shfl_sync(FULL, fr[w], src);
-                        const int pb = __ffs(f) - 1;
-                        if (lane == src) fr[w] &= fr[w] - 1;                    // S = free rows without the pivot row
-                        if (lane < WM) cand[(size_t)w * WM + lane] = fr[w];
-                        if (lane == 0) { s_pp[k] = 32 * src + pb; s_pw[k] = w; }
+                        p = 32 * src + __ffs(__shfl_sync(FULL, v[i], src)) - 1;
+                    }
+                    if (lane == 0) s_p[k] = p;
+                }
+            }
+            __syncthreads();
+            OSDT_MARK(2);
+            if (warp == 0) {
+                int p = s_p[lane];                                   // pivot row of candidate `lane`, -1: no free row
+                unsigned acc = __ballot_sync(FULL, p >= 0);
+                const unsigned below = (1u << lane) - 1u;
+                // interaction matrix: bit k of im = this candidate has the pivot row of candidate k
+                unsigned im = 0;
+#pragma unroll 8
+                for (int k = 0; k < KB; ++k) {
+                    const int pk = __shfl_sync(FULL, p, k);
+                    const int pc = pk < 0 ? 0 : pk;
+                    const uint32_t bit = (cand[(size_t)lane * WM + (pc >> 5)] >> (pc & 31)) & (pk < 0 ? 0u : 1u);
+                    im |= bit << k;
+                }
+                im &= ~(1u << lane);
+                // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
+                unsigned todo = __ballot_sync(FULL, (im & below & acc) != 0);
+                while (todo) {
+                    const int kp = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned lowk = (1u << kp) - 1u;
+                    unsigned imk = __shfl_sync(FULL, im, kp) & acc & lowk;
+                    if (!imk) continue;
+#ifdef QLDPC_OSD_TIMING
+                    ++osdt_fix;
+#endif
+                    uint32_t v = (lane < WM) ? cand[(size_t)kp * WM + lane] : 0u;
+                    const int pc = p < 0 ? 0 : p;
+                    while (imk) {
+                        const int k = __ffs(imk) - 1;
+                        if (lane < WM) v ^= cand[(size_t)k * WM + lane];
+                        const uint32_t wv = __shfl_sync(FULL, v, pc >> 5);
+                        imk = __ballot_sync(FULL, p >= 0 && ((wv >> (pc & 31)) & 1u)) & acc & lowk & ~((2u << k) - 1u);
+                    }
+                    if (lane < WM) cand[(size_t)kp * WM + lane] = v;
+                    const unsigned bal = __ballot_sync(FULL, v != 0);
+                    int newp = -1;
+                    if (bal) {
+                        const int src = __ffs(bal) - 1;
+                        newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
+                    }
+                    if (lane == kp) p = newp;
+                    if (newp < 0) acc &= ~(1u << kp);
+                    __syncwarp();
+                    // refresh row kp and column kp of the interaction matrix
+                    const int pc2 = p < 0 ? 0 : p;
+                    const uint32_t wv = __shfl_sync(FULL, v, pc2 >> 5);
+                    const unsigned rowkp = __ballot_sync(FULL, p >= 0 && ((wv >> (pc2 & 31)) & 1u)) & ~(1u << kp);
+                    uint32_t b = 0;
+                    if (newp >= 0) b = (cand[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
+                    if (lane == kp) im = rowkp;
+                    else im = (im & ~(1u << kp)) | (b << kp);
+                    todo |= __ballot_sync(FULL, b != 0 && lane > kp);
+                }
+                // never more pivots than the rank of H
+                while (__popc(acc) > rank - npiv) acc &= ~(0x80000000u >> __clz(acc));
+                const bool mine = (acc >> lane) & 1u;
+                // S = free rows without the pivot row; fold the entries above the diagonal in (descending order)
+                if (mine) cand[(size_t)lane * WM + (p >> 5)] &= ~(1u << (p & 31));
+                __syncwarp();
+                const unsigned jm = mine ? (im & acc & ~((2u << lane) - 1u)) : 0u;
+                unsigned bt = __ballot_sync(FULL, jm != 0);
+                while (bt) {
+                    const int b = 31 - __clz(bt);
+                    bt &= ~(1u << b);
+                    unsigned jb = __shfl_sync(FULL, jm, b);
+#ifdef QLDPC_OSD_TIMING
+                    ++osdt_fix;
+#endif
+                    uint32_t v = 0;
+                    while (jb) {
+                        const int a = __ffs(jb) - 1;
+                        jb &= jb - 1;
+                        if (lane < WM) v ^= cand[(size_t)a * WM + lane];
+                    }
+                    if (lane < WM) cand[(size_t)b * WM + lane] ^= v;
+                    __syncwarp();
+                }
+                // publish the pivots
+                if (mine) {
+                    const int a = npiv + __popc(acc & below);
+                    prow[a] = (uint16_t)p;
+                    pcolj[a] = (uint16_t)(j + lane);
+                    rowpiv[p] = (uint16_t)a;
+                    atomicOr(&used[p >> 5], 1u << (p & 31));
+                }
+                s_p[lane] = mine ? p : -1;
+                if (lane == 0) s_acc = acc;
+            }
+            __syncthreads();
+            OSDT_MARK(3);
+            const unsigned acc = s_acc;
+            // apply: column c ^= sum over the accepted candidates k with bit p_k of c set (as it stands now) of S'_k
+            for (int g0 = warp * 32; g0 <= m; g0 += 4 * NW * 32) {
+                unsigned x[4];
+                int cb[4];
 #pragma unroll
-                        for (int w2 = w + 1; w2 < NW; ++w2) {
-                            const uint32_t has = __shfl_sync(FULL, (fr[w2] >> pb) & 1u, src);
-                            if (has) fr[w2] ^= fr[w];
-                            if (lane == src) fr[w2] &= ~(1u << pb);             // row p is used from now on
+                for (int i = 0; i < 4; ++i) {
+                    const int c = g0 + i * NW * 32 + lane;
+                    cb[i] = (c <= m ? c : m) * WM;
+                    x[i] = 0;
+                }
+                for (unsigned t = acc; t; t &= t - 1) {
+                    const int k = __ffs(t) - 1;
+                    const int p = s_p[k];
+                    const int wo = p >> 5, sh = p & 31;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] |= ((TC[cb[i] + wo] >> sh) & 1u) << k;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int c0 = g0 + i * NW * 32;
+                    unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= m);
+#ifdef QLDPC_OSD_TIMING
+                    osdt_hits += __popc(hit);
+#endif
+                    while (hit) {
+                        const int l = __ffs(hit) - 1;
+                        hit &= hit - 1;
+                        unsigned xx = __shfl_sync(FULL, x[i], l);
+                        if (lane < WM) {
+                            uint32_t sv = 0;
+                            while (xx) {
+                                const int k = __ffs(xx) - 1;
+                                xx &= xx - 1;
+                                sv ^= cand[(size_t)k * WM + lane];
+                            }
+                            TC[(size_t)(c0 + l) * WM + lane] ^= sv;
                         }
-                        ++k;
                     }
                 }
-                if (lane == 0) s_k = k;
             }
+            npiv += __popc(acc);
+            j += KB;
             __syncthreads();
-            const int nacc = s_k;                                   // pivots accepted in this round
-            // apply the batch: every column of T with bit p_a set ^= S_a, a = 0 .. K-1 in order (and so does the syndrome column)
-            for (int c0 = warp * 32; c0 < m; c0 += NW * 32) {
-                const int c = c0 + lane;
-                for (int a2 = 0; a2 < nacc; ++a2) {
-                    const int p = s_pp[a2];
-                    const uint32_t pbit = 1u << (p & 31);
-                    unsigned hit = __ballot_sync(FULL, c < m && (TC[(size_t)c * WM + (p >> 5)] & pbit));
-                    if (hit) {
-                        const uint32_t sv = (lane < WM) ? cand[(size_t)s_pw[a2] * WM + lane] : 0u;
-                        while (hit) {
-                            const int cc = c0 + __ffs(hit) - 1;
-                            hit &= hit - 1;
-                            if (lane < WM) TC[(size_t)cc * WM + lane] ^= sv;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-            if (warp == NW - 1) {
-                for (int a2 = 0; a2 < nacc; ++a2) {
-                    const int p = s_pp[a2];
-                    const bool hasb = (bw[p >> 5] >> (p & 31)) & 1u;
-                    __syncwarp();
-                    if (hasb && lane < WM) bw[lane] ^= cand[(size_t)s_pw[a2] * WM + lane];
-                    __syncwarp();
-                }
-            }
-            if (warp == 1) {
-                uint32_t u = (lane < WM) ? used[lane] : 0u;
-                for (int a2 = 0; a2 < nacc; ++a2) {
-                    const int p = s_pp[a2];
-                    if (lane == (p >> 5)) u |= 1u << (p & 31);
-                    if (lane == 0) { prow[npiv + a2] = (uint16_t)p; pcolj[npiv + a2] = (uint16_t)(j + s_pw[a2]); }
-                }
-                if (lane < WM) used[lane] = u;
-            }
-            npiv += nacc;
-            j += NW;
-            __syncthreads();
+            OSDT_MARK(4);
+#ifdef QLDPC_OSD_TIMING
+            ++osdt_rounds; osdt_piv += __popc(acc);
+#endif
         }
 
         // ---- validity; back-substitution over the pivots in reverse order ---------------------------
-        const uint32_t *ufin = used;
         int bad = 0;
         for (int w = tid; w < WM; w += NT) {
             const int rows = m - 32 * w;
             const uint32_t live = rows >= 32 ? 0xffffffffu : ((1u << rows) - 1u);
-            if (bw[w] & ~ufin[w] & live) bad = 1;
+            if (bw[w] & ~used[w] & live) bad = 1;
         }
         bad = __syncthreads_or(bad);
         if (bad) {                                                   // inconsistent syndrome: redo with the reference's pivot rule
@@ -1181,29 +1285,44 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             continue;
         }
         if (warp == 0) {
-            // x_k = b[p_k]; if set, b ^= reduced column j_k (its entries in the rows of the earlier pivots).  One word of b
-            // per lane and pass; passes over the word blocks are independent because every bit of b is read only after
-            // all later pivots have been applied, which the reverse order guarantees within a pass over ALL words --
-            // so the words are kept in shared memory and each step touches the whole column.
-            for (int k = npiv - 1; k >= 0; --k) {
-                const int r = prow[k], jk = pcolj[k];
-                const uint32_t bit = (bw[r >> 5] >> (r & 31)) & 1u;
-                __syncwarp();
-                if (bit) {
-                    for (int w = lane; w < WM; w += 32) {
-                        uint32_t x = reduced_word(jk, w);
-                        if (w == (r >> 5)) x &= ~(1u << (r & 31));       // keep x_k itself
-                        bw[w] ^= x & ufin[w];                            // (free rows are not involved any more)
-                    }
-                    if (lane == 0) { const int v = ord[jk]; solw[v >> 5] ^= 1u << (v & 31); }
+            // x_k = b[p_k]; if set, b ^= reduced column j_k (its entries in the rows of the earlier pivots).  Every bit of
+            // b is final once all later pivots have been applied, so the next pivot to fire is the LATEST pivot among
+            // the set bits of b that belong to pivots before the current one: found with one pass over the set bits (a
+            // word per lane) and a warp maximum -- as many steps as the solution has pivots, not as H has rows.
+            uint32_t bword = (lane < WM) ? (bw[lane] & used[lane]) : 0u;
+            int kcur = npiv;                                          // pivots >= kcur are done
+            while (true) {
+                int best = -1;
+                for (uint32_t t = bword; t; t &= t - 1) {
+                    const int kk = (int)rowpiv[32 * lane + __ffs(t) - 1];
+                    if (kk < kcur && kk > best) best = kk;
                 }
-                __syncwarp();
+                best = __reduce_max_sync(FULL, best);
+                if (best < 0) break;
+                const int r = prow[best], jk = pcolj[best];
+                if (lane < WM) {
+                    uint32_t x = reduced_word(jk, lane) & used[lane];
+                    if (lane == (r >> 5)) x &= ~(1u << (r & 31));    // keep x_k itself
+                    bword ^= x;
+                }
+                if (lane == 0) { const int v = ord[jk]; solw[v >> 5] ^= 1u << (v & 31); }
+                kcur = best;
             }
         }
         __syncthreads();
+        OSDT_MARK(5);
         for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
         if (tid == 0 && P.valid) P.valid[shot] = 1;
+#ifdef QLDPC_OSD_TIMING
+        ++osdt_shots;
+#endif
     }
+#ifdef QLDPC_OSD_TIMING
+    if (blockIdx.x == 0 && tid == 0 && osdt_shots)
+        printf("[osd timing] CTA 0: %lld shots, %lld rounds, %lld pivots, %lld column updates by warp 0 (of 8), %lld resolve fix-ups; cycles per shot: sort %lld, setup %lld, evaluate %lld, resolve %lld, apply %lld, backsub %lld, other %lld\n",
+               osdt_shots, osdt_rounds, osdt_piv, osdt_hits, osdt_fix, osdt[0] / osdt_shots, osdt[1] / osdt_shots, osdt[2] / osdt_shots, osdt[3] / osdt_shots,
+               osdt[4] / osdt_shots, osdt[5] / osdt_shots, osdt[7] / osdt_shots);
+#endif
 }
 
 }  // namespace qldpc

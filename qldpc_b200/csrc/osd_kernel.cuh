@@ -997,6 +997,8 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 #define OSDT_MARK(i)
 #endif
 
+template <int N> struct OsdIC { static constexpr int value = N; };
+
 template <typename K, bool PACKED>
 __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSDBlockParams P)
 {
@@ -1008,34 +1010,46 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
     const int tid = threadIdx.x, NT = OSDB_THREADS, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *TC = reinterpret_cast<uint32_t *>(smem);                      // [m + 1][WM]  column c of T; column m = syndrome
-    uint32_t *bw = TC + (size_t)m * WM;
-    uint16_t *prow = reinterpret_cast<uint16_t *>(TC + (size_t)(m + 1) * WM);   // [m] pivot row of the k-th pivot
+    uint32_t *TCP = reinterpret_cast<uint32_t *>(smem);                     // [m + 1][WM]  slot a: column prow[a] of T; slot m: syndrome column
+    uint32_t *bw = TCP + (size_t)m * WM;
+    uint16_t *prow = reinterpret_cast<uint16_t *>(TCP + (size_t)(m + 1) * WM);  // [m] pivot row of the k-th pivot
     uint16_t *pcolj = prow + m;                                            // [m] sorted position of the k-th pivot column
-    uint16_t *rowpiv = pcolj + m;                                          // [m] index of the pivot that row r belongs to
+    uint16_t *rowpiv = pcolj + m;                                          // [m] index of the pivot that row r belongs to, 0xFFFF: free
     uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(rowpiv + m) + 3) & ~(uintptr_t)3);   // [WM]
     uint32_t *cand = used + WM;                                             // [KB][WM] free rows of the candidates
     uint32_t *solw = cand + (size_t)KB * WM;                                // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
     uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
-    __shared__ int s_p[KB];
-    __shared__ unsigned s_acc;
+    __shared__ uint32_t s_pl[KB];                      // pivot rows accepted in this round, in order
+    __shared__ int s_off[KB];                          // and where their S' vectors are (offset into cand)
+    __shared__ int s_nacc;
     constexpr bool packed_chk = PACKED;               // m <= 1024 and column weight <= 3 (checked by the host)
 
-    // XOR of the TC columns of the checks of sorted position jj, word w
-    auto reduced_word = [&](int jj, int w) -> uint32_t {
+    // column c of T, word w: stored once row c has become a pivot row, the unit vector until then
+    auto tcol = [&](int c, int w) -> uint32_t {
+        const unsigned a = rowpiv[c];
+        return a != 0xFFFFu ? TCP[(size_t)a * WM + w] : ((c >> 5) == w ? (1u << (c & 31)) : 0u);
+    };
+    // reduced column (XOR of the T columns of its checks), word w: from the packed check list / of sorted position jj
+    auto reduced_packed = [&](uint32_t e, int w) -> uint32_t {
+        const int cnt = (int)(e >> 30);
         uint32_t x = 0;
-        const int col = ord[jj];
-        if (packed_chk) {
-            const uint32_t e = __ldg(P.colpack + col);
-            const int cnt = (int)(e >> 30);
-            if (cnt > 0) x = TC[(size_t)(e & 1023u) * WM + w];
-            if (cnt > 1) x ^= TC[(size_t)((e >> 10) & 1023u) * WM + w];
-            if (cnt > 2) x ^= TC[(size_t)((e >> 20) & 1023u) * WM + w];
-        } else {
-            for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= TC[(size_t)P.vtab[2 * a + 1] * WM + w];
-        }
+        if (cnt > 0) x = tcol((int)(e & 1023u), w);
+        if (cnt > 1) x ^= tcol((int)((e >> 10) & 1023u), w);
+        if (cnt > 2) x ^= tcol((int)((e >> 20) & 1023u), w);
         return x;
+    };
+    auto reduced_word = [&](int jj, int w) -> uint32_t {
+        const int col = ord[jj];
+        if (packed_chk) return reduced_packed(__ldg(P.colpack + col), w);
+        uint32_t x = 0;
+        for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= tcol((int)P.vtab[2 * a + 1], w);
+        return x;
+    };
+    // packed check lists of the candidates of the round that starts at sorted position jb: lane i < CPW holds candidate i * NW + warp
+    auto fetch = [&](int jb) -> uint32_t {
+        const int jj = jb + lane * NW + warp;
+        return (packed_chk && lane < CPW && jj < n) ? __ldg(P.colpack + ord[jj]) : 0u;
     };
 
     const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
@@ -1054,7 +1068,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         if (osdbf_bitonic_fits<K>(m, n)) {
             // bitonic sort of (key, index) pairs in the (still unused) transform area: O(n log^2 n) instead of the
             // O(n^2) rank counting -- 78 stages of 2048 compare-exchanges for n = 2592
-            kbits *sk = reinterpret_cast<kbits *>(TC);
+            kbits *sk = reinterpret_cast<kbits *>(TCP);
             uint16_t *si = reinterpret_cast<uint16_t *>(sk + N2);
             for (int j = tid; j < N2; j += NT) {
                 sk[j] = (j < n) ? KeyBits<K>::get(llr[j]) : ~(kbits)0;
@@ -1091,17 +1105,15 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         }
         __syncthreads();                                              // keys are dead from here on
         OSDT_MARK(0);
-        // ---- residual syndrome s ^ H*hard; T = I ------------------------------------------------
+        // ---- residual syndrome s ^ H*hard; T = I (no column stored yet) ---------------------------
         for (int v = tid; v < n; v += NT)
             if ((hard[v >> 5] >> (v & 31)) & 1u)
                 for (int a = P.var_ptr[v]; a < P.var_ptr[v + 1]; ++a) {
                     const int c = (int)P.vtab[2 * a + 1];
                     atomicXor(&bw[c >> 5], 1u << (c & 31));
                 }
-        for (int t = tid; t < m * WM; t += NT) {
-            const int c = t / WM, w = t - c * WM;
-            TC[t] = (w == (c >> 5)) ? (1u << (c & 31)) : 0u;
-        }
+        for (int r = tid; r < m; r += NT) rowpiv[r] = 0xFFFFu;
+        uint32_t e_cur = fetch(0);
         __syncthreads();
 
         // ---- forward elimination, KB candidate columns per round ------------------------------------
@@ -1109,41 +1121,66 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
         const int rank = P.rank;
         OSDT_MARK(1);
         while (j < n && npiv < rank) {
-            // evaluate: candidate k = i * NW + warp, a word per lane; lowest free row
+            // evaluate: candidate k = i * NW + warp, a word per lane (the check lists were fetched a round ahead)
             {
+                const uint32_t e_nx = fetch(j + KB);
                 uint32_t v[CPW];
 #pragma unroll
                 for (int i = 0; i < CPW; ++i) {
                     const int jj = j + i * NW + warp;
-                    v[i] = (lane < WM && jj < n) ? (reduced_word(jj, lane) & ~used[lane]) : 0u;
+                    const uint32_t e = __shfl_sync(FULL, e_cur, i);
+                    uint32_t x = 0;
+                    if (lane < WM && jj < n) x = (packed_chk ? reduced_packed(e, lane) : reduced_word(jj, lane)) & ~used[lane];
+                    v[i] = x;
                 }
 #pragma unroll
-                for (int i = 0; i < CPW; ++i) {
-                    const int k = i * NW + warp;
-                    if (lane < WM) cand[(size_t)k * WM + lane] = v[i];
-                    const unsigned bal = __ballot_sync(FULL, v[i] != 0);
-                    int p = -1;
-                    if (bal) {
-                        const int src = __ffs(bal) - 1;
-                        p = 32 * src + __ffs(__shfl_sync(FULL, v[i], src)) - 1;
-                    }
-                    if (lane == 0) s_p[k] = p;
-                }
+                for (int i = 0; i < CPW; ++i)
+                    if (lane < WM) cand[(size_t)(i * NW + warp) * WM + lane] = v[i];
+                e_cur = e_nx;
             }
             __syncthreads();
             OSDT_MARK(2);
             if (warp == 0) {
-                int p = s_p[lane];                                   // pivot row of candidate `lane`, -1: no free row
-                unsigned acc = __ballot_sync(FULL, p >= 0);
-                const unsigned below = (1u << lane) - 1u;
-                // interaction matrix: bit k of im = this candidate has the pivot row of candidate k
-                unsigned im = 0;
+                // bits that exactly one candidate of the round has (lane = word): a pivot row chosen among them is in no
+                // other candidate, so the candidate neither has to be brought to anyone else nor changes when others pivot
+                uint32_t uq = 0;
+                {
+                    uint32_t s1 = 0, s2 = 0;
+                    if (lane < WM) {
 #pragma unroll 8
-                for (int k = 0; k < KB; ++k) {
+                        for (int k = 0; k < KB; ++k) {
+                            const uint32_t x = cand[(size_t)k * WM + lane];
+                            s2 |= s1 & x;
+                            s1 |= x;
+                        }
+                    }
+                    uq = s1 & ~s2;
+                }
+                // lane = candidate: first exclusive bit, else first bit
+                int p = -1;
+                bool excl = false;
+                {
+                    int fu = -1, fx = -1;
+                    uint32_t wu = 0, wx = 0;
+#pragma unroll 3
+                    for (int w = WM - 1; w >= 0; --w) {
+                        const uint32_t x = cand[(size_t)lane * WM + w];
+                        const uint32_t u = x & __shfl_sync(FULL, uq, w);
+                        if (x) { fx = w; wx = x; }
+                        if (u) { fu = w; wu = u; }
+                    }
+                    if (fu >= 0) { p = 32 * fu + __ffs(wu) - 1; excl = true; }
+                    else if (fx >= 0) p = 32 * fx + __ffs(wx) - 1;
+                }
+                unsigned acc = __ballot_sync(FULL, p >= 0);
+                const unsigned shared_piv = __ballot_sync(FULL, p >= 0 && !excl);
+                const unsigned below = (1u << lane) - 1u;
+                // interaction matrix: bit k of im = this candidate has the pivot row of candidate k (possible for shared pivot rows only)
+                unsigned im = 0;
+                for (unsigned t = shared_piv; t; t &= t - 1) {
+                    const int k = __ffs(t) - 1;
                     const int pk = __shfl_sync(FULL, p, k);
-                    const int pc = pk < 0 ? 0 : pk;
-                    const uint32_t bit = (cand[(size_t)lane * WM + (pc >> 5)] >> (pc & 31)) & (pk < 0 ? 0u : 1u);
-                    im |= bit << k;
+                    im |= ((cand[(size_t)lane * WM + (pk >> 5)] >> (pk & 31)) & 1u) << k;
                 }
                 im &= ~(1u << lane);
                 // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
@@ -1166,24 +1203,32 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                         imk = __ballot_sync(FULL, p >= 0 && ((wv >> (pc & 31)) & 1u)) & acc & lowk & ~((2u << k) - 1u);
                     }
                     if (lane < WM) cand[(size_t)kp * WM + lane] = v;
-                    const unsigned bal = __ballot_sync(FULL, v != 0);
-                    int newp = -1;
-                    if (bal) {
-                        const int src = __ffs(bal) - 1;
-                        newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
+                    // the pivot row stays if the candidate still has it (always, if it was exclusive)
+                    const int oldp = __shfl_sync(FULL, p, kp);
+                    const bool keep = (__shfl_sync(FULL, v, oldp >> 5) >> (oldp & 31)) & 1u;
+                    int newp = oldp;
+                    if (!keep) {
+                        const unsigned bal = __ballot_sync(FULL, v != 0);
+                        newp = -1;
+                        if (bal) {
+                            const int src = __ffs(bal) - 1;
+                            newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
+                        }
+                        if (lane == kp) p = newp;
+                        if (newp < 0) acc &= ~(1u << kp);
                     }
-                    if (lane == kp) p = newp;
-                    if (newp < 0) acc &= ~(1u << kp);
                     __syncwarp();
-                    // refresh row kp and column kp of the interaction matrix
+                    // refresh row kp (and, with a new pivot row, column kp) of the interaction matrix
                     const int pc2 = p < 0 ? 0 : p;
                     const uint32_t wv = __shfl_sync(FULL, v, pc2 >> 5);
                     const unsigned rowkp = __ballot_sync(FULL, p >= 0 && ((wv >> (pc2 & 31)) & 1u)) & ~(1u << kp);
-                    uint32_t b = 0;
-                    if (newp >= 0) b = (cand[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
                     if (lane == kp) im = rowkp;
-                    else im = (im & ~(1u << kp)) | (b << kp);
-                    todo |= __ballot_sync(FULL, b != 0 && lane > kp);
+                    if (!keep) {
+                        uint32_t b = 0;
+                        if (newp >= 0) b = (cand[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
+                        if (lane != kp) im = (im & ~(1u << kp)) | (b << kp);
+                        todo |= __ballot_sync(FULL, b != 0 && lane > kp);
+                    }
                 }
                 // never more pivots than the rank of H
                 while (__popc(acc) > rank - npiv) acc &= ~(0x80000000u >> __clz(acc));
@@ -1211,39 +1256,43 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                 }
                 // publish the pivots
                 if (mine) {
-                    const int a = npiv + __popc(acc & below);
-                    prow[a] = (uint16_t)p;
-                    pcolj[a] = (uint16_t)(j + lane);
-                    rowpiv[p] = (uint16_t)a;
+                    const int a = __popc(acc & below);
+                    s_pl[a] = (uint32_t)p;
+                    s_off[a] = lane * WM;
+                    prow[npiv + a] = (uint16_t)p;
+                    pcolj[npiv + a] = (uint16_t)(j + lane);
+                    rowpiv[p] = (uint16_t)(npiv + a);
                     atomicOr(&used[p >> 5], 1u << (p & 31));
                 }
-                s_p[lane] = mine ? p : -1;
-                if (lane == 0) s_acc = acc;
+                if (lane == 0) s_nacc = __popc(acc);
             }
             __syncthreads();
             OSDT_MARK(3);
-            const unsigned acc = s_acc;
-            // apply: column c ^= sum over the accepted candidates k with bit p_k of c set (as it stands now) of S'_k
-            for (int g0 = warp * 32; g0 <= m; g0 += 4 * NW * 32) {
-                unsigned x[4];
-                int cb[4];
+            const int nacc = s_nacc;
+            // apply.  Row c of T is added to other rows only once c is a pivot row: the columns of free rows are unit vectors
+            // and have no pivot row of this round, so only the stored columns (pivots 0 .. npiv-1) and the syndrome take part.
+            // Column ^= sum over the accepted candidates a whose pivot row the column has (as it stands now) of S'_a.
+            auto apply_group = [&](auto ni_c, int g0) {
+                constexpr int NI = decltype(ni_c)::value;
+                unsigned x[NI];
+                int cb[NI];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int c = g0 + i * NW * 32 + lane;
-                    cb[i] = (c <= m ? c : m) * WM;
+                for (int i = 0; i < NI; ++i) {
+                    const int idx = g0 + i * NW * 32 + lane;
+                    cb[i] = (idx < npiv ? idx : m) * WM;
                     x[i] = 0;
                 }
-                for (unsigned t = acc; t; t &= t - 1) {
-                    const int k = __ffs(t) - 1;
-                    const int p = s_p[k];
-                    const int wo = p >> 5, sh = p & 31;
+#pragma unroll 4
+                for (int a = 0; a < nacc; ++a) {                     // bit nacc-1-a of x: pivot a
+                    const uint32_t p = s_pl[a];
+                    const int wo = (int)(p >> 5), sh = 31 - (int)(p & 31);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) x[i] |= ((TC[cb[i] + wo] >> sh) & 1u) << k;
+                    for (int i = 0; i < NI; ++i) x[i] = __funnelshift_l(TCP[cb[i] + wo] << sh, x[i], 1);
                 }
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < NI; ++i) {
                     const int c0 = g0 + i * NW * 32;
-                    unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= m);
+                    unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= npiv);
 #ifdef QLDPC_OSD_TIMING
                     osdt_hits += __popc(hit);
 #endif
@@ -1251,24 +1300,37 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                         const int l = __ffs(hit) - 1;
                         hit &= hit - 1;
                         unsigned xx = __shfl_sync(FULL, x[i], l);
+                        const int slot = (c0 + l < npiv) ? c0 + l : m;
                         if (lane < WM) {
                             uint32_t sv = 0;
                             while (xx) {
-                                const int k = __ffs(xx) - 1;
+                                const int b = __ffs(xx) - 1;
                                 xx &= xx - 1;
-                                sv ^= cand[(size_t)k * WM + lane];
+                                sv ^= cand[s_off[nacc - 1 - b] + lane];
                             }
-                            TC[(size_t)(c0 + l) * WM + lane] ^= sv;
+                            TCP[(size_t)slot * WM + lane] ^= sv;
                         }
                     }
                 }
+            };
+            for (int g0 = warp * 32; g0 <= npiv; g0 += 4 * NW * 32) {
+                const int ni = (npiv + 1 - g0 + NW * 32 - 1) / (NW * 32);
+                if (ni >= 4) apply_group(OsdIC<4>(), g0);
+                else if (ni == 3) apply_group(OsdIC<3>(), g0);
+                else if (ni == 2) apply_group(OsdIC<2>(), g0);
+                else apply_group(OsdIC<1>(), g0);
             }
-            npiv += __popc(acc);
+            // the columns of the new pivot rows: unit vector ^ S'
+            for (int a = warp; a < nacc; a += NW) {
+                const uint32_t p = s_pl[a];
+                if (lane < WM) TCP[(size_t)(npiv + a) * WM + lane] = cand[s_off[a] + lane] | (lane == (int)(p >> 5) ? (1u << (p & 31)) : 0u);
+            }
+            npiv += nacc;
             j += KB;
             __syncthreads();
             OSDT_MARK(4);
 #ifdef QLDPC_OSD_TIMING
-            ++osdt_rounds; osdt_piv += __popc(acc);
+            ++osdt_rounds; osdt_piv += nacc;
 #endif
         }
 

@@ -109,16 +109,17 @@ static cudaError_t launch_osd_block(const qldpc_code *c, const OSDBlockParams &P
 template <typename K>
 static cudaError_t launch_osd_block_fast(const qldpc_code *c, const OSDBlockParams &P, long long count_hint, cudaStream_t st)
 {
-    auto kern = P.colpack ? osd0_block_fast_kernel<K, true> : osd0_block_fast_kernel<K, false>;
+    auto kern = P.colpack ? (P.WM == 27 ? osd0_block_fast_kernel<K, true, 27> : osd0_block_fast_kernel<K, true, 0>)
+                          : (P.WM == 27 ? osd0_block_fast_kernel<K, false, 27> : osd0_block_fast_kernel<K, false, 0>);   // 27 words: [[144,12,12]] x 12 rounds
     const size_t smem = osdbf_smem_bytes<K>(P.m, P.n);
     if (smem > (size_t)c->smem_optin) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSDB_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, OSDBF_THREADS, smem);
     long long grid = (long long)c->num_sms * std::max(1, occ);
     if (count_hint >= 0) grid = std::max<long long>(1, std::min<long long>(grid, count_hint));
-    kern<<<(int)grid, OSDB_THREADS, smem, st>>>(P);
+    kern<<<(int)grid, OSDBF_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 

@@ -956,6 +956,10 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 // packed 3 x 10 bits (m <= 1024, column weight <= 3: the space-time matrices; otherwise from the CSC in global memory).
 // ------------------------------------------------------------------------------------------------
 constexpr int OSDB_BATCH = 32;
+#ifndef OSDBF_THREADS_N
+#define OSDBF_THREADS_N 512
+#endif
+constexpr int OSDBF_THREADS = OSDBF_THREADS_N;
 
 // the sort runs as a bitonic sort inside the (still idle) transform area when (key, index) pairs of the padded length fit
 // there; only the rank-counting fallback needs the keys outside of it.
@@ -990,24 +994,28 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 
 // -DQLDPC_OSD_TIMING: per-phase clock64() totals of CTA 0, printed at the end of the launch (diagnostic builds only)
 #ifdef QLDPC_OSD_TIMING
-#define OSDT_DECL long long osdt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, osdt_t = clock64(); long long osdt_rounds = 0, osdt_piv = 0, osdt_shots = 0, osdt_hits = 0, osdt_fix = 0
+#define OSDT_DECL long long osdt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, osdt_t = clock64(); long long osdt_rounds = 0, osdt_piv = 0, osdt_shots = 0, osdt_hits = 0, osdt_fix = 0, osdt_bfix = 0, osdt_zero = 0, osdt_lost = 0, osdt_shared = 0, osdt_r[6] = {0, 0, 0, 0, 0, 0}, osdt_rt = 0
 #define OSDT_MARK(i) do { const long long osdt_n = clock64(); osdt[i] += osdt_n - osdt_t; osdt_t = osdt_n; } while (0)
+#define OSDT_R0 osdt_rt = clock64()
+#define OSDT_R(i) do { const long long osdt_n = clock64(); osdt_r[i] += osdt_n - osdt_rt; osdt_rt = osdt_n; } while (0)
 #else
+#define OSDT_R0
+#define OSDT_R(i)
 #define OSDT_DECL
 #define OSDT_MARK(i)
 #endif
 
 template <int N> struct OsdIC { static constexpr int value = N; };
 
-template <typename K, bool PACKED>
-__global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSDBlockParams P)
+template <typename K, bool PACKED, int WMT>
+__global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const OSDBlockParams P)
 {
     typedef typename KeyBits<K>::type kbits;
-    constexpr int NW = OSDB_THREADS / 32;
+    constexpr int NW = OSDBF_THREADS / 32;
     constexpr int KB = OSDB_BATCH, CPW = KB / NW;               // candidates per round / per warp
     static_assert(KB == 32 && KB % NW == 0, "one candidate per lane of the resolving warp");
-    const int m = P.m, n = P.n, WM = P.WM, WN = P.WN;
-    const int tid = threadIdx.x, NT = OSDB_THREADS, lane = tid & 31, warp = tid >> 5;
+    const int m = P.m, n = P.n, WM = WMT ? WMT : P.WM, WN = P.WN;       // WMT: the word count at compile time (loops over words unroll), 0: any
+    const int tid = threadIdx.x, NT = OSDBF_THREADS, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *TCP = reinterpret_cast<uint32_t *>(smem);                     // [m + 1][WM]  slot a: column prow[a] of T; slot m: syndrome column
@@ -1023,6 +1031,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
     __shared__ uint32_t s_pl[KB];                      // pivot rows accepted in this round, in order
     __shared__ int s_off[KB];                          // and where their S' vectors are (offset into cand)
     __shared__ int s_nacc;
+    __shared__ int s_p0[KB];                           // lowest free row of a candidate, -1: none
     constexpr bool packed_chk = PACKED;               // m <= 1024 and column weight <= 3 (checked by the host)
 
     // column c of T, word w: stored once row c has become a pivot row, the unit vector until then
@@ -1134,8 +1143,16 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                     v[i] = x;
                 }
 #pragma unroll
-                for (int i = 0; i < CPW; ++i)
+                for (int i = 0; i < CPW; ++i) {
                     if (lane < WM) cand[(size_t)(i * NW + warp) * WM + lane] = v[i];
+                    const unsigned bal = __ballot_sync(FULL, v[i] != 0);
+                    int p0 = -1;
+                    if (bal) {
+                        const int src = __ffs(bal) - 1;
+                        p0 = 32 * src + __ffs(__shfl_sync(FULL, v[i], src)) - 1;
+                    }
+                    if (lane == 0) s_p0[i * NW + warp] = p0;
+                }
                 e_cur = e_nx;
             }
             __syncthreads();
@@ -1143,11 +1160,12 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
             if (warp == 0) {
                 // bits that exactly one candidate of the round has (lane = word): a pivot row chosen among them is in no
                 // other candidate, so the candidate neither has to be brought to anyone else nor changes when others pivot
+                OSDT_R0;
                 uint32_t uq = 0;
                 {
                     uint32_t s1 = 0, s2 = 0;
                     if (lane < WM) {
-#pragma unroll 8
+#pragma unroll
                         for (int k = 0; k < KB; ++k) {
                             const uint32_t x = cand[(size_t)k * WM + lane];
                             s2 |= s1 & x;
@@ -1156,80 +1174,91 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                     }
                     uq = s1 & ~s2;
                 }
+                OSDT_R(0);
                 // lane = candidate: first exclusive bit, else first bit
-                int p = -1;
+                int p = s_p0[lane];
                 bool excl = false;
                 {
-                    int fu = -1, fx = -1;
-                    uint32_t wu = 0, wx = 0;
-#pragma unroll 3
+                    int fu = -1;
+                    uint32_t wu = 0;
+#pragma unroll
                     for (int w = WM - 1; w >= 0; --w) {
-                        const uint32_t x = cand[(size_t)lane * WM + w];
-                        const uint32_t u = x & __shfl_sync(FULL, uq, w);
-                        if (x) { fx = w; wx = x; }
+                        const uint32_t u = cand[(size_t)lane * WM + w] & __shfl_sync(FULL, uq, w);
                         if (u) { fu = w; wu = u; }
                     }
                     if (fu >= 0) { p = 32 * fu + __ffs(wu) - 1; excl = true; }
-                    else if (fx >= 0) p = 32 * fx + __ffs(wx) - 1;
                 }
+                OSDT_R(1);
                 unsigned acc = __ballot_sync(FULL, p >= 0);
                 const unsigned shared_piv = __ballot_sync(FULL, p >= 0 && !excl);
                 const unsigned below = (1u << lane) - 1u;
-                // interaction matrix: bit k of im = this candidate has the pivot row of candidate k (possible for shared pivot rows only)
+                // interaction matrix: bit k of im = this candidate has the pivot row of candidate k (shared pivot rows only: an
+                // exclusive one is in nobody else), bit `lane` = it has its own.  Reducing candidate k' by candidate k is
+                // im[k'] ^= im[k] on this matrix -- the vectors themselves are only touched to carry the XOR out.
                 unsigned im = 0;
-                for (unsigned t = shared_piv; t; t &= t - 1) {
-                    const int k = __ffs(t) - 1;
-                    const int pk = __shfl_sync(FULL, p, k);
-                    im |= ((cand[(size_t)lane * WM + (pk >> 5)] >> (pk & 31)) & 1u) << k;
+                for (unsigned t = shared_piv; t;) {
+                    int kk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { kk[u] = t ? __ffs(t) - 1 : -1; t &= t - 1; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int pk = __shfl_sync(FULL, p, kk[u] < 0 ? 0 : kk[u]);
+                        if (kk[u] >= 0) im |= ((cand[(size_t)lane * WM + (pk >> 5)] >> (pk & 31)) & 1u) << kk[u];
+                    }
                 }
-                im &= ~(1u << lane);
+                if (p >= 0) im |= 1u << lane;
+                OSDT_R(2);
+#ifdef QLDPC_OSD_TIMING
+                osdt_shared += __popc(shared_piv);
+#endif
                 // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
                 unsigned todo = __ballot_sync(FULL, (im & below & acc) != 0);
                 while (todo) {
                     const int kp = __ffs(todo) - 1;
                     todo &= todo - 1;
                     const unsigned lowk = (1u << kp) - 1u;
-                    unsigned imk = __shfl_sync(FULL, im, kp) & acc & lowk;
+                    unsigned row = __shfl_sync(FULL, im, kp);
+                    unsigned imk = row & acc & lowk;
                     if (!imk) continue;
 #ifdef QLDPC_OSD_TIMING
                     ++osdt_fix;
 #endif
                     uint32_t v = (lane < WM) ? cand[(size_t)kp * WM + lane] : 0u;
-                    const int pc = p < 0 ? 0 : p;
-                    while (imk) {
-                        const int k = __ffs(imk) - 1;
+                    do {
+                        const int k = __ffs(imk) - 1;                 // rows of accepted candidates have nothing below their own bit
                         if (lane < WM) v ^= cand[(size_t)k * WM + lane];
-                        const uint32_t wv = __shfl_sync(FULL, v, pc >> 5);
-                        imk = __ballot_sync(FULL, p >= 0 && ((wv >> (pc & 31)) & 1u)) & acc & lowk & ~((2u << k) - 1u);
-                    }
+                        row ^= __shfl_sync(FULL, im, k);
+                        imk = row & acc & lowk;
+                    } while (imk);
                     if (lane < WM) cand[(size_t)kp * WM + lane] = v;
-                    // the pivot row stays if the candidate still has it (always, if it was exclusive)
-                    const int oldp = __shfl_sync(FULL, p, kp);
-                    const bool keep = (__shfl_sync(FULL, v, oldp >> 5) >> (oldp & 31)) & 1u;
-                    int newp = oldp;
-                    if (!keep) {
-                        const unsigned bal = __ballot_sync(FULL, v != 0);
-                        newp = -1;
-                        if (bal) {
-                            const int src = __ffs(bal) - 1;
-                            newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
-                        }
-                        if (lane == kp) p = newp;
-                        if (newp < 0) acc &= ~(1u << kp);
+                    if ((row >> kp) & 1u) {                            // it still has its pivot row
+                        if (lane == kp) im = row;
+                        __syncwarp();
+                        continue;
                     }
+#ifdef QLDPC_OSD_TIMING
+                    ++osdt_lost;
+#endif
+                    const unsigned bal = __ballot_sync(FULL, v != 0);
+                    if (!bal) {                                        // dependent on the candidates before it
+#ifdef QLDPC_OSD_TIMING
+                        ++osdt_zero;
+#endif
+                        acc &= ~(1u << kp);
+                        if (lane == kp) { p = -1; im = 0; }
+                        __syncwarp();
+                        continue;
+                    }
+                    const int src = __ffs(bal) - 1;
+                    const int newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
                     __syncwarp();
-                    // refresh row kp (and, with a new pivot row, column kp) of the interaction matrix
-                    const int pc2 = p < 0 ? 0 : p;
-                    const uint32_t wv = __shfl_sync(FULL, v, pc2 >> 5);
-                    const unsigned rowkp = __ballot_sync(FULL, p >= 0 && ((wv >> (pc2 & 31)) & 1u)) & ~(1u << kp);
-                    if (lane == kp) im = rowkp;
-                    if (!keep) {
-                        uint32_t b = 0;
-                        if (newp >= 0) b = (cand[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
-                        if (lane != kp) im = (im & ~(1u << kp)) | (b << kp);
-                        todo |= __ballot_sync(FULL, b != 0 && lane > kp);
-                    }
+                    // a new pivot row: column kp of the matrix changes
+                    const uint32_t b = (cand[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
+                    if (lane == kp) { p = newp; im = row | (1u << kp); }
+                    else im = (im & ~(1u << kp)) | (b << kp);
+                    todo |= __ballot_sync(FULL, b != 0 && lane > kp);
                 }
+                OSDT_R(3);
                 // never more pivots than the rank of H
                 while (__popc(acc) > rank - npiv) acc &= ~(0x80000000u >> __clz(acc));
                 const bool mine = (acc >> lane) & 1u;
@@ -1243,7 +1272,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                     bt &= ~(1u << b);
                     unsigned jb = __shfl_sync(FULL, jm, b);
 #ifdef QLDPC_OSD_TIMING
-                    ++osdt_fix;
+                    ++osdt_bfix;
 #endif
                     uint32_t v = 0;
                     while (jb) {
@@ -1254,6 +1283,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                     if (lane < WM) cand[(size_t)b * WM + lane] ^= v;
                     __syncwarp();
                 }
+                OSDT_R(4);
                 // publish the pivots
                 if (mine) {
                     const int a = __popc(acc & below);
@@ -1265,6 +1295,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
                     atomicOr(&used[p >> 5], 1u << (p & 31));
                 }
                 if (lane == 0) s_nacc = __popc(acc);
+                OSDT_R(5);
             }
             __syncthreads();
             OSDT_MARK(3);
@@ -1380,10 +1411,14 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_fast_kernel(const OSD
 #endif
     }
 #ifdef QLDPC_OSD_TIMING
-    if (blockIdx.x == 0 && tid == 0 && osdt_shots)
+    if (blockIdx.x == 0 && tid == 0 && osdt_shots) {
+        printf("[osd resolve] per round: shared-pivot candidates %.2f, forward fix-ups %.2f (pivot lost %.2f, dependent %.2f), backward folds %.2f; cycles: exclusive bits %lld, pivot choice %lld, interaction gather %lld, forward %lld, truncate+fold %lld, publish %lld\n",
+               (double)osdt_shared / osdt_rounds, (double)osdt_fix / osdt_rounds, (double)osdt_lost / osdt_rounds, (double)osdt_zero / osdt_rounds, (double)osdt_bfix / osdt_rounds,
+               osdt_r[0] / osdt_rounds, osdt_r[1] / osdt_rounds, osdt_r[2] / osdt_rounds, osdt_r[3] / osdt_rounds, osdt_r[4] / osdt_rounds, osdt_r[5] / osdt_rounds);
         printf("[osd timing] CTA 0: %lld shots, %lld rounds, %lld pivots, %lld column updates by warp 0 (of 8), %lld resolve fix-ups; cycles per shot: sort %lld, setup %lld, evaluate %lld, resolve %lld, apply %lld, backsub %lld, other %lld\n",
                osdt_shots, osdt_rounds, osdt_piv, osdt_hits, osdt_fix, osdt[0] / osdt_shots, osdt[1] / osdt_shots, osdt[2] / osdt_shots, osdt[3] / osdt_shots,
                osdt[4] / osdt_shots, osdt[5] / osdt_shots, osdt[7] / osdt_shots);
+    }
 #endif
 }
 

@@ -994,16 +994,55 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 
 // -DQLDPC_OSD_TIMING: per-phase clock64() totals of CTA 0, printed at the end of the launch (diagnostic builds only)
 #ifdef QLDPC_OSD_TIMING
-#define OSDT_DECL long long osdt[8] = {0, 0, 0, 0, 0, 0, 0, 0}, osdt_t = clock64(); long long osdt_rounds = 0, osdt_piv = 0, osdt_shots = 0, osdt_hits = 0, osdt_fix = 0, osdt_bfix = 0, osdt_zero = 0, osdt_lost = 0, osdt_shared = 0, osdt_r[6] = {0, 0, 0, 0, 0, 0}, osdt_rt = 0
-#define OSDT_MARK(i) do { const long long osdt_n = clock64(); osdt[i] += osdt_n - osdt_t; osdt_t = osdt_n; } while (0)
-#define OSDT_R0 osdt_rt = clock64()
-#define OSDT_R(i) do { const long long osdt_n = clock64(); osdt_r[i] += osdt_n - osdt_rt; osdt_rt = osdt_n; } while (0)
+// accumulators in shared memory, touched by thread 0 only (registers are scarce at 512 threads x 2 CTAs)
+#define OSDT_DECL __shared__ long long osdt_sh[32]; long long *osdt = osdt_sh, *osdt_r = osdt_sh + 8; \
+    long long &osdt_t = osdt_sh[14], &osdt_rt = osdt_sh[15], &osdt_rounds = osdt_sh[16], &osdt_piv = osdt_sh[17], &osdt_shots = osdt_sh[18], &osdt_hits = osdt_sh[19], \
+              &osdt_fix = osdt_sh[20], &osdt_bfix = osdt_sh[21], &osdt_zero = osdt_sh[22], &osdt_lost = osdt_sh[23], &osdt_shared = osdt_sh[24]; \
+    if (threadIdx.x == 0) { for (int i = 0; i < 32; ++i) osdt_sh[i] = 0; osdt_t = clock64(); } __syncthreads()
+#define OSDT_MARK(i) do { if (threadIdx.x == 0) { const long long osdt_n = clock64(); osdt[i] += osdt_n - osdt_t; osdt_t = osdt_n; } } while (0)
+#define OSDT_R0 do { if (threadIdx.x == 0) osdt_rt = clock64(); } while (0)
+#define OSDT_R(i) do { if (threadIdx.x == 0) { const long long osdt_n = clock64(); osdt_r[i] += osdt_n - osdt_rt; osdt_rt = osdt_n; } } while (0)
+#define OSDT_ADD(var, val) do { if (threadIdx.x == 0) var += (val); } while (0)
 #else
-#define OSDT_R0
-#define OSDT_R(i)
 #define OSDT_DECL
 #define OSDT_MARK(i)
+#define OSDT_R0
+#define OSDT_R(i)
+#define OSDT_ADD(var, val)
 #endif
+
+// (key, index) pairs of the block kernel's register-resident bitonic sort.  float keys: one 64-bit word, key << 16 | index (a single
+// unsigned compare orders by key, then by index: the stable order); double keys: the 64-bit key and the index side by side.
+template <typename KBt> struct OsdSortElem;
+template <> struct OsdSortElem<uint32_t> {
+    unsigned long long v;
+    static constexpr int BYTES = 8;
+    __device__ __forceinline__ static OsdSortElem make(uint32_t key, uint32_t idx) { return OsdSortElem{((unsigned long long)key << 16) | idx}; }
+    __device__ __forceinline__ bool after(const OsdSortElem &o) const { return v > o.v; }
+    __device__ __forceinline__ OsdSortElem shfl_xor(int mask) const { return OsdSortElem{__shfl_xor_sync(0xffffffffu, v, mask)}; }
+    __device__ __forceinline__ uint32_t index() const { return (uint32_t)v & 0xFFFFu; }
+    __device__ __forceinline__ void store(unsigned char *base, int N2, int buf, int pos) const { reinterpret_cast<unsigned long long *>(base)[buf * N2 + pos] = v; }
+    __device__ __forceinline__ static OsdSortElem load(const unsigned char *base, int N2, int buf, int pos) { return OsdSortElem{reinterpret_cast<const unsigned long long *>(base)[buf * N2 + pos]}; }
+};
+template <> struct OsdSortElem<unsigned long long> {
+    unsigned long long k;
+    uint32_t i;
+    static constexpr int BYTES = 10;
+    __device__ __forceinline__ static OsdSortElem make(unsigned long long key, uint32_t idx) { return OsdSortElem{key, idx}; }
+    __device__ __forceinline__ bool after(const OsdSortElem &o) const { return k > o.k || (k == o.k && i > o.i); }
+    __device__ __forceinline__ OsdSortElem shfl_xor(int mask) const { return OsdSortElem{__shfl_xor_sync(0xffffffffu, k, mask), __shfl_xor_sync(0xffffffffu, i, mask)}; }
+    __device__ __forceinline__ uint32_t index() const { return i; }
+    __device__ __forceinline__ void store(unsigned char *base, int N2, int buf, int pos) const
+    {
+        reinterpret_cast<unsigned long long *>(base)[buf * N2 + pos] = k;
+        reinterpret_cast<uint16_t *>(base + 16 * (size_t)N2)[buf * N2 + pos] = (uint16_t)i;
+    }
+    __device__ __forceinline__ static OsdSortElem load(const unsigned char *base, int N2, int buf, int pos)
+    {
+        return OsdSortElem{reinterpret_cast<const unsigned long long *>(base)[buf * N2 + pos], reinterpret_cast<const uint16_t *>(base + 16 * (size_t)N2)[buf * N2 + pos]};
+    }
+};
+constexpr int OSDBF_EPT = 8;                 // elements per thread of the register-resident sort
 
 template <int N> struct OsdIC { static constexpr int value = N; };
 
@@ -1074,7 +1113,64 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
         int N2 = 1;
         while (N2 < n) N2 <<= 1;
-        if (osdbf_bitonic_fits<K>(m, n)) {
+        if (N2 == OSDBF_EPT * NT && (size_t)2 * N2 * OsdSortElem<kbits>::BYTES <= 4 * (size_t)m * WM) {
+            // bitonic sort with the elements in registers: thread (warp, lane) holds the elements 256 warp + 32 e + lane, e < 8.
+            // Partners at distance < 32 come by shuffle, at 32 / 64 / 128 from the thread's own registers; only the 10 stages at
+            // distance >= 256 (of 78) go through shared memory (double-buffered in the still unused transform area: one barrier each).
+            typedef OsdSortElem<kbits> El;
+            constexpr int EPT = OSDBF_EPT;
+            El el[EPT];
+            const int bi = warp * (32 * EPT) + lane;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = bi + 32 * e;
+                el[e] = (i < n) ? El::make(KeyBits<K>::get(llr[i]), (uint32_t)i) : El::make(~(kbits)0, 0xFFFFu);
+            }
+            // element i takes its partner's value iff (mine > partner) ^ (i is the upper one of the pair) ^ (i lies in a descending block)
+            auto reg_stage = [&](auto d_c, unsigned descm) {
+                constexpr int D = decltype(d_c)::value;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if ((e & D) == 0) {
+                        if (el[e].after(el[e | D]) != (bool)((descm >> e) & 1u)) { const El t = el[e]; el[e] = el[e | D]; el[e | D] = t; }
+                    }
+            };
+            unsigned char *sbase = reinterpret_cast<unsigned char *>(TCP);
+            int buf = 0;
+            for (int k = 2; k <= N2; k <<= 1) {
+                // bit e of descm: element e of this thread lies in a descending block of length k
+                unsigned descm = 0;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) descm |= (((bi + 32 * e) & k) != 0 ? 1u : 0u) << e;
+                for (int jd = k >> 1; jd > 0; jd >>= 1) {
+                    if (jd >= 32 * EPT) {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) el[e].store(sbase, N2, buf, bi + 32 * e);
+                        __syncthreads();
+                        const bool hi = (bi & jd) != 0;                                  // (a warp bit)
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const El o = El::load(sbase, N2, buf, (bi + 32 * e) ^ jd);
+                            if (el[e].after(o) != (hi != (bool)((descm >> e) & 1u))) el[e] = o;
+                        }
+                        buf ^= 1;
+                    } else if (jd == 128) reg_stage(OsdIC<4>(), descm);
+                    else if (jd == 64) reg_stage(OsdIC<2>(), descm);
+                    else if (jd == 32) reg_stage(OsdIC<1>(), descm);
+                    else {
+                        const bool hi = (lane & jd) != 0;
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const El o = el[e].shfl_xor(jd);
+                            if (el[e].after(o) != (hi != (bool)((descm >> e) & 1u))) el[e] = o;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (bi + 32 * e < n) ord[bi + 32 * e] = (uint16_t)el[e].index();
+        } else if (osdbf_bitonic_fits<K>(m, n)) {
             // bitonic sort of (key, index) pairs in the (still unused) transform area: O(n log^2 n) instead of the
             // O(n^2) rank counting -- 78 stages of 2048 compare-exchanges for n = 2592
             kbits *sk = reinterpret_cast<kbits *>(TCP);
@@ -1208,9 +1304,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 }
                 if (p >= 0) im |= 1u << lane;
                 OSDT_R(2);
-#ifdef QLDPC_OSD_TIMING
-                osdt_shared += __popc(shared_piv);
-#endif
+OSDT_ADD(osdt_shared, __popc(shared_piv));
                 // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
                 unsigned todo = __ballot_sync(FULL, (im & below & acc) != 0);
                 while (todo) {
@@ -1220,9 +1314,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     unsigned row = __shfl_sync(FULL, im, kp);
                     unsigned imk = row & acc & lowk;
                     if (!imk) continue;
-#ifdef QLDPC_OSD_TIMING
-                    ++osdt_fix;
-#endif
+OSDT_ADD(osdt_fix, 1);
                     uint32_t v = (lane < WM) ? cand[(size_t)kp * WM + lane] : 0u;
                     do {
                         const int k = __ffs(imk) - 1;                 // rows of accepted candidates have nothing below their own bit
@@ -1236,14 +1328,10 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                         __syncwarp();
                         continue;
                     }
-#ifdef QLDPC_OSD_TIMING
-                    ++osdt_lost;
-#endif
+OSDT_ADD(osdt_lost, 1);
                     const unsigned bal = __ballot_sync(FULL, v != 0);
                     if (!bal) {                                        // dependent on the candidates before it
-#ifdef QLDPC_OSD_TIMING
-                        ++osdt_zero;
-#endif
+OSDT_ADD(osdt_zero, 1);
                         acc &= ~(1u << kp);
                         if (lane == kp) { p = -1; im = 0; }
                         __syncwarp();
@@ -1271,9 +1359,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     const int b = 31 - __clz(bt);
                     bt &= ~(1u << b);
                     unsigned jb = __shfl_sync(FULL, jm, b);
-#ifdef QLDPC_OSD_TIMING
-                    ++osdt_bfix;
-#endif
+OSDT_ADD(osdt_bfix, 1);
                     uint32_t v = 0;
                     while (jb) {
                         const int a = __ffs(jb) - 1;
@@ -1324,9 +1410,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 for (int i = 0; i < NI; ++i) {
                     const int c0 = g0 + i * NW * 32;
                     unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= npiv);
-#ifdef QLDPC_OSD_TIMING
-                    osdt_hits += __popc(hit);
-#endif
+OSDT_ADD(osdt_hits, __popc(hit));
                     while (hit) {
                         const int l = __ffs(hit) - 1;
                         hit &= hit - 1;
@@ -1360,9 +1444,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
             j += KB;
             __syncthreads();
             OSDT_MARK(4);
-#ifdef QLDPC_OSD_TIMING
-            ++osdt_rounds; osdt_piv += nacc;
-#endif
+OSDT_ADD(osdt_rounds, 1); OSDT_ADD(osdt_piv, nacc);
         }
 
         // ---- validity; back-substitution over the pivots in reverse order ---------------------------
@@ -1406,9 +1488,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
         OSDT_MARK(5);
         for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
         if (tid == 0 && P.valid) P.valid[shot] = 1;
-#ifdef QLDPC_OSD_TIMING
-        ++osdt_shots;
-#endif
+OSDT_ADD(osdt_shots, 1);
     }
 #ifdef QLDPC_OSD_TIMING
     if (blockIdx.x == 0 && tid == 0 && osdt_shots) {

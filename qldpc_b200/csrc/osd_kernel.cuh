@@ -984,7 +984,7 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     o += 2 * (size_t)m * 3;                                     // pivot rows / sorted positions of the pivot columns / pivot index of a row (uint16)
     o = (o + 3) & ~(size_t)3;
     o += 4 * (size_t)WM;                                        // used
-    o += 4 * (size_t)WM * OSDB_BATCH * 3;                       // candidate columns of three consecutive rounds
+    o += 4 * (size_t)WM * OSDB_BATCH;                           // candidate columns of the round
     o += 4 * (size_t)WN;                                        // solution words
     o = (o + 7) & ~(size_t)7;
     o += osdbf_key_area<K>(m, n);                               // keys (rank-counting path only)
@@ -992,6 +992,24 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     return o + 64;
 }
 
+// -DQLDPC_OSD_TIMING: per-phase clock64() totals of CTA 0, printed at the end of the launch (diagnostic builds only)
+#ifdef QLDPC_OSD_TIMING
+// accumulators in shared memory, touched by thread 0 only (registers are scarce at 512 threads x 2 CTAs)
+#define OSDT_DECL __shared__ long long osdt_sh[32]; long long *osdt = osdt_sh, *osdt_r = osdt_sh + 8; \
+    long long &osdt_t = osdt_sh[14], &osdt_rt = osdt_sh[15], &osdt_rounds = osdt_sh[16], &osdt_piv = osdt_sh[17], &osdt_shots = osdt_sh[18], &osdt_hits = osdt_sh[19], \
+              &osdt_fix = osdt_sh[20], &osdt_bfix = osdt_sh[21], &osdt_zero = osdt_sh[22], &osdt_lost = osdt_sh[23], &osdt_shared = osdt_sh[24]; \
+    if (threadIdx.x == 0) { for (int i = 0; i < 32; ++i) osdt_sh[i] = 0; osdt_t = clock64(); } __syncthreads()
+#define OSDT_MARK(i) do { if (threadIdx.x == 0) { const long long osdt_n = clock64(); osdt[i] += osdt_n - osdt_t; osdt_t = osdt_n; } } while (0)
+#define OSDT_R0 do { if (threadIdx.x == 0) osdt_rt = clock64(); } while (0)
+#define OSDT_R(i) do { if (threadIdx.x == 0) { const long long osdt_n = clock64(); osdt_r[i] += osdt_n - osdt_rt; osdt_rt = osdt_n; } } while (0)
+#define OSDT_ADD(var, val) do { if (threadIdx.x == 0) var += (val); } while (0)
+#else
+#define OSDT_DECL
+#define OSDT_MARK(i)
+#define OSDT_R0
+#define OSDT_R(i)
+#define OSDT_ADD(var, val)
+#endif
 
 // (key, index) pairs of the block kernel's register-resident bitonic sort.  float keys: one 64-bit word, key << 16 | index (a single
 // unsigned compare orders by key, then by index: the stable order); double keys: the 64-bit key and the index side by side.
@@ -1032,9 +1050,8 @@ template <typename K, bool PACKED, int WMT>
 __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const OSDBlockParams P)
 {
     typedef typename KeyBits<K>::type kbits;
-    constexpr int NW = OSDBF_THREADS / 32, NWW = NW - 1;        // warps; worker warps (warp 0 resolves)
-    constexpr int KB = OSDB_BATCH;                              // candidates per round
-    constexpr int CPW = (KB + NWW - 1) / NWW;                   // candidates per worker warp
+    constexpr int NW = OSDBF_THREADS / 32;
+    constexpr int KB = OSDB_BATCH, CPW = KB / NW;               // candidates per round / per warp
     static_assert(KB == 32 && KB % NW == 0, "one candidate per lane of the resolving warp");
     const int m = P.m, n = P.n, WM = WMT ? WMT : P.WM, WN = P.WN;       // WMT: the word count at compile time (loops over words unroll), 0: any
     const int tid = threadIdx.x, NT = OSDBF_THREADS, lane = tid & 31, warp = tid >> 5;
@@ -1046,16 +1063,14 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
     uint16_t *pcolj = prow + m;                                            // [m] sorted position of the k-th pivot column
     uint16_t *rowpiv = pcolj + m;                                          // [m] index of the pivot that row r belongs to, 0xFFFF: free
     uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(rowpiv + m) + 3) & ~(uintptr_t)3);   // [WM]
-    uint32_t *cand = used + WM;                                             // [3][KB][WM] free rows of the candidates of three consecutive rounds
-    uint32_t *solw = cand + (size_t)3 * KB * WM;                            // [WN]
+    uint32_t *cand = used + WM;                                             // [KB][WM] free rows of the candidates
+    uint32_t *solw = cand + (size_t)KB * WM;                                // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
     uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
-    // per round, double-buffered by its parity: what warp 0 hands to the workers
-    __shared__ uint16_t s_pl[2][KB];                   // accepted candidates in order: pivot row | candidate << 10
-    __shared__ int16_t s_p0[2][KB];                    // lowest free row of a candidate as evaluated, -1: none
-    __shared__ uint32_t s_fm[2][KB];                   // chain entries (see resolve): mask of the earlier pivots whose S has this pivot row ...
-    __shared__ uint8_t s_fq[2][KB];                    // ... and the coefficient bit they correct
-    __shared__ int s_nacc[2], s_nfold[2], s_last[2];
+    __shared__ uint32_t s_pl[KB];                      // pivot rows accepted in this round, in order
+    __shared__ int s_off[KB];                          // and where their S' vectors are (offset into cand)
+    __shared__ int s_nacc;
+    __shared__ int s_p0[KB];                           // lowest free row of a candidate, -1: none
     constexpr bool packed_chk = PACKED;               // m <= 1024 and column weight <= 3 (checked by the host)
 
     // column c of T, word w: stored once row c has become a pivot row, the unit vector until then
@@ -1079,13 +1094,20 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
         for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= tcol((int)P.vtab[2 * a + 1], w);
         return x;
     };
+    // packed check lists of the candidates of the round that starts at sorted position jb: lane i < CPW holds candidate i * NW + warp
+    auto fetch = [&](int jb) -> uint32_t {
+        const int jj = jb + lane * NW + warp;
+        return (packed_chk && lane < CPW && jj < n) ? __ldg(P.colpack + ord[jj]) : 0u;
+    };
 
     const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
+    OSDT_DECL;
     for (long long it = blockIdx.x; it < count; it += gridDim.x) {
         const long long shot = P.idx ? (long long)P.idx[it] : it;
         const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
         const uint32_t *hard = P.hard + (size_t)shot * WN;
         __syncthreads();
+        OSDT_MARK(7);
         // ---- stable ascending order of |llr| ----------------------------------------------------
         for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; }
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
@@ -1187,6 +1209,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
             }
         }
         __syncthreads();                                              // keys are dead from here on
+        OSDT_MARK(0);
         // ---- residual syndrome s ^ H*hard; T = I (no column stored yet) ---------------------------
         for (int v = tid; v < n; v += NT)
             if ((hard[v >> 5] >> (v & 31)) & 1u)
@@ -1195,301 +1218,233 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     atomicXor(&bw[c >> 5], 1u << (c & 31));
                 }
         for (int r = tid; r < m; r += NT) rowpiv[r] = 0xFFFFu;
+        uint32_t e_cur = fetch(0);
         __syncthreads();
 
-        // ---- forward elimination, KB candidate columns per round, software-pipelined ---------------------
-        // Round r = the candidates at sorted positions 32 r .. 32 r + 31; T(r) = the transform after rounds < r; E_r = the row
-        // operations of round r as the linear map  c -> c ^ sum_a x_a S_a,  x_a = c[p_a] ^ sum_{b < a, S_b[p_a]} x_b.
-        // In slot s, concurrently:
-        //   warp 0       brings the candidates of round s+1 (evaluated against T(s)) up to date with E_s -- the map acts on a
-        //                candidate like on any column of T -- and resolves round s+1 (pivot rows, S vectors, chain entries);
-        //   warps 1..15  apply E_s to the stored columns of T and to the syndrome, then evaluate the candidates of round s+2
-        //                against T(s+1).
-        // One block barrier per round; the serial resolve of one round runs under the apply of the previous one.
+        // ---- forward elimination, KB candidate columns per round ------------------------------------
+        int j = 0, npiv = 0;
         const int rank = P.rank;
-        int npiv = 0;                                                // pivots applied to T
-        int npivR = 0;                                               // warp 0: pivots published
-        auto cbuf = [&](int r) -> uint32_t * { return cand + (size_t)(r % 3) * KB * WM; };
-        auto prefetch = [&](int r, int widx, int nwarps) -> uint32_t {
-            const int k = lane * nwarps + widx, jj = KB * r + k;
-            return (packed_chk && k < KB && jj < n) ? __ldg(P.colpack + ord[jj]) : 0u;
-        };
-        // candidates k = i * nwarps + widx of round r against the stored T; lane i of e_pref holds the packed check list of the i-th
-        auto evaluate = [&](int r, int widx, int nwarps, uint32_t e_pref) {
-            uint32_t *cb = cbuf(r);
+        OSDT_MARK(1);
+        while (j < n && npiv < rank) {
+            // evaluate: candidate k = i * NW + warp, a word per lane (the check lists were fetched a round ahead)
+            {
+                const uint32_t e_nx = fetch(j + KB);
+                uint32_t v[CPW];
 #pragma unroll
-            for (int i = 0; i < CPW; ++i) {
-                const int k = i * nwarps + widx, jj = KB * r + k;
-                if (k < KB) {                                         // (uniform)
-                    const uint32_t e = __shfl_sync(FULL, e_pref, i);
+                for (int i = 0; i < CPW; ++i) {
+                    const int jj = j + i * NW + warp;
+                    const uint32_t e = __shfl_sync(FULL, e_cur, i);
                     uint32_t x = 0;
                     if (lane < WM && jj < n) x = (packed_chk ? reduced_packed(e, lane) : reduced_word(jj, lane)) & ~used[lane];
-                    if (lane < WM) cb[(size_t)k * WM + lane] = x;
-                    const unsigned bal = __ballot_sync(FULL, x != 0);
+                    v[i] = x;
+                }
+#pragma unroll
+                for (int i = 0; i < CPW; ++i) {
+                    if (lane < WM) cand[(size_t)(i * NW + warp) * WM + lane] = v[i];
+                    const unsigned bal = __ballot_sync(FULL, v[i] != 0);
                     int p0 = -1;
                     if (bal) {
                         const int src = __ffs(bal) - 1;
-                        p0 = 32 * src + __ffs(__shfl_sync(FULL, x, src)) - 1;
+                        p0 = 32 * src + __ffs(__shfl_sync(FULL, v[i], src)) - 1;
                     }
-                    if (lane == 0) s_p0[r & 1][k] = (int16_t)p0;
+                    if (lane == 0) s_p0[i * NW + warp] = p0;
                 }
+                e_cur = e_nx;
             }
-        };
-        // coefficients of E (parity par) for a column whose pivot-row bits were gathered into t (bit nacc-1-a: pivot a)
-        auto chain = [&](unsigned t, int par, int nfold) -> unsigned {
-            for (int f = 0; f < nfold; ++f)
-                if (__popc(t & s_fm[par][f]) & 1) t ^= 1u << s_fq[par][f];
-            return t;
-        };
-
-        // warp 0: resolve round r.  cb = its candidates (free rows, up to date), p0 = lowest free row of candidate `lane`.
-        auto resolve = [&](int r, int p0) {
-            uint32_t *cb = cbuf(r);
-            const int par = r & 1;
-            // bits that exactly one candidate of the round has (lane = word): a pivot row chosen among them is in no other
-            // candidate, so the candidate neither has to be brought to anyone else nor changes when others pivot
-            uint32_t uq = 0;
-            {
-                uint32_t s1 = 0, s2 = 0;
-                if (lane < WM) {
-#pragma unroll
-                    for (int k = 0; k < KB; ++k) {
-                        const uint32_t x = cb[(size_t)k * WM + lane];
-                        s2 |= s1 & x;
-                        s1 |= x;
-                    }
-                }
-                uq = s1 & ~s2;
-            }
-            // lane = candidate: first exclusive bit, else first bit
-            int p = p0;
-            bool excl = false;
-            {
-                int fu = -1;
-                uint32_t wu = 0;
-#pragma unroll
-                for (int w = WM - 1; w >= 0; --w) {
-                    const uint32_t u = cb[(size_t)lane * WM + w] & __shfl_sync(FULL, uq, w);
-                    if (u) { fu = w; wu = u; }
-                }
-                if (fu >= 0) { p = 32 * fu + __ffs(wu) - 1; excl = true; }
-            }
-            unsigned acc = __ballot_sync(FULL, p >= 0);
-            const unsigned shared_piv = __ballot_sync(FULL, p >= 0 && !excl);
-            const unsigned below = (1u << lane) - 1u;
-            // interaction matrix: bit k of im = this candidate has the pivot row of candidate k (shared pivot rows only: an
-            // exclusive one is in nobody else), bit `lane` = it has its own.  Reducing candidate k' by candidate k is
-            // im[k'] ^= im[k] on this matrix -- the vectors themselves are only touched to carry the XOR out.
-            unsigned im = 0;
-            for (unsigned t = shared_piv; t;) {
-                int kk[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) { kk[u] = t ? __ffs(t) - 1 : -1; t &= t - 1; }
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int pk = __shfl_sync(FULL, p, kk[u] < 0 ? 0 : kk[u]);
-                    if (kk[u] >= 0) im |= ((cb[(size_t)lane * WM + (pk >> 5)] >> (pk & 31)) & 1u) << kk[u];
-                }
-            }
-            if (p >= 0) im |= 1u << lane;
-            // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
-            unsigned todo = __ballot_sync(FULL, (im & below & acc) != 0);
-            while (todo) {
-                const int kp = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const unsigned lowk = (1u << kp) - 1u;
-                unsigned row = __shfl_sync(FULL, im, kp);
-                unsigned imk = row & acc & lowk;
-                if (!imk) continue;
-                uint32_t v = (lane < WM) ? cb[(size_t)kp * WM + lane] : 0u;
-                do {
-                    const int k = __ffs(imk) - 1;                 // rows of accepted candidates have nothing below their own bit
-                    if (lane < WM) v ^= cb[(size_t)k * WM + lane];
-                    row ^= __shfl_sync(FULL, im, k);
-                    imk = row & acc & lowk;
-                } while (imk);
-                if (lane < WM) cb[(size_t)kp * WM + lane] = v;
-                if ((row >> kp) & 1u) {                            // it still has its pivot row
-                    if (lane == kp) im = row;
-                    __syncwarp();
-                    continue;
-                }
-                const unsigned bal = __ballot_sync(FULL, v != 0);
-                if (!bal) {                                        // dependent on the candidates before it
-                    acc &= ~(1u << kp);
-                    if (lane == kp) { p = -1; im = 0; }
-                    __syncwarp();
-                    continue;
-                }
-                const int src = __ffs(bal) - 1;
-                const int newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
-                __syncwarp();
-                // a new pivot row: column kp of the matrix changes
-                const uint32_t b = (cb[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
-                if (lane == kp) { p = newp; im = row | (1u << kp); }
-                else im = (im & ~(1u << kp)) | (b << kp);
-                todo |= __ballot_sync(FULL, b != 0 && lane > kp);
-            }
-            // never more pivots than the rank of H
-            while (__popc(acc) > rank - npivR) acc &= ~(0x80000000u >> __clz(acc));
-            const bool mine = (acc >> lane) & 1u;
-            const int nacc = __popc(acc);
-            // S = free rows without the pivot row
-            if (mine) cb[(size_t)lane * WM + (p >> 5)] &= ~(1u << (p & 31));
-            // chain entries: an accepted candidate b whose S has the pivot row of a LATER accepted candidate a makes the
-            // coefficient of a depend on the coefficient of b (x_a ^= x_b); listed by ascending a, in coefficient-bit positions
-            const unsigned jm = mine ? (im & acc & ~((2u << lane) - 1u)) : 0u;
-            int nfold = 0;
-            for (unsigned t = __reduce_or_sync(FULL, jm); t; t &= t - 1) {
-                const int a = __ffs(t) - 1;
-                unsigned mq = 0;
-                for (unsigned u = __ballot_sync(FULL, (jm >> a) & 1u); u; u &= u - 1)
-                    mq |= 1u << (nacc - 1 - __popc(acc & ((1u << (__ffs(u) - 1)) - 1u)));
-                if (lane == 0) {
-                    s_fm[par][nfold] = mq;
-                    s_fq[par][nfold] = (uint8_t)(nacc - 1 - __popc(acc & ((1u << a) - 1u)));
-                }
-                ++nfold;
-            }
-            // publish
-            if (mine) {
-                const int a = __popc(acc & below);
-                s_pl[par][a] = (uint16_t)(p | (lane << 10));
-                prow[npivR + a] = (uint16_t)p;
-                pcolj[npivR + a] = (uint16_t)(KB * r + lane);
-            }
-            npivR += nacc;
-            if (lane == 0) {
-                s_nacc[par] = nacc;
-                s_nfold[par] = nfold;
-                s_last[par] = (npivR >= rank || KB * (r + 1) >= n) ? 1 : 0;
-            }
-        };
-
-        // prologue: round 0 is evaluated by everybody (T = I), then resolved while the workers evaluate round 1
-        evaluate(0, warp, NW, prefetch(0, warp, NW));
-        __syncthreads();
-        if (warp == 0) resolve(0, (int)s_p0[0][lane]);
-        else evaluate(1, warp - 1, NWW, prefetch(1, warp - 1, NWW));
-        __syncthreads();
-        for (int s = 0;; ++s) {
-            const int par = s & 1;
-            const int nacc = s_nacc[par], nfold = s_nfold[par];
-            const bool last = s_last[par] != 0;
-            const uint32_t *cb0 = cbuf(s);
+            __syncthreads();
+            OSDT_MARK(2);
             if (warp == 0) {
-                if (!last) {
-                    // the candidates of round s+1 were evaluated against T(s): apply E_s to them (lane = candidate)
-                    uint32_t *cb1 = cbuf(s + 1);
-                    unsigned x = 0;
-#pragma unroll 4
-                    for (int a = 0; a < nacc; ++a) {
-                        const uint32_t p = s_pl[par][a] & 1023u;
-                        x = __funnelshift_l(cb1[(size_t)lane * WM + (p >> 5)] << (31 - (p & 31)), x, 1);
+                // bits that exactly one candidate of the round has (lane = word): a pivot row chosen among them is in no
+                // other candidate, so the candidate neither has to be brought to anyone else nor changes when others pivot
+                OSDT_R0;
+                uint32_t uq = 0;
+                {
+                    uint32_t s1 = 0, s2 = 0;
+                    if (lane < WM) {
+#pragma unroll
+                        for (int k = 0; k < KB; ++k) {
+                            const uint32_t x = cand[(size_t)k * WM + lane];
+                            s2 |= s1 & x;
+                            s1 |= x;
+                        }
                     }
-                    x = chain(x, par, nfold);
-                    int p0 = (int)s_p0[(s + 1) & 1][lane];
-                    unsigned hit = __ballot_sync(FULL, x != 0);
+                    uq = s1 & ~s2;
+                }
+                OSDT_R(0);
+                // lane = candidate: first exclusive bit, else first bit
+                int p = s_p0[lane];
+                bool excl = false;
+                {
+                    int fu = -1;
+                    uint32_t wu = 0;
+#pragma unroll
+                    for (int w = WM - 1; w >= 0; --w) {
+                        const uint32_t u = cand[(size_t)lane * WM + w] & __shfl_sync(FULL, uq, w);
+                        if (u) { fu = w; wu = u; }
+                    }
+                    if (fu >= 0) { p = 32 * fu + __ffs(wu) - 1; excl = true; }
+                }
+                OSDT_R(1);
+                unsigned acc = __ballot_sync(FULL, p >= 0);
+                const unsigned shared_piv = __ballot_sync(FULL, p >= 0 && !excl);
+                const unsigned below = (1u << lane) - 1u;
+                // interaction matrix: bit k of im = this candidate has the pivot row of candidate k (shared pivot rows only: an
+                // exclusive one is in nobody else), bit `lane` = it has its own.  Reducing candidate k' by candidate k is
+                // im[k'] ^= im[k] on this matrix -- the vectors themselves are only touched to carry the XOR out.
+                unsigned im = 0;
+                for (unsigned t = shared_piv; t;) {
+                    int kk[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { kk[u] = t ? __ffs(t) - 1 : -1; t &= t - 1; }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int pk = __shfl_sync(FULL, p, kk[u] < 0 ? 0 : kk[u]);
+                        if (kk[u] >= 0) im |= ((cand[(size_t)lane * WM + (pk >> 5)] >> (pk & 31)) & 1u) << kk[u];
+                    }
+                }
+                if (p >= 0) im |= 1u << lane;
+                OSDT_R(2);
+OSDT_ADD(osdt_shared, __popc(shared_piv));
+                // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
+                unsigned todo = __ballot_sync(FULL, (im & below & acc) != 0);
+                while (todo) {
+                    const int kp = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const unsigned lowk = (1u << kp) - 1u;
+                    unsigned row = __shfl_sync(FULL, im, kp);
+                    unsigned imk = row & acc & lowk;
+                    if (!imk) continue;
+OSDT_ADD(osdt_fix, 1);
+                    uint32_t v = (lane < WM) ? cand[(size_t)kp * WM + lane] : 0u;
+                    do {
+                        const int k = __ffs(imk) - 1;                 // rows of accepted candidates have nothing below their own bit
+                        if (lane < WM) v ^= cand[(size_t)k * WM + lane];
+                        row ^= __shfl_sync(FULL, im, k);
+                        imk = row & acc & lowk;
+                    } while (imk);
+                    if (lane < WM) cand[(size_t)kp * WM + lane] = v;
+                    if ((row >> kp) & 1u) {                            // it still has its pivot row
+                        if (lane == kp) im = row;
+                        __syncwarp();
+                        continue;
+                    }
+OSDT_ADD(osdt_lost, 1);
+                    const unsigned bal = __ballot_sync(FULL, v != 0);
+                    if (!bal) {                                        // dependent on the candidates before it
+OSDT_ADD(osdt_zero, 1);
+                        acc &= ~(1u << kp);
+                        if (lane == kp) { p = -1; im = 0; }
+                        __syncwarp();
+                        continue;
+                    }
+                    const int src = __ffs(bal) - 1;
+                    const int newp = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
+                    __syncwarp();
+                    // a new pivot row: column kp of the matrix changes
+                    const uint32_t b = (cand[(size_t)lane * WM + (newp >> 5)] >> (newp & 31)) & 1u;
+                    if (lane == kp) { p = newp; im = row | (1u << kp); }
+                    else im = (im & ~(1u << kp)) | (b << kp);
+                    todo |= __ballot_sync(FULL, b != 0 && lane > kp);
+                }
+                OSDT_R(3);
+                // never more pivots than the rank of H
+                while (__popc(acc) > rank - npiv) acc &= ~(0x80000000u >> __clz(acc));
+                const bool mine = (acc >> lane) & 1u;
+                // S = free rows without the pivot row; fold the entries above the diagonal in (descending order)
+                if (mine) cand[(size_t)lane * WM + (p >> 5)] &= ~(1u << (p & 31));
+                __syncwarp();
+                const unsigned jm = mine ? (im & acc & ~((2u << lane) - 1u)) : 0u;
+                unsigned bt = __ballot_sync(FULL, jm != 0);
+                while (bt) {
+                    const int b = 31 - __clz(bt);
+                    bt &= ~(1u << b);
+                    unsigned jb = __shfl_sync(FULL, jm, b);
+OSDT_ADD(osdt_bfix, 1);
+                    uint32_t v = 0;
+                    while (jb) {
+                        const int a = __ffs(jb) - 1;
+                        jb &= jb - 1;
+                        if (lane < WM) v ^= cand[(size_t)a * WM + lane];
+                    }
+                    if (lane < WM) cand[(size_t)b * WM + lane] ^= v;
+                    __syncwarp();
+                }
+                OSDT_R(4);
+                // publish the pivots
+                if (mine) {
+                    const int a = __popc(acc & below);
+                    s_pl[a] = (uint32_t)p;
+                    s_off[a] = lane * WM;
+                    prow[npiv + a] = (uint16_t)p;
+                    pcolj[npiv + a] = (uint16_t)(j + lane);
+                    rowpiv[p] = (uint16_t)(npiv + a);
+                    atomicOr(&used[p >> 5], 1u << (p & 31));
+                }
+                if (lane == 0) s_nacc = __popc(acc);
+                OSDT_R(5);
+            }
+            __syncthreads();
+            OSDT_MARK(3);
+            const int nacc = s_nacc;
+            // apply.  Row c of T is added to other rows only once c is a pivot row: the columns of free rows are unit vectors
+            // and have no pivot row of this round, so only the stored columns (pivots 0 .. npiv-1) and the syndrome take part.
+            // Column ^= sum over the accepted candidates a whose pivot row the column has (as it stands now) of S'_a.
+            auto apply_group = [&](auto ni_c, int g0) {
+                constexpr int NI = decltype(ni_c)::value;
+                unsigned x[NI];
+                int cb[NI];
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int idx = g0 + i * NW * 32 + lane;
+                    cb[i] = (idx < npiv ? idx : m) * WM;
+                    x[i] = 0;
+                }
+#pragma unroll 4
+                for (int a = 0; a < nacc; ++a) {                     // bit nacc-1-a of x: pivot a
+                    const uint32_t p = s_pl[a];
+                    const int wo = (int)(p >> 5), sh = 31 - (int)(p & 31);
+#pragma unroll
+                    for (int i = 0; i < NI; ++i) x[i] = __funnelshift_l(TCP[cb[i] + wo] << sh, x[i], 1);
+                }
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int c0 = g0 + i * NW * 32;
+                    unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= npiv);
+OSDT_ADD(osdt_hits, __popc(hit));
                     while (hit) {
                         const int l = __ffs(hit) - 1;
                         hit &= hit - 1;
-                        unsigned xx = __shfl_sync(FULL, x, l);
-                        uint32_t v = (lane < WM) ? cb1[(size_t)l * WM + lane] : 0u, pivrows = 0;
-                        while (xx) {
-                            const int b = __ffs(xx) - 1;
-                            xx &= xx - 1;
-                            const uint32_t e = s_pl[par][nacc - 1 - b];
-                            const int p = (int)(e & 1023u);
-                            if (lane < WM) v ^= cb0[(size_t)(e >> 10) * WM + lane];
-                            if (lane == (p >> 5)) pivrows |= 1u << (p & 31);     // the candidate ends up with exactly the pivot rows whose
-                        }                                                        // coefficient is set: they are no free rows any more
-                        v &= ~pivrows;
-                        if (lane < WM) cb1[(size_t)l * WM + lane] = v;
-                        const unsigned bal = __ballot_sync(FULL, v != 0);
-                        int np0 = -1;
-                        if (bal) {
-                            const int src = __ffs(bal) - 1;
-                            np0 = 32 * src + __ffs(__shfl_sync(FULL, v, src)) - 1;
-                        }
-                        if (lane == l) p0 = np0;
-                    }
-                    __syncwarp();
-                    resolve(s + 1, p0);
-                }
-            } else {
-                const int widx = warp - 1;
-                const uint32_t e_pref = last ? 0u : prefetch(s + 2, widx, NWW);
-                // the columns of the new pivot rows: E_s applied to the unit vector (its own S, and through the chain those of later pivots)
-                for (int a = widx; a < nacc; a += NWW) {
-                    const int p = (int)(s_pl[par][a] & 1023u);
-                    unsigned xx = chain(1u << (nacc - 1 - a), par, nfold);
-                    if (lane < WM) {
-                        uint32_t v = (lane == (p >> 5)) ? (1u << (p & 31)) : 0u;
-                        while (xx) {
-                            const int b = __ffs(xx) - 1;
-                            xx &= xx - 1;
-                            v ^= cb0[(size_t)(s_pl[par][nacc - 1 - b] >> 10) * WM + lane];
-                        }
-                        TCP[(size_t)(npiv + a) * WM + lane] = v;
-                    }
-                    if (lane == 0) { rowpiv[p] = (uint16_t)(npiv + a); atomicOr(&used[p >> 5], 1u << (p & 31)); }
-                }
-                // Row c of T is added to other rows only once c is a pivot row: the columns of free rows are unit vectors and have
-                // no pivot row of this round, so only the stored columns (pivots 0 .. npiv-1) and the syndrome take part.
-                auto apply_group = [&](auto ni_c, int g0) {
-                    constexpr int NI = decltype(ni_c)::value;
-                    unsigned x[NI];
-                    int cb[NI];
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const int idx = g0 + i * NWW * 32 + lane;
-                        cb[i] = (idx < npiv ? idx : m) * WM;
-                        x[i] = 0;
-                    }
-#pragma unroll 4
-                    for (int a = 0; a < nacc; ++a) {                     // bit nacc-1-a of x: pivot a
-                        const uint32_t p = s_pl[par][a] & 1023u;
-                        const int wo = (int)(p >> 5), sh = 31 - (int)(p & 31);
-#pragma unroll
-                        for (int i = 0; i < NI; ++i) x[i] = __funnelshift_l(TCP[cb[i] + wo] << sh, x[i], 1);
-                    }
-#pragma unroll
-                    for (int i = 0; i < NI; ++i) {
-                        const int c0 = g0 + i * NWW * 32;
-                        if (nfold) x[i] = chain(x[i], par, nfold);
-                        unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= npiv);
-                        while (hit) {
-                            const int l = __ffs(hit) - 1;
-                            hit &= hit - 1;
-                            unsigned xx = __shfl_sync(FULL, x[i], l);
-                            const int slot = (c0 + l < npiv) ? c0 + l : m;
-                            if (lane < WM) {
-                                uint32_t sv = 0;
-                                while (xx) {
-                                    const int b = __ffs(xx) - 1;
-                                    xx &= xx - 1;
-                                    sv ^= cb0[(size_t)(s_pl[par][nacc - 1 - b] >> 10) * WM + lane];
-                                }
-                                TCP[(size_t)slot * WM + lane] ^= sv;
+                        unsigned xx = __shfl_sync(FULL, x[i], l);
+                        const int slot = (c0 + l < npiv) ? c0 + l : m;
+                        if (lane < WM) {
+                            uint32_t sv = 0;
+                            while (xx) {
+                                const int b = __ffs(xx) - 1;
+                                xx &= xx - 1;
+                                sv ^= cand[s_off[nacc - 1 - b] + lane];
                             }
+                            TCP[(size_t)slot * WM + lane] ^= sv;
                         }
                     }
-                };
-                for (int g0 = widx * 32; g0 <= npiv; g0 += 4 * NWW * 32) {
-                    const int ni = (npiv + 1 - g0 + NWW * 32 - 1) / (NWW * 32);
-                    if (ni >= 4) apply_group(OsdIC<4>(), g0);
-                    else if (ni == 3) apply_group(OsdIC<3>(), g0);
-                    else if (ni == 2) apply_group(OsdIC<2>(), g0);
-                    else apply_group(OsdIC<1>(), g0);
                 }
-                if (!last) {
-                    asm volatile("bar.sync 1, %0;" ::"n"(NWW * 32) : "memory");      // T(s+1) is complete (workers only)
-                    evaluate(s + 2, widx, NWW, e_pref);
-                }
+            };
+            for (int g0 = warp * 32; g0 <= npiv; g0 += 4 * NW * 32) {
+                const int ni = (npiv + 1 - g0 + NW * 32 - 1) / (NW * 32);
+                if (ni >= 4) apply_group(OsdIC<4>(), g0);
+                else if (ni == 3) apply_group(OsdIC<3>(), g0);
+                else if (ni == 2) apply_group(OsdIC<2>(), g0);
+                else apply_group(OsdIC<1>(), g0);
+            }
+            // the columns of the new pivot rows: unit vector ^ S'
+            for (int a = warp; a < nacc; a += NW) {
+                const uint32_t p = s_pl[a];
+                if (lane < WM) TCP[(size_t)(npiv + a) * WM + lane] = cand[s_off[a] + lane] | (lane == (int)(p >> 5) ? (1u << (p & 31)) : 0u);
             }
             npiv += nacc;
+            j += KB;
             __syncthreads();
-            if (last) break;
+            OSDT_MARK(4);
+OSDT_ADD(osdt_rounds, 1); OSDT_ADD(osdt_piv, nacc);
         }
 
         // ---- validity; back-substitution over the pivots in reverse order ---------------------------
@@ -1530,9 +1485,21 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
             }
         }
         __syncthreads();
+        OSDT_MARK(5);
         for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
         if (tid == 0 && P.valid) P.valid[shot] = 1;
+OSDT_ADD(osdt_shots, 1);
     }
+#ifdef QLDPC_OSD_TIMING
+    if (blockIdx.x == 0 && tid == 0 && osdt_shots) {
+        printf("[osd resolve] per round: shared-pivot candidates %.2f, forward fix-ups %.2f (pivot lost %.2f, dependent %.2f), backward folds %.2f; cycles: exclusive bits %lld, pivot choice %lld, interaction gather %lld, forward %lld, truncate+fold %lld, publish %lld\n",
+               (double)osdt_shared / osdt_rounds, (double)osdt_fix / osdt_rounds, (double)osdt_lost / osdt_rounds, (double)osdt_zero / osdt_rounds, (double)osdt_bfix / osdt_rounds,
+               osdt_r[0] / osdt_rounds, osdt_r[1] / osdt_rounds, osdt_r[2] / osdt_rounds, osdt_r[3] / osdt_rounds, osdt_r[4] / osdt_rounds, osdt_r[5] / osdt_rounds);
+        printf("[osd timing] CTA 0: %lld shots, %lld rounds, %lld pivots, %lld column updates by warp 0 (of 8), %lld resolve fix-ups; cycles per shot: sort %lld, setup %lld, evaluate %lld, resolve %lld, apply %lld, backsub %lld, other %lld\n",
+               osdt_shots, osdt_rounds, osdt_piv, osdt_hits, osdt_fix, osdt[0] / osdt_shots, osdt[1] / osdt_shots, osdt[2] / osdt_shots, osdt[3] / osdt_shots,
+               osdt[4] / osdt_shots, osdt[5] / osdt_shots, osdt[7] / osdt_shots);
+    }
+#endif
 }
 
 }  // namespace qldpc

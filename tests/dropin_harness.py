@@ -34,8 +34,23 @@ def _purge(names):
             del sys.modules[k]
 
 
-def run_script(rel, swap, edits=(), from_rework=False, workdir=None):
-    """Executes baseline/_ref/<rel> as __main__.  swap=False: the reference's own decoders; swap=True: the CUDA path."""
+def _snapshot(x):
+    import numpy as np
+    if isinstance(x, np.ndarray):
+        return x.copy()
+    if isinstance(x, tuple):
+        return tuple(_snapshot(v) for v in x)
+    if isinstance(x, list):
+        try:
+            return np.array(x)
+        except Exception:
+            return list(x)
+    return x
+
+
+def run_script(rel, swap, edits=(), from_rework=False, workdir=None, record=()):
+    """Executes baseline/_ref/<rel> as __main__.  swap=False: the reference's own decoders; swap=True: the CUDA path.
+    record: (module, function) names whose calls are logged -- ns["__calls__"][function] = [(args, result), ...] (copies)."""
     src = open(os.path.join(REF, rel)).read()
     for pat, rep in edits:
         src, cnt = re.subn(pat, rep, src)
@@ -54,6 +69,7 @@ def run_script(rel, swap, edits=(), from_rework=False, workdir=None):
     draw = types.ModuleType("drawUtils")
     draw.plotGraph = draw.plotMatrix = lambda *a, **k: None
     sys.modules["drawUtils"] = draw
+    wrapped = []
     try:
         os.chdir(workdir)
         for d in ("data", "media", "rework"):
@@ -67,13 +83,30 @@ def run_script(rel, swap, edits=(), from_rework=False, workdir=None):
             sys.path.insert(0, REF)
             if from_rework:
                 sys.path.insert(0, os.path.join(REF, "rework"))     # `decoding` = rework/decoding.py, as when run from rework/
-        ns = {"__name__": "__main__", "__file__": os.path.join(REF, rel)}
+        calls = {}
+        for modname, fname in record:
+            import importlib
+            mod = importlib.import_module(modname)
+            orig = getattr(mod, fname)
+            wrapped.append((mod, fname, orig))
+
+            def make(orig=orig, key=fname):
+                def f(*a, **k):
+                    args = tuple(_snapshot(v) for v in a)
+                    r = orig(*a, **k)
+                    calls.setdefault(key, []).append((args, _snapshot(r)))
+                    return r
+                return f
+            setattr(mod, fname, make())
+        ns = {"__name__": "__main__", "__file__": os.path.join(REF, rel), "__calls__": calls}
         out = io.StringIO()
         with contextlib.redirect_stdout(out), contextlib.redirect_stderr(io.StringIO()):
             exec(compile(src, rel, "exec"), ns)
         ns["__stdout__"] = out.getvalue()
         return ns
     finally:
+        for mod, fname, orig in wrapped:
+            setattr(mod, fname, orig)
         os.chdir(cwd)
         if swap:
             import qldpc_b200.compat as compat

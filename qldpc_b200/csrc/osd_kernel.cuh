@@ -980,7 +980,7 @@ template <typename K>
 __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 {
     const int WM = (m + 31) / 32, WN = (n + 31) / 32;
-    size_t o = 4 * (size_t)(m + 1) * WM;                        // TC, syndrome column
+    size_t o = 4 * (size_t)(m + 2) * WM;                        // TC, syndrome column, zero slot
     o += 2 * (size_t)m * 3;                                     // pivot rows / sorted positions of the pivot columns / pivot index of a row (uint16)
     o = (o + 3) & ~(size_t)3;
     o += 4 * (size_t)WM;                                        // used
@@ -1057,11 +1057,11 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
     const int tid = threadIdx.x, NT = OSDBF_THREADS, lane = tid & 31, warp = tid >> 5;
     const unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) unsigned char smem[];
-    uint32_t *TCP = reinterpret_cast<uint32_t *>(smem);                     // [m + 1][WM]  slot a: column prow[a] of T; slot m: syndrome column
+    uint32_t *TCP = reinterpret_cast<uint32_t *>(smem);                     // [m + 2][WM]  slot a: column prow[a] of T; slot m: syndrome column; slot m+1: zeros
     uint32_t *bw = TCP + (size_t)m * WM;
-    uint16_t *prow = reinterpret_cast<uint16_t *>(TCP + (size_t)(m + 1) * WM);  // [m] pivot row of the k-th pivot
+    uint16_t *prow = reinterpret_cast<uint16_t *>(TCP + (size_t)(m + 2) * WM);  // [m] pivot row of the k-th pivot
     uint16_t *pcolj = prow + m;                                            // [m] sorted position of the k-th pivot column
-    uint16_t *rowpiv = pcolj + m;                                          // [m] index of the pivot that row r belongs to, 0xFFFF: free
+    uint16_t *rowpiv = pcolj + m;                                          // [m] slot of the column of row r: its pivot index, m+1 (the zero slot) while free
     uint32_t *used = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(rowpiv + m) + 3) & ~(uintptr_t)3);   // [WM]
     uint32_t *cand = used + WM;                                             // [KB][WM] free rows of the candidates
     uint32_t *solw = cand + (size_t)KB * WM;                                // [WN]
@@ -1069,45 +1069,42 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
     uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
     __shared__ uint32_t s_pl[KB];                      // pivot rows accepted in this round, in order
     __shared__ int s_off[KB];                          // and where their S' vectors are (offset into cand)
+    __shared__ uint2 s_g[KB];                          // and {word, 31 - bit} of the pivot row, as the coefficient gather wants them
     __shared__ int s_nacc;
-    __shared__ int s_p0[KB];                           // lowest free row of a candidate, -1: none
     constexpr bool packed_chk = PACKED;               // m <= 1024 and column weight <= 3 (checked by the host)
 
-    // column c of T, word w: stored once row c has become a pivot row, the unit vector until then
-    auto tcol = [&](int c, int w) -> uint32_t {
-        const unsigned a = rowpiv[c];
-        return a != 0xFFFFu ? TCP[(size_t)a * WM + w] : ((c >> 5) == w ? (1u << (c & 31)) : 0u);
-    };
-    // reduced column (XOR of the T columns of its checks), word w: from the packed check list / of sorted position jj
-    auto reduced_packed = [&](uint32_t e, int w) -> uint32_t {
-        const int cnt = (int)(e >> 30);
-        uint32_t x = 0;
-        if (cnt > 0) x = tcol((int)(e & 1023u), w);
-        if (cnt > 1) x ^= tcol((int)((e >> 10) & 1023u), w);
-        if (cnt > 2) x ^= tcol((int)((e >> 20) & 1023u), w);
-        return x;
-    };
-    auto reduced_word = [&](int jj, int w) -> uint32_t {
+    // Column c of T = the stored column of its slot if row c is a pivot row, the unit vector e_c otherwise.  Free rows point at the
+    // zero slot, so "stored ^ e_c" is right on the FREE rows for every c (a stored column holds its own unit bit, which e_c cancels --
+    // on a pivot row, masked off by the caller), and "stored" alone is right on the pivot rows (back-substitution).
+    auto tcol_free = [&](int c, int w) -> uint32_t { return TCP[(size_t)rowpiv[c] * WM + w] ^ ((c >> 5) == w ? (1u << (c & 31)) : 0u); };
+    auto tcol_piv = [&](int c, int w) -> uint32_t { return TCP[(size_t)rowpiv[c] * WM + w]; };
+    // reduced column of sorted position jj on the pivot rows (XOR of the T columns of its checks), word w
+    auto reduced_piv = [&](int jj, int w) -> uint32_t {
         const int col = ord[jj];
-        if (packed_chk) return reduced_packed(__ldg(P.colpack + col), w);
         uint32_t x = 0;
-        for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= tcol((int)P.vtab[2 * a + 1], w);
+        if (packed_chk) {
+            const uint32_t e = __ldg(P.colpack + col);
+            const int cnt = (int)(e >> 30);
+            if (cnt > 0) x = tcol_piv((int)(e & 1023u), w);
+            if (cnt > 1) x ^= tcol_piv((int)((e >> 10) & 1023u), w);
+            if (cnt > 2) x ^= tcol_piv((int)((e >> 20) & 1023u), w);
+        } else {
+            for (int a = P.var_ptr[col]; a < P.var_ptr[col + 1]; ++a) x ^= tcol_piv((int)P.vtab[2 * a + 1], w);
+        }
         return x;
     };
-    // packed check lists of the candidates of the round that starts at sorted position jb: lane i < CPW holds candidate i * NW + warp
+    // packed check list of candidate `lane` of the round that starts at sorted position jb
     auto fetch = [&](int jb) -> uint32_t {
-        const int jj = jb + lane * NW + warp;
-        return (packed_chk && lane < CPW && jj < n) ? __ldg(P.colpack + ord[jj]) : 0u;
+        const int jj = jb + lane;
+        return (packed_chk && jj < n) ? __ldg(P.colpack + ord[jj]) : 0u;
     };
 
     const long long count = P.count_dev ? (long long)*P.count_dev : P.count_host;
-    OSDT_DECL;
     for (long long it = blockIdx.x; it < count; it += gridDim.x) {
         const long long shot = P.idx ? (long long)P.idx[it] : it;
         const K *llr = reinterpret_cast<const K *>(P.llr) + (size_t)shot * n;
         const uint32_t *hard = P.hard + (size_t)shot * WN;
         __syncthreads();
-        OSDT_MARK(7);
         // ---- stable ascending order of |llr| ----------------------------------------------------
         for (int w = tid; w < WM; w += NT) { bw[w] = P.synd[(size_t)shot * WM + w]; used[w] = 0; }
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
@@ -1209,7 +1206,6 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
             }
         }
         __syncthreads();                                              // keys are dead from here on
-        OSDT_MARK(0);
         // ---- residual syndrome s ^ H*hard; T = I (no column stored yet) ---------------------------
         for (int v = tid; v < n; v += NT)
             if ((hard[v >> 5] >> (v & 31)) & 1u)
@@ -1217,46 +1213,54 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     const int c = (int)P.vtab[2 * a + 1];
                     atomicXor(&bw[c >> 5], 1u << (c & 31));
                 }
-        for (int r = tid; r < m; r += NT) rowpiv[r] = 0xFFFFu;
+        for (int r = tid; r < m; r += NT) rowpiv[r] = (uint16_t)(m + 1);
+        for (int w = tid; w < WM; w += NT) TCP[(size_t)(m + 1) * WM + w] = 0u;
         uint32_t e_cur = fetch(0);
         __syncthreads();
 
         // ---- forward elimination, KB candidate columns per round ------------------------------------
         int j = 0, npiv = 0;
         const int rank = P.rank;
-        OSDT_MARK(1);
         while (j < n && npiv < rank) {
-            // evaluate: candidate k = i * NW + warp, a word per lane (the check lists were fetched a round ahead)
+            // evaluate: lane = candidate, warp w takes the words w, w + NW, ... of all 32 (the check lists were fetched a round ahead).
+            // 3 loads per word and warp serve 32 candidates (bank conflicts among the lanes' slots included, a fraction of the
+            // instructions of one warp per candidate).
             {
                 const uint32_t e_nx = fetch(j + KB);
-                uint32_t v[CPW];
+                if (packed_chk) {
+                    const uint32_t e = e_cur;
+                    const int cnt = (int)(e >> 30);
+                    int base[3], uw[3];
+                    uint32_t ub[3];
 #pragma unroll
-                for (int i = 0; i < CPW; ++i) {
-                    const int jj = j + i * NW + warp;
-                    const uint32_t e = __shfl_sync(FULL, e_cur, i);
-                    uint32_t x = 0;
-                    if (lane < WM && jj < n) x = (packed_chk ? reduced_packed(e, lane) : reduced_word(jj, lane)) & ~used[lane];
-                    v[i] = x;
-                }
-#pragma unroll
-                for (int i = 0; i < CPW; ++i) {
-                    if (lane < WM) cand[(size_t)(i * NW + warp) * WM + lane] = v[i];
-                    const unsigned bal = __ballot_sync(FULL, v[i] != 0);
-                    int p0 = -1;
-                    if (bal) {
-                        const int src = __ffs(bal) - 1;
-                        p0 = 32 * src + __ffs(__shfl_sync(FULL, v[i], src)) - 1;
+                    for (int i = 0; i < 3; ++i) {
+                        const int c = (int)((e >> (10 * i)) & 1023u);
+                        const bool on = cnt > i;
+                        base[i] = (on ? (int)rowpiv[c] : m + 1) * WM;
+                        uw[i] = on ? (c >> 5) : -1;
+                        ub[i] = 1u << (c & 31);
                     }
-                    if (lane == 0) s_p0[i * NW + warp] = p0;
+                    for (int w = warp; w < WM; w += NW) {
+                        uint32_t x = TCP[base[0] + w] ^ TCP[base[1] + w] ^ TCP[base[2] + w];
+                        x ^= (uw[0] == w ? ub[0] : 0u) ^ (uw[1] == w ? ub[1] : 0u) ^ (uw[2] == w ? ub[2] : 0u);
+                        cand[(size_t)lane * WM + w] = x & ~used[w];
+                    }
+                } else {
+                    const int jj = j + lane;
+                    const int col = jj < n ? (int)ord[jj] : 0;
+                    const int a0 = jj < n ? P.var_ptr[col] : 0, a1 = jj < n ? P.var_ptr[col + 1] : 0;
+                    for (int w = warp; w < WM; w += NW) {
+                        uint32_t x = 0;
+                        for (int a = a0; a < a1; ++a) x ^= tcol_free((int)P.vtab[2 * a + 1], w);
+                        cand[(size_t)lane * WM + w] = x & ~used[w];
+                    }
                 }
                 e_cur = e_nx;
             }
             __syncthreads();
-            OSDT_MARK(2);
             if (warp == 0) {
                 // bits that exactly one candidate of the round has (lane = word): a pivot row chosen among them is in no
                 // other candidate, so the candidate neither has to be brought to anyone else nor changes when others pivot
-                OSDT_R0;
                 uint32_t uq = 0;
                 {
                     uint32_t s1 = 0, s2 = 0;
@@ -1270,21 +1274,22 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     }
                     uq = s1 & ~s2;
                 }
-                OSDT_R(0);
                 // lane = candidate: first exclusive bit, else first bit
-                int p = s_p0[lane];
+                int p = -1;
                 bool excl = false;
                 {
-                    int fu = -1;
-                    uint32_t wu = 0;
+                    int fu = -1, fx = -1;
+                    uint32_t wu = 0, wx = 0;
 #pragma unroll
                     for (int w = WM - 1; w >= 0; --w) {
-                        const uint32_t u = cand[(size_t)lane * WM + w] & __shfl_sync(FULL, uq, w);
+                        const uint32_t x = cand[(size_t)lane * WM + w];
+                        const uint32_t u = x & __shfl_sync(FULL, uq, w);
+                        if (x) { fx = w; wx = x; }
                         if (u) { fu = w; wu = u; }
                     }
                     if (fu >= 0) { p = 32 * fu + __ffs(wu) - 1; excl = true; }
+                    else if (fx >= 0) p = 32 * fx + __ffs(wx) - 1;
                 }
-                OSDT_R(1);
                 unsigned acc = __ballot_sync(FULL, p >= 0);
                 const unsigned shared_piv = __ballot_sync(FULL, p >= 0 && !excl);
                 const unsigned below = (1u << lane) - 1u;
@@ -1303,8 +1308,6 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     }
                 }
                 if (p >= 0) im |= 1u << lane;
-                OSDT_R(2);
-OSDT_ADD(osdt_shared, __popc(shared_piv));
                 // forward: a candidate that has the pivot row of an accepted candidate before it is reduced by it first
                 unsigned todo = __ballot_sync(FULL, (im & below & acc) != 0);
                 while (todo) {
@@ -1314,7 +1317,6 @@ OSDT_ADD(osdt_shared, __popc(shared_piv));
                     unsigned row = __shfl_sync(FULL, im, kp);
                     unsigned imk = row & acc & lowk;
                     if (!imk) continue;
-OSDT_ADD(osdt_fix, 1);
                     uint32_t v = (lane < WM) ? cand[(size_t)kp * WM + lane] : 0u;
                     do {
                         const int k = __ffs(imk) - 1;                 // rows of accepted candidates have nothing below their own bit
@@ -1328,10 +1330,8 @@ OSDT_ADD(osdt_fix, 1);
                         __syncwarp();
                         continue;
                     }
-OSDT_ADD(osdt_lost, 1);
                     const unsigned bal = __ballot_sync(FULL, v != 0);
                     if (!bal) {                                        // dependent on the candidates before it
-OSDT_ADD(osdt_zero, 1);
                         acc &= ~(1u << kp);
                         if (lane == kp) { p = -1; im = 0; }
                         __syncwarp();
@@ -1346,7 +1346,6 @@ OSDT_ADD(osdt_zero, 1);
                     else im = (im & ~(1u << kp)) | (b << kp);
                     todo |= __ballot_sync(FULL, b != 0 && lane > kp);
                 }
-                OSDT_R(3);
                 // never more pivots than the rank of H
                 while (__popc(acc) > rank - npiv) acc &= ~(0x80000000u >> __clz(acc));
                 const bool mine = (acc >> lane) & 1u;
@@ -1359,7 +1358,6 @@ OSDT_ADD(osdt_zero, 1);
                     const int b = 31 - __clz(bt);
                     bt &= ~(1u << b);
                     unsigned jb = __shfl_sync(FULL, jm, b);
-OSDT_ADD(osdt_bfix, 1);
                     uint32_t v = 0;
                     while (jb) {
                         const int a = __ffs(jb) - 1;
@@ -1369,11 +1367,11 @@ OSDT_ADD(osdt_bfix, 1);
                     if (lane < WM) cand[(size_t)b * WM + lane] ^= v;
                     __syncwarp();
                 }
-                OSDT_R(4);
                 // publish the pivots
                 if (mine) {
                     const int a = __popc(acc & below);
                     s_pl[a] = (uint32_t)p;
+                    s_g[a] = make_uint2((unsigned)(p >> 5), (unsigned)(31 - (p & 31)));
                     s_off[a] = lane * WM;
                     prow[npiv + a] = (uint16_t)p;
                     pcolj[npiv + a] = (uint16_t)(j + lane);
@@ -1381,10 +1379,8 @@ OSDT_ADD(osdt_bfix, 1);
                     atomicOr(&used[p >> 5], 1u << (p & 31));
                 }
                 if (lane == 0) s_nacc = __popc(acc);
-                OSDT_R(5);
             }
             __syncthreads();
-            OSDT_MARK(3);
             const int nacc = s_nacc;
             // apply.  Row c of T is added to other rows only once c is a pivot row: the columns of free rows are unit vectors
             // and have no pivot row of this round, so only the stored columns (pivots 0 .. npiv-1) and the syndrome take part.
@@ -1401,16 +1397,14 @@ OSDT_ADD(osdt_bfix, 1);
                 }
 #pragma unroll 4
                 for (int a = 0; a < nacc; ++a) {                     // bit nacc-1-a of x: pivot a
-                    const uint32_t p = s_pl[a];
-                    const int wo = (int)(p >> 5), sh = 31 - (int)(p & 31);
+                    const uint2 g = s_g[a];
 #pragma unroll
-                    for (int i = 0; i < NI; ++i) x[i] = __funnelshift_l(TCP[cb[i] + wo] << sh, x[i], 1);
+                    for (int i = 0; i < NI; ++i) x[i] = __funnelshift_l(TCP[cb[i] + g.x] << g.y, x[i], 1);
                 }
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
                     const int c0 = g0 + i * NW * 32;
                     unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= npiv);
-OSDT_ADD(osdt_hits, __popc(hit));
                     while (hit) {
                         const int l = __ffs(hit) - 1;
                         hit &= hit - 1;
@@ -1435,16 +1429,16 @@ OSDT_ADD(osdt_hits, __popc(hit));
                 else if (ni == 2) apply_group(OsdIC<2>(), g0);
                 else apply_group(OsdIC<1>(), g0);
             }
-            // the columns of the new pivot rows: unit vector ^ S'
-            for (int a = warp; a < nacc; a += NW) {
-                const uint32_t p = s_pl[a];
-                if (lane < WM) TCP[(size_t)(npiv + a) * WM + lane] = cand[s_off[a] + lane] | (lane == (int)(p >> 5) ? (1u << (p & 31)) : 0u);
+            // the columns of the new pivot rows: unit vector ^ S' (lane = pivot of the round, warp w writes the words w, w + NW, ...)
+            if (lane < nacc) {
+                const uint32_t p = s_pl[lane];
+                const int off = s_off[lane];
+                for (int w = warp; w < WM; w += NW)
+                    TCP[(size_t)(npiv + lane) * WM + w] = cand[off + w] | (w == (int)(p >> 5) ? (1u << (p & 31)) : 0u);
             }
             npiv += nacc;
             j += KB;
             __syncthreads();
-            OSDT_MARK(4);
-OSDT_ADD(osdt_rounds, 1); OSDT_ADD(osdt_piv, nacc);
         }
 
         // ---- validity; back-substitution over the pivots in reverse order ---------------------------
@@ -1476,7 +1470,7 @@ OSDT_ADD(osdt_rounds, 1); OSDT_ADD(osdt_piv, nacc);
                 if (best < 0) break;
                 const int r = prow[best], jk = pcolj[best];
                 if (lane < WM) {
-                    uint32_t x = reduced_word(jk, lane) & used[lane];
+                    uint32_t x = reduced_piv(jk, lane) & used[lane];
                     if (lane == (r >> 5)) x &= ~(1u << (r & 31));    // keep x_k itself
                     bword ^= x;
                 }
@@ -1485,21 +1479,9 @@ OSDT_ADD(osdt_rounds, 1); OSDT_ADD(osdt_piv, nacc);
             }
         }
         __syncthreads();
-        OSDT_MARK(5);
         for (int w = tid; w < WN; w += NT) P.out[(size_t)shot * WN + w] = solw[w];
         if (tid == 0 && P.valid) P.valid[shot] = 1;
-OSDT_ADD(osdt_shots, 1);
     }
-#ifdef QLDPC_OSD_TIMING
-    if (blockIdx.x == 0 && tid == 0 && osdt_shots) {
-        printf("[osd resolve] per round: shared-pivot candidates %.2f, forward fix-ups %.2f (pivot lost %.2f, dependent %.2f), backward folds %.2f; cycles: exclusive bits %lld, pivot choice %lld, interaction gather %lld, forward %lld, truncate+fold %lld, publish %lld\n",
-               (double)osdt_shared / osdt_rounds, (double)osdt_fix / osdt_rounds, (double)osdt_lost / osdt_rounds, (double)osdt_zero / osdt_rounds, (double)osdt_bfix / osdt_rounds,
-               osdt_r[0] / osdt_rounds, osdt_r[1] / osdt_rounds, osdt_r[2] / osdt_rounds, osdt_r[3] / osdt_rounds, osdt_r[4] / osdt_rounds, osdt_r[5] / osdt_rounds);
-        printf("[osd timing] CTA 0: %lld shots, %lld rounds, %lld pivots, %lld column updates by warp 0 (of 8), %lld resolve fix-ups; cycles per shot: sort %lld, setup %lld, evaluate %lld, resolve %lld, apply %lld, backsub %lld, other %lld\n",
-               osdt_shots, osdt_rounds, osdt_piv, osdt_hits, osdt_fix, osdt[0] / osdt_shots, osdt[1] / osdt_shots, osdt[2] / osdt_shots, osdt[3] / osdt_shots,
-               osdt[4] / osdt_shots, osdt[5] / osdt_shots, osdt[7] / osdt_shots);
-    }
-#endif
 }
 
 }  // namespace qldpc

@@ -1069,6 +1069,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
     uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
     __shared__ uint32_t s_pl[KB];                      // pivot rows accepted in this round, in order
     __shared__ int s_off[KB];                          // and where their S' vectors are (offset into cand)
+    __shared__ int s_pex[KB], s_pany[KB];              // per candidate: lowest free row that no other candidate of the round has / lowest free row (INT_MAX: none)
     __shared__ uint2 s_g[KB];                          // and {word, 31 - bit} of the pivot row, as the coefficient gather wants them
     __shared__ int s_nacc;
     constexpr bool packed_chk = PACKED;               // m <= 1024 and column weight <= 3 (checked by the host)
@@ -1214,6 +1215,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     atomicXor(&bw[c >> 5], 1u << (c & 31));
                 }
         for (int r = tid; r < m; r += NT) rowpiv[r] = (uint16_t)(m + 1);
+        if (tid < KB) { s_pex[tid] = 0x7fffffff; s_pany[tid] = 0x7fffffff; }
         for (int w = tid; w < WM; w += NT) TCP[(size_t)(m + 1) * WM + w] = 0u;
         uint32_t e_cur = fetch(0);
         __syncthreads();
@@ -1227,6 +1229,25 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
             // instructions of one warp per candidate).
             {
                 const uint32_t e_nx = fetch(j + KB);
+                // word w of candidate `lane` is x: store it, and note the candidate's lowest bit that no other candidate of the round has
+                // (bits that occur twice = OR over the lanes of x & (OR of the lanes before): one prefix-OR scan and two warp reductions)
+                auto finish_word = [&](int w, uint32_t x) {
+                    cand[(size_t)lane * WM + w] = x;
+                    uint32_t pre = x;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(FULL, pre, d);
+                        if (lane >= d) pre |= o;
+                    }
+                    uint32_t before = __shfl_up_sync(FULL, pre, 1);
+                    if (lane == 0) before = 0;
+                    const uint32_t twice = __reduce_or_sync(FULL, x & before);
+                    if (x) {
+                        atomicMin(&s_pany[lane], 32 * w + __ffs(x) - 1);
+                        const uint32_t u = x & ~twice;
+                        if (u) atomicMin(&s_pex[lane], 32 * w + __ffs(u) - 1);
+                    }
+                };
                 if (packed_chk) {
                     const uint32_t e = e_cur;
                     const int cnt = (int)(e >> 30);
@@ -1243,7 +1264,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     for (int w = warp; w < WM; w += NW) {
                         uint32_t x = TCP[base[0] + w] ^ TCP[base[1] + w] ^ TCP[base[2] + w];
                         x ^= (uw[0] == w ? ub[0] : 0u) ^ (uw[1] == w ? ub[1] : 0u) ^ (uw[2] == w ? ub[2] : 0u);
-                        cand[(size_t)lane * WM + w] = x & ~used[w];
+                        finish_word(w, x & ~used[w]);
                     }
                 } else {
                     const int jj = j + lane;
@@ -1252,44 +1273,21 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     for (int w = warp; w < WM; w += NW) {
                         uint32_t x = 0;
                         for (int a = a0; a < a1; ++a) x ^= tcol_free((int)P.vtab[2 * a + 1], w);
-                        cand[(size_t)lane * WM + w] = x & ~used[w];
+                        finish_word(w, x & ~used[w]);
                     }
                 }
                 e_cur = e_nx;
             }
             __syncthreads();
             if (warp == 0) {
-                // bits that exactly one candidate of the round has (lane = word): a pivot row chosen among them is in no
-                // other candidate, so the candidate neither has to be brought to anyone else nor changes when others pivot
-                uint32_t uq = 0;
-                {
-                    uint32_t s1 = 0, s2 = 0;
-                    if (lane < WM) {
-#pragma unroll
-                        for (int k = 0; k < KB; ++k) {
-                            const uint32_t x = cand[(size_t)k * WM + lane];
-                            s2 |= s1 & x;
-                            s1 |= x;
-                        }
-                    }
-                    uq = s1 & ~s2;
-                }
-                // lane = candidate: first exclusive bit, else first bit
-                int p = -1;
-                bool excl = false;
-                {
-                    int fu = -1, fx = -1;
-                    uint32_t wu = 0, wx = 0;
-#pragma unroll
-                    for (int w = WM - 1; w >= 0; --w) {
-                        const uint32_t x = cand[(size_t)lane * WM + w];
-                        const uint32_t u = x & __shfl_sync(FULL, uq, w);
-                        if (x) { fx = w; wx = x; }
-                        if (u) { fu = w; wu = u; }
-                    }
-                    if (fu >= 0) { p = 32 * fu + __ffs(wu) - 1; excl = true; }
-                    else if (fx >= 0) p = 32 * fx + __ffs(wx) - 1;
-                }
+                // lane = candidate.  Pivot row: its lowest free row that no other candidate of the round has (found during the
+                // evaluation) -- such a candidate neither has to be brought to anyone else nor changes when others pivot -- else its
+                // lowest free row
+                const int pex = s_pex[lane], pany = s_pany[lane];
+                s_pex[lane] = 0x7fffffff;
+                s_pany[lane] = 0x7fffffff;
+                const bool excl = pex != 0x7fffffff;
+                int p = excl ? pex : (pany != 0x7fffffff ? pany : -1);
                 unsigned acc = __ballot_sync(FULL, p >= 0);
                 const unsigned shared_piv = __ballot_sync(FULL, p >= 0 && !excl);
                 const unsigned below = (1u << lane) - 1u;

@@ -932,26 +932,32 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 // OSD-0 for large check matrices, column-major transform, forward elimination in batches: the production block kernel.
 //
 // Same observation as osd0_fast_kernel: the OSD-0 solution does not depend on which row pivots a column, and a column
-// with no free row never gets one back.  The transform is stored by COLUMNS (TC[c] = column c of T, an m-bit vector of
-// WM words; column m is the syndrome column): the reduced column j = T h_j is the XOR of the <= 3 TC columns of the
-// checks of variable ordering[j]; a row operation "rows S ^= row p" becomes "every TC column with bit p set ^= S".
-// Only FREE rows are eliminated (S = free rows of the pivot column): pivot rows are frozen once chosen, T fills in like
-// L^-1 instead of B^-1, and the solution follows from a back-substitution over the pivots in reverse order.
+// with no free row never gets one back.  The transform is stored by COLUMNS, an m-bit vector of WM words each: the reduced
+// column j = T h_j is the XOR of the <= 3 columns of T that belong to the checks of variable ordering[j]; a row operation
+// "rows S ^= row p" becomes "every column of T with bit p set ^= S".  Only FREE rows are eliminated (S = free rows of the
+// pivot column): pivot rows are frozen once chosen, T fills in like L^-1 instead of B^-1, and the solution follows from a
+// back-substitution over the pivots in reverse order.  Row c of T is added to other rows only once c is a pivot row, so the
+// column of a free row is the unit vector and is never stored: slot a holds the column of the a-th pivot row (rowpiv[c] =
+// its slot, or the zero slot m+1 while c is free), slot m the syndrome column.
 //
-// A round takes OSDB_BATCH = 32 consecutive candidate columns:
-//   evaluate  every warp reduces 4 candidates against the current T (a word per lane) and finds their lowest free row;
-//   resolve   warp 0, lane k = candidate k.  The 32 x 32 interaction matrix I[k'][k] = "candidate k' has the pivot row of
-//             candidate k" is gathered once; it is almost empty (the reduced columns are sparse), so nearly every nonzero
-//             candidate is accepted as it stands.  A candidate with an entry below the diagonal is first reduced by the
-//             accepted candidates before it (and may turn out dependent); entries above the diagonal are folded into the
-//             vectors afterwards, in descending order, S'_b = S_b ^ sum_{a > b, S_b[p_a]} S'_a, which turns the SEQUENCE
-//             of row operations of the batch into ONE linear map  c -> c ^ sum_a c[p_a] S'_a  whose coefficients are
-//             bits of the column as it stood BEFORE the round;
-//   apply     each warp owns columns of T: a lane gathers the <= 32 coefficient bits of its column (independent loads,
-//             no chain through the pivots), then the warp XORs the selected S' vectors into the columns that have any
-//             (~10 of 864 per pivot), a word per lane.  No barrier inside, warps never touch each other's columns.
-// Three barriers per 32 candidates (the round-1/2 kernel spent three per 8 and walked every column through the pivots
-// of the batch one after the other: 1.2 M of its 2.0 M cycles per shot).
+// One CTA of 512 threads per shot; a round takes OSDB_BATCH = 32 consecutive candidate columns:
+//   evaluate  lane = candidate; warp w computes the words w, w + 16 of all 32 reduced columns (three loads per word serve 32
+//             candidates) and, per word, the bits that exactly one candidate has (prefix-OR scan over the lanes + two warp
+//             reductions); every candidate's lowest exclusive bit / lowest bit is left in shared memory (atomicMin);
+//   resolve   warp 0, lane k = candidate k.  A candidate with an exclusive bit pivots on it: nobody else has that row, so it is
+//             neither reduced by anybody nor changed when the others pivot.  For the rest the 32 x 32 interaction matrix
+//             I[k'][k] = "candidate k' has the pivot row of candidate k" is gathered once; reducing k' by k is
+//             row[k'] ^= row[k] on it, the vectors are touched only to carry the XOR out, and a candidate whose own bit
+//             disappears is dependent or takes a new pivot row.  Entries above the diagonal are folded into the vectors
+//             afterwards, in descending order, S'_b = S_b ^ sum_{a > b, S_b[p_a]} S'_a, which turns the SEQUENCE of row
+//             operations of the round into ONE linear map  c -> c ^ sum_a c[p_a] S'_a  whose coefficients are bits of the
+//             column as it stood BEFORE the round;
+//   apply     each warp owns stored columns (consecutive slots: conflict-free): a lane gathers the <= 32 coefficient bits of
+//             its column (independent loads, no chain through the pivots), then the warp XORs the selected S' vectors into
+//             the columns that have any (~65 per round), a word per lane; the columns of the new pivot rows (unit vector ^
+//             S') are appended with lane = pivot.  No barrier inside, warps never touch each other's columns.
+// Three barriers per 32 candidates (the round-1 kernel spent three per 8 and walked every column through the pivots of the
+// batch one after the other: 1.2 M of its 2.0 M cycles per shot).  2.4e5 -> 1.04e6 failed shots/s on 864 x 2592.
 // Inconsistent syndromes are handed to osd0_block_kernel (redo list).  The checks of a column come from a per-code table
 // packed 3 x 10 bits (m <= 1024, column weight <= 3: the space-time matrices; otherwise from the CSC in global memory).
 // ------------------------------------------------------------------------------------------------
@@ -992,24 +998,6 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     return o + 64;
 }
 
-// -DQLDPC_OSD_TIMING: per-phase clock64() totals of CTA 0, printed at the end of the launch (diagnostic builds only)
-#ifdef QLDPC_OSD_TIMING
-// accumulators in shared memory, touched by thread 0 only (registers are scarce at 512 threads x 2 CTAs)
-#define OSDT_DECL __shared__ long long osdt_sh[32]; long long *osdt = osdt_sh, *osdt_r = osdt_sh + 8; \
-    long long &osdt_t = osdt_sh[14], &osdt_rt = osdt_sh[15], &osdt_rounds = osdt_sh[16], &osdt_piv = osdt_sh[17], &osdt_shots = osdt_sh[18], &osdt_hits = osdt_sh[19], \
-              &osdt_fix = osdt_sh[20], &osdt_bfix = osdt_sh[21], &osdt_zero = osdt_sh[22], &osdt_lost = osdt_sh[23], &osdt_shared = osdt_sh[24]; \
-    if (threadIdx.x == 0) { for (int i = 0; i < 32; ++i) osdt_sh[i] = 0; osdt_t = clock64(); } __syncthreads()
-#define OSDT_MARK(i) do { if (threadIdx.x == 0) { const long long osdt_n = clock64(); osdt[i] += osdt_n - osdt_t; osdt_t = osdt_n; } } while (0)
-#define OSDT_R0 do { if (threadIdx.x == 0) osdt_rt = clock64(); } while (0)
-#define OSDT_R(i) do { if (threadIdx.x == 0) { const long long osdt_n = clock64(); osdt_r[i] += osdt_n - osdt_rt; osdt_rt = osdt_n; } } while (0)
-#define OSDT_ADD(var, val) do { if (threadIdx.x == 0) var += (val); } while (0)
-#else
-#define OSDT_DECL
-#define OSDT_MARK(i)
-#define OSDT_R0
-#define OSDT_R(i)
-#define OSDT_ADD(var, val)
-#endif
 
 // (key, index) pairs of the block kernel's register-resident bitonic sort.  float keys: one 64-bit word, key << 16 | index (a single
 // unsigned compare orders by key, then by index: the stable order); double keys: the 64-bit key and the index side by side.

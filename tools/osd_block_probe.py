@@ -1,5 +1,5 @@
-"""BP (CTA-per-shot, float32) + block OSD-0 on the 864 x 2592 space-time matrix at p = 0.001 / 0.003: OSD stage time and rate.
-With a library built with QLDPC_NVCC_EXTRA=-DQLDPC_OSD_TIMING the kernel prints its per-phase cycle counts."""
+"""BP (CTA-per-shot, float32) + block OSD-0 on the 864 x 2592 space-time matrix at p = 0.001 / 0.003: OSD stage time and rate
+(the ncu target of profiles/r2zd_osd_block_ncu_summary.txt: -k regex:osd0_block_fast -c 1 captures the p = 0.001 launch)."""
 import json, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))

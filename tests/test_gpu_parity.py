@@ -574,6 +574,57 @@ def test_spacetime_144x12_bp_osd_vs_oracle():
     assert np.array_equal(_synd(Hst, corr32), synd)
 
 
+@pytest.mark.parametrize("rounds,kind", [(12, "ties"), (12, "random"), (5, "ties"), (3, "random")])
+def test_block_osd_rounds_of_32_candidates_vs_oracle(rounds, kind):
+    """The block-per-shot OSD-0 kernel (rounds of 32 candidates: exclusive pivot rows, interaction matrix, folded row operations) on
+    space-time matrices with LLRs that are NOT a BP output: a random order fills T in far more than a BP posterior does (many
+    candidates without an exclusive bit, long reduction chains), and LLRs quantised to 8 levels put hundreds of columns in a tie
+    (stable order: lower index first).  float32 and float64 keys; 12 rounds = 864 x 2592 (27-word kernel, register sort), 5 rounds =
+    360 x 1080 (generic word count, register sort does not apply), 3 rounds = 216 x 648."""
+    from qldpc_b200 import Code, graph
+    from qldpc_b200.spaceTime import spaceTimeMatrix
+    H, _ = load_code_file("[[144, 12, 12]]")
+    Hst = spaceTimeMatrix(H, rounds).astype(np.int64)
+    m, n = Hst.shape
+    rng = np.random.default_rng(100 + rounds)
+    B = 20
+    err = (rng.random((B, n)) < 0.02).astype(np.uint8)
+    synd = _synd(Hst, err)
+    llr = rng.normal(2.0, 3.0, size=(B, n))
+    if kind == "ties":
+        llr = np.round(llr)                                                # ~8 distinct magnitudes, sign kept
+        llr[llr == 0] = 1.0
+    llr32 = llr.astype(np.float32).astype(np.float64)
+    hard = (llr < 0).astype(np.uint8)
+    g = O.Graph(Hst, *O.auto_schedule(Hst, O.MIN_SUM))
+    code = Code(Hst, None, (graph.SEQ, graph.SEQ))
+    for L in (llr, llr32):
+        ref = np.stack([O.osd0(g, synd[b], L[b], hard[b]) for b in range(B)])
+        got = code.osd_decode_batch(synd, L, hard)
+        assert np.array_equal(got, ref)
+        assert np.array_equal(_synd(Hst, got.astype(np.uint8)), synd)      # full row rank: every solution satisfies its syndrome
+    # the float32-key instantiation (what the fused float32 BP -> OSD path launches), through the device-pointer ABI
+    import torch
+    from qldpc_b200 import _lib
+    lib, dev, st = _lib.lib(), torch.device("cuda", 0), torch.cuda.current_stream().cuda_stream
+
+    def pack(bits, words):
+        u8 = torch.from_numpy(np.ascontiguousarray(bits, dtype=np.uint8)).to(dev)
+        w = torch.zeros((B, words), dtype=torch.int32, device=dev)
+        _lib.check(lib.qldpc_pack_bits_dev(u8.data_ptr(), w.data_ptr(), B, bits.shape[1], st))
+        return w
+    sw, hw = pack(synd, code.words_m), pack(hard, code.words_n)
+    l32 = torch.from_numpy(llr32.astype(np.float32)).to(dev)
+    out = torch.zeros((B, code.words_n), dtype=torch.int32, device=dev)
+    valid = torch.zeros(B, dtype=torch.uint8, device=dev)
+    _lib.check(lib.qldpc_osd_decode_dev(code.handle, None, None, B, sw.data_ptr(), l32.data_ptr(), 0, hw.data_ptr(), out.data_ptr(),
+                                        valid.data_ptr(), st))
+    torch.cuda.synchronize()
+    ow = out.cpu().numpy().view(np.uint32)
+    got32 = ((ow[:, np.arange(n) >> 5] >> (np.arange(n) & 31).astype(np.uint32)) & 1).astype(np.int64)
+    assert np.array_equal(got32, ref) and bool(valid.all())
+
+
 def test_osd_w_full_order7_vs_oracle():
     """41 225 candidates per shot on [[144,12,12]] (order 7, no cap): against the C oracle."""
     H, _ = load_code_file("[[144, 12, 12]]")

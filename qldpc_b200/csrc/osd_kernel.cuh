@@ -995,6 +995,8 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     o = (o + 7) & ~(size_t)7;
     o += osdbf_key_area<K>(m, n);                               // keys (rank-counting path only)
     o += 2 * (size_t)n;                                         // ordering (uint16)
+    o = (o + 3) & ~(size_t)3;
+    o += 6 * (size_t)(m + 1);                                   // list of the columns that take part in a round: coefficient bits, slot
     return o + 64;
 }
 
@@ -1055,6 +1057,9 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
     uint32_t *solw = cand + (size_t)KB * WM;                                // [WN]
     kbits *keys = reinterpret_cast<kbits *>((reinterpret_cast<uintptr_t>(solw + WN) + 7) & ~(uintptr_t)7);
     uint16_t *ord = reinterpret_cast<uint16_t *>(reinterpret_cast<unsigned char *>(keys) + osdbf_key_area<K>(m, n));
+    uint32_t *s_hx = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(ord + n) + 3) & ~(uintptr_t)3);   // [m + 1] coefficient bits of the columns that take part in the round
+    uint16_t *s_hslot = reinterpret_cast<uint16_t *>(s_hx + (m + 1));                                             // [m + 1] and their slots
+    __shared__ int s_nhit;
     __shared__ uint32_t s_pl[KB];                      // pivot rows accepted in this round, in order
     __shared__ int s_off[KB];                          // and where their S' vectors are (offset into cand)
     __shared__ int s_pex[KB], s_pany[KB];              // per candidate: lowest free row that no other candidate of the round has / lowest free row (INT_MAX: none)
@@ -1364,7 +1369,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     rowpiv[p] = (uint16_t)(npiv + a);
                     atomicOr(&used[p >> 5], 1u << (p & 31));
                 }
-                if (lane == 0) s_nacc = __popc(acc);
+                if (lane == 0) { s_nacc = __popc(acc); s_nhit = 0; }
             }
             __syncthreads();
             const int nacc = s_nacc;
@@ -1390,20 +1395,18 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
                     const int c0 = g0 + i * NW * 32;
-                    unsigned hit = __ballot_sync(FULL, x[i] != 0 && c0 + lane <= npiv);
-                    while (hit) {
-                        const int l = __ffs(hit) - 1;
-                        hit &= hit - 1;
-                        unsigned xx = __shfl_sync(FULL, x[i], l);
-                        const int slot = (c0 + l < npiv) ? c0 + l : m;
-                        if (lane < WM) {
-                            uint32_t sv = 0;
-                            while (xx) {
-                                const int b = __ffs(xx) - 1;
-                                xx &= xx - 1;
-                                sv ^= cand[s_off[nacc - 1 - b] + lane];
-                            }
-                            TCP[(size_t)slot * WM + lane] ^= sv;
+                    // the columns that take part go to a list; the XORs are dealt out evenly over the warps afterwards (the hits
+                    // cluster: handled where they are found, the warp with the most of them held everybody up)
+                    const bool h = x[i] != 0 && c0 + lane <= npiv;
+                    const unsigned hit = __ballot_sync(FULL, h);
+                    if (hit) {
+                        int base = 0;
+                        if (lane == 0) base = atomicAdd(&s_nhit, __popc(hit));
+                        base = __shfl_sync(FULL, base, 0);
+                        if (h) {
+                            const int pos = base + __popc(hit & ((1u << lane) - 1u));
+                            s_hslot[pos] = (uint16_t)(c0 + lane < npiv ? c0 + lane : m);
+                            s_hx[pos] = x[i];
                         }
                     }
                 }
@@ -1421,6 +1424,23 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 const int off = s_off[lane];
                 for (int w = warp; w < WM; w += NW)
                     TCP[(size_t)(npiv + lane) * WM + w] = cand[off + w] | (w == (int)(p >> 5) ? (1u << (p & 31)) : 0u);
+            }
+            __syncthreads();
+            {
+                const int nhit = s_nhit;
+                for (int hI = warp; hI < nhit; hI += NW) {
+                    unsigned xx = s_hx[hI];
+                    const int slot = s_hslot[hI];
+                    if (lane < WM) {
+                        uint32_t sv = 0;
+                        while (xx) {
+                            const int b = __ffs(xx) - 1;
+                            xx &= xx - 1;
+                            sv ^= cand[s_off[nacc - 1 - b] + lane];
+                        }
+                        TCP[(size_t)slot * WM + lane] ^= sv;
+                    }
+                }
             }
             npiv += nacc;
             j += KB;

@@ -1428,17 +1428,21 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
             __syncthreads();
             {
                 const int nhit = s_nhit;
-                for (int hI = warp; hI < nhit; hI += NW) {
-                    unsigned xx = s_hx[hI];
-                    const int slot = s_hslot[hI];
+                for (int hI = warp; hI < nhit; hI += 2 * NW) {         // two columns in flight per warp
+                    const bool two = hI + NW < nhit;
+                    unsigned xa = s_hx[hI], xb = two ? s_hx[hI + NW] : 0u;
+                    const int sa = s_hslot[hI], sb = two ? (int)s_hslot[hI + NW] : sa;
                     if (lane < WM) {
-                        uint32_t sv = 0;
-                        while (xx) {
-                            const int b = __ffs(xx) - 1;
-                            xx &= xx - 1;
-                            sv ^= cand[s_off[nacc - 1 - b] + lane];
-                        }
-                        TCP[(size_t)slot * WM + lane] ^= sv;
+                        // most columns have a single pivot row of the round: first term of both, then the rest
+                        uint32_t va = cand[s_off[nacc - __ffs(xa)] + lane];
+                        uint32_t vb = two ? cand[s_off[nacc - __ffs(xb)] + lane] : 0u;
+                        uint32_t ta = TCP[(size_t)sa * WM + lane], tb = TCP[(size_t)sb * WM + lane];
+                        xa &= xa - 1;
+                        xb &= xb - 1;
+                        while (xa) { va ^= cand[s_off[nacc - __ffs(xa)] + lane]; xa &= xa - 1; }
+                        while (xb) { vb ^= cand[s_off[nacc - __ffs(xb)] + lane]; xb &= xb - 1; }
+                        TCP[(size_t)sa * WM + lane] = ta ^ va;
+                        if (two) TCP[(size_t)sb * WM + lane] = tb ^ vb;
                     }
                 }
             }

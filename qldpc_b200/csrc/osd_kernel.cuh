@@ -1040,7 +1040,7 @@ template <typename K, bool PACKED, int WMT>
 __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const OSDBlockParams P)
 {
     typedef typename KeyBits<K>::type kbits;
-    constexpr int NW = OSDBF_THREADS / 32;
+    constexpr int NW = OSDBF_THREADS / 32, NWW = NW - 1;         // warps; warps that gather while warp 0 folds
     constexpr int KB = OSDB_BATCH, CPW = KB / NW;               // candidates per round / per warp
     static_assert(KB == 32 && KB % NW == 0, "one candidate per lane of the resolving warp");
     const int m = P.m, n = P.n, WM = WMT ? WMT : P.WM, WN = P.WN;       // WMT: the word count at compile time (loops over words unroll), 0: any
@@ -1340,6 +1340,21 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 // never more pivots than the rank of H
                 while (__popc(acc) > rank - npiv) acc &= ~(0x80000000u >> __clz(acc));
                 const bool mine = (acc >> lane) & 1u;
+                // publish the pivots: the other warps start gathering the coefficient bits of the stored columns (which needs the
+                // pivot ROWS only) while this warp still folds the S vectors
+                if (mine) {
+                    const int a = __popc(acc & below);
+                    s_pl[a] = (uint32_t)p;
+                    s_g[a] = make_uint2((unsigned)(p >> 5), (unsigned)(31 - (p & 31)));
+                    s_off[a] = lane * WM;
+                    prow[npiv + a] = (uint16_t)p;
+                    pcolj[npiv + a] = (uint16_t)(j + lane);
+                    rowpiv[p] = (uint16_t)(npiv + a);
+                    atomicOr(&used[p >> 5], 1u << (p & 31));
+                }
+                if (lane == 0) { s_nacc = __popc(acc); s_nhit = 0; }
+                __threadfence_block();
+                asm volatile("bar.arrive 1, %0;" ::"n"(NW * 32) : "memory");
                 // S = free rows without the pivot row; fold the entries above the diagonal in (descending order)
                 if (mine) cand[(size_t)lane * WM + (p >> 5)] &= ~(1u << (p & 31));
                 __syncwarp();
@@ -1358,20 +1373,9 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     if (lane < WM) cand[(size_t)b * WM + lane] ^= v;
                     __syncwarp();
                 }
-                // publish the pivots
-                if (mine) {
-                    const int a = __popc(acc & below);
-                    s_pl[a] = (uint32_t)p;
-                    s_g[a] = make_uint2((unsigned)(p >> 5), (unsigned)(31 - (p & 31)));
-                    s_off[a] = lane * WM;
-                    prow[npiv + a] = (uint16_t)p;
-                    pcolj[npiv + a] = (uint16_t)(j + lane);
-                    rowpiv[p] = (uint16_t)(npiv + a);
-                    atomicOr(&used[p >> 5], 1u << (p & 31));
-                }
-                if (lane == 0) { s_nacc = __popc(acc); s_nhit = 0; }
+            } else {
+                asm volatile("bar.sync 1, %0;" ::"n"(NW * 32) : "memory");      // the pivot rows of the round are known
             }
-            __syncthreads();
             const int nacc = s_nacc;
             // apply.  Row c of T is added to other rows only once c is a pivot row: the columns of free rows are unit vectors
             // and have no pivot row of this round, so only the stored columns (pivots 0 .. npiv-1) and the syndrome take part.
@@ -1382,7 +1386,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 int cb[NI];
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
-                    const int idx = g0 + i * NW * 32 + lane;
+                    const int idx = g0 + i * NWW * 32 + lane;
                     cb[i] = (idx < npiv ? idx : m) * WM;
                     x[i] = 0;
                 }
@@ -1394,7 +1398,7 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 }
 #pragma unroll
                 for (int i = 0; i < NI; ++i) {
-                    const int c0 = g0 + i * NW * 32;
+                    const int c0 = g0 + i * NWW * 32;
                     // the columns that take part go to a list; the XORs are dealt out evenly over the warps afterwards (the hits
                     // cluster: handled where they are found, the warp with the most of them held everybody up)
                     const bool h = x[i] != 0 && c0 + lane <= npiv;
@@ -1411,13 +1415,14 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                     }
                 }
             };
-            for (int g0 = warp * 32; g0 <= npiv; g0 += 4 * NW * 32) {
-                const int ni = (npiv + 1 - g0 + NW * 32 - 1) / (NW * 32);
+            for (int g0 = (warp - 1) * 32; warp > 0 && g0 <= npiv; g0 += 4 * NWW * 32) {
+                const int ni = (npiv + 1 - g0 + NWW * 32 - 1) / (NWW * 32);
                 if (ni >= 4) apply_group(OsdIC<4>(), g0);
                 else if (ni == 3) apply_group(OsdIC<3>(), g0);
                 else if (ni == 2) apply_group(OsdIC<2>(), g0);
                 else apply_group(OsdIC<1>(), g0);
             }
+            __syncthreads();                                          // warp 0 has folded: the S' vectors are final
             // the columns of the new pivot rows: unit vector ^ S' (lane = pivot of the round, warp w writes the words w, w + NW, ...)
             if (lane < nacc) {
                 const uint32_t p = s_pl[lane];
@@ -1425,7 +1430,6 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 for (int w = warp; w < WM; w += NW)
                     TCP[(size_t)(npiv + lane) * WM + w] = cand[off + w] | (w == (int)(p >> 5) ? (1u << (p & 31)) : 0u);
             }
-            __syncthreads();
             {
                 const int nhit = s_nhit;
                 for (int hI = warp; hI < nhit; hI += 2 * NW) {         // two columns in flight per warp

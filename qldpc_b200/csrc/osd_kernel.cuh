@@ -1289,11 +1289,11 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
                 // im[k'] ^= im[k] on this matrix -- the vectors themselves are only touched to carry the XOR out.
                 unsigned im = 0;
                 for (unsigned t = shared_piv; t;) {
-                    int kk[8];
+                    int kk[4];
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) { kk[u] = t ? __ffs(t) - 1 : -1; t &= t - 1; }
+                    for (int u = 0; u < 4; ++u) { kk[u] = t ? __ffs(t) - 1 : -1; t &= t - 1; }
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
+                    for (int u = 0; u < 4; ++u) {
                         const int pk = __shfl_sync(FULL, p, kk[u] < 0 ? 0 : kk[u]);
                         if (kk[u] >= 0) im |= ((cand[(size_t)lane * WM + (pk >> 5)] >> (pk & 31)) & 1u) << kk[u];
                     }

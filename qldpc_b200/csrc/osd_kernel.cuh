@@ -952,12 +952,15 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 //             afterwards, in descending order, S'_b = S_b ^ sum_{a > b, S_b[p_a]} S'_a, which turns the SEQUENCE of row
 //             operations of the round into ONE linear map  c -> c ^ sum_a c[p_a] S'_a  whose coefficients are bits of the
 //             column as it stood BEFORE the round;
-//   apply     each warp owns stored columns (consecutive slots: conflict-free): a lane gathers the <= 32 coefficient bits of
-//             its column (independent loads, no chain through the pivots), then the warp XORs the selected S' vectors into
-//             the columns that have any (~65 per round), a word per lane; the columns of the new pivot rows (unit vector ^
-//             S') are appended with lane = pivot.  No barrier inside, warps never touch each other's columns.
-// Three barriers per 32 candidates (the round-1 kernel spent three per 8 and walked every column through the pivots of the
-// batch one after the other: 1.2 M of its 2.0 M cycles per shot).  2.4e5 -> 1.04e6 failed shots/s on 864 x 2592.
+//   apply     warp 0 publishes the pivot ROWS as soon as the forward reduction is done (bar.arrive on a named barrier) and folds
+//             while warps 1..15 gather: a lane collects the <= 32 coefficient bits of its stored column (consecutive slots:
+//             conflict-free; independent loads, no chain through the pivots); the columns that have any (~65 per round) go to a
+//             shared list.  After a block barrier the XORs of the selected S' vectors into those columns (a word per lane) are
+//             dealt out evenly over all 16 warps -- the hits cluster -- and the columns of the new pivot rows (unit vector ^ S')
+//             are appended with lane = pivot.
+// Four block barriers and one named barrier per 32 candidates (the round-1 kernel spent three per 8 and walked every column
+// through the pivots of the batch one after the other: 1.2 M of its 2.0 M cycles per shot).  2.4e5 -> 1.17e6 failed shots/s on
+// 864 x 2592.
 // Inconsistent syndromes are handed to osd0_block_kernel (redo list).  The checks of a column come from a per-code table
 // packed 3 x 10 bits (m <= 1024, column weight <= 3: the space-time matrices; otherwise from the CSC in global memory).
 // ------------------------------------------------------------------------------------------------

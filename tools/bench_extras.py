@@ -198,6 +198,9 @@ def baseline_configs(quick=False, only=None, emit=None):
             put(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f32, {label}", p=p, **res,
                 bp_only=dict(ms=res_bp["ms"], shots_per_s=res_bp["shots_per_s"], shot_iterations_per_s=res_bp["shot_iterations_per_s"]),
                 roofline=roof, bp_only_hbm_staged=staged, bp_only_cta_staged=cta_staged, bp_only_cta_staged_f64=cta_staged_f64)
+            # the bit-exact arithmetic on the same shots: float64 min-sum (bp_stage_kernel) + block OSD with float64 keys
+            res64 = r.run(p, B // 2, dict(max_iter=50, **dict(ms_kw, precision=64)), 0, synd_override=synd[:B // 2], reps=1)
+            put(f"4: space-time [[144,12,12]]x12 (864x2592, E={E}) p={p} min-sum BP50 + OSD-0, f64 (bit-exact), CTA-per-shot (staged)", p=p, **res64)
             if p == 0.001:      # the reference decodes these matrices with sum-product (studies/studyTT.py:49)
                 sp32 = r.run(p, B, dict(variant="sum_product", max_iter=50, precision=32), 0, synd_override=synd, reps=1)
                 sp64 = r.run(p, B // 4, dict(variant="sum_product", max_iter=50, precision=64), 0, synd_override=synd[:B // 4], reps=1)

@@ -1004,39 +1004,6 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
 }
 
 
-// (key, index) pairs of the block kernel's register-resident bitonic sort.  float keys: one 64-bit word, key << 16 | index (a single
-// unsigned compare orders by key, then by index: the stable order); double keys: the 64-bit key and the index side by side.
-template <typename KBt> struct OsdSortElem;
-template <> struct OsdSortElem<uint32_t> {
-    unsigned long long v;
-    static constexpr int BYTES = 8;
-    __device__ __forceinline__ static OsdSortElem make(uint32_t key, uint32_t idx) { return OsdSortElem{((unsigned long long)key << 16) | idx}; }
-    __device__ __forceinline__ bool after(const OsdSortElem &o) const { return v > o.v; }
-    __device__ __forceinline__ OsdSortElem shfl_xor(int mask) const { return OsdSortElem{__shfl_xor_sync(0xffffffffu, v, mask)}; }
-    __device__ __forceinline__ uint32_t index() const { return (uint32_t)v & 0xFFFFu; }
-    __device__ __forceinline__ void store(unsigned char *base, int N2, int buf, int pos) const { reinterpret_cast<unsigned long long *>(base)[buf * N2 + pos] = v; }
-    __device__ __forceinline__ static OsdSortElem load(const unsigned char *base, int N2, int buf, int pos) { return OsdSortElem{reinterpret_cast<const unsigned long long *>(base)[buf * N2 + pos]}; }
-};
-template <> struct OsdSortElem<unsigned long long> {
-    unsigned long long k;
-    uint32_t i;
-    static constexpr int BYTES = 10;
-    __device__ __forceinline__ static OsdSortElem make(unsigned long long key, uint32_t idx) { return OsdSortElem{key, idx}; }
-    __device__ __forceinline__ bool after(const OsdSortElem &o) const { return k > o.k || (k == o.k && i > o.i); }
-    __device__ __forceinline__ OsdSortElem shfl_xor(int mask) const { return OsdSortElem{__shfl_xor_sync(0xffffffffu, k, mask), __shfl_xor_sync(0xffffffffu, i, mask)}; }
-    __device__ __forceinline__ uint32_t index() const { return i; }
-    __device__ __forceinline__ void store(unsigned char *base, int N2, int buf, int pos) const
-    {
-        reinterpret_cast<unsigned long long *>(base)[buf * N2 + pos] = k;
-        reinterpret_cast<uint16_t *>(base + 16 * (size_t)N2)[buf * N2 + pos] = (uint16_t)i;
-    }
-    __device__ __forceinline__ static OsdSortElem load(const unsigned char *base, int N2, int buf, int pos)
-    {
-        return OsdSortElem{reinterpret_cast<const unsigned long long *>(base)[buf * N2 + pos], reinterpret_cast<const uint16_t *>(base + 16 * (size_t)N2)[buf * N2 + pos]};
-    }
-};
-constexpr int OSDBF_EPT = 8;                 // elements per thread of the register-resident sort
-
 template <int N> struct OsdIC { static constexpr int value = N; };
 
 template <typename K, bool PACKED, int WMT>
@@ -1107,63 +1074,89 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
         for (int w = tid; w < WN; w += NT) solw[w] = hard[w];
         int N2 = 1;
         while (N2 < n) N2 <<= 1;
-        if (N2 == OSDBF_EPT * NT && (size_t)2 * N2 * OsdSortElem<kbits>::BYTES <= 4 * (size_t)m * WM) {
-            // bitonic sort with the elements in registers: thread (warp, lane) holds the elements 256 warp + 32 e + lane, e < 8.
-            // Partners at distance < 32 come by shuffle, at 32 / 64 / 128 from the thread's own registers; only the 10 stages at
-            // distance >= 256 (of 78) go through shared memory (double-buffered in the still unused transform area: one barrier each).
-            typedef OsdSortElem<kbits> El;
-            constexpr int EPT = OSDBF_EPT;
-            El el[EPT];
-            const int bi = warp * (32 * EPT) + lane;
+        constexpr int RE = 8;                                          // elements per thread of the radix sort, at most
+        const int E = (n + NT - 1) / NT, NTOT = NT * E;
+        if (E <= RE && (size_t)NTOT * (sizeof(kbits) + 2) + NW * 256 * 2 + 256 * 4 + 16 <= 4 * (size_t)m * WM) {
+            // Stable LSD radix sort of (key, index), 8 bits per pass (4 passes for float keys, 8 for double), in the still unused
+            // transform area.  Thread (warp, lane) holds the elements at positions 32 E warp + 32 e + lane, e < E: within a warp the
+            // rank of an element among the equal digits before it is popc(match_any & lanes below) plus a running per-warp count per
+            // digit; a column scan over the warps and a 256-wide scan of the digit totals give the destinations.  ~200 instructions
+            // per thread and pass (the bitonic network it replaces: 78 stages, ~4000 instructions per thread).
+            unsigned char *sb = reinterpret_cast<unsigned char *>(TCP);
+            kbits *kb = reinterpret_cast<kbits *>(sb);                                     // [NTOT]
+            uint16_t *ib = reinterpret_cast<uint16_t *>(kb + NTOT);                        // [NTOT]
+            uint16_t *hist = ib + NTOT;                                                    // [NW][256]
+            uint32_t *base = reinterpret_cast<uint32_t *>((reinterpret_cast<uintptr_t>(hist + NW * 256) + 3) & ~(uintptr_t)3);   // [256]
+            __shared__ uint32_t s_wsum[8];
+            kbits key[RE];
+            uint32_t idx[RE];
+            const int p0 = warp * 32 * E + lane;
 #pragma unroll
-            for (int e = 0; e < EPT; ++e) {
-                const int i = bi + 32 * e;
-                el[e] = (i < n) ? El::make(KeyBits<K>::get(llr[i]), (uint32_t)i) : El::make(~(kbits)0, 0xFFFFu);
-            }
-            // element i takes its partner's value iff (mine > partner) ^ (i is the upper one of the pair) ^ (i lies in a descending block)
-            auto reg_stage = [&](auto d_c, unsigned descm) {
-                constexpr int D = decltype(d_c)::value;
-#pragma unroll
-                for (int e = 0; e < EPT; ++e)
-                    if ((e & D) == 0) {
-                        if (el[e].after(el[e | D]) != (bool)((descm >> e) & 1u)) { const El t = el[e]; el[e] = el[e | D]; el[e | D] = t; }
-                    }
-            };
-            unsigned char *sbase = reinterpret_cast<unsigned char *>(TCP);
-            int buf = 0;
-            for (int k = 2; k <= N2; k <<= 1) {
-                // bit e of descm: element e of this thread lies in a descending block of length k
-                unsigned descm = 0;
-#pragma unroll
-                for (int e = 0; e < EPT; ++e) descm |= (((bi + 32 * e) & k) != 0 ? 1u : 0u) << e;
-                for (int jd = k >> 1; jd > 0; jd >>= 1) {
-                    if (jd >= 32 * EPT) {
-#pragma unroll
-                        for (int e = 0; e < EPT; ++e) el[e].store(sbase, N2, buf, bi + 32 * e);
-                        __syncthreads();
-                        const bool hi = (bi & jd) != 0;                                  // (a warp bit)
-#pragma unroll
-                        for (int e = 0; e < EPT; ++e) {
-                            const El o = El::load(sbase, N2, buf, (bi + 32 * e) ^ jd);
-                            if (el[e].after(o) != (hi != (bool)((descm >> e) & 1u))) el[e] = o;
-                        }
-                        buf ^= 1;
-                    } else if (jd == 128) reg_stage(OsdIC<4>(), descm);
-                    else if (jd == 64) reg_stage(OsdIC<2>(), descm);
-                    else if (jd == 32) reg_stage(OsdIC<1>(), descm);
-                    else {
-                        const bool hi = (lane & jd) != 0;
-#pragma unroll
-                        for (int e = 0; e < EPT; ++e) {
-                            const El o = el[e].shfl_xor(jd);
-                            if (el[e].after(o) != (hi != (bool)((descm >> e) & 1u))) el[e] = o;
-                        }
-                    }
+            for (int e = 0; e < RE; ++e)
+                if (e < E) {
+                    const int pos = p0 + 32 * e;
+                    key[e] = (pos < n) ? KeyBits<K>::get(llr[pos]) : ~(kbits)0;           // padding sorts last
+                    idx[e] = (pos < n) ? (uint32_t)pos : 0xFFFFu;
                 }
+            for (int pass = 0; pass < (int)sizeof(kbits); ++pass) {
+                const int shift = 8 * pass;
+                for (int i = tid; i < NW * 128; i += NT) reinterpret_cast<uint32_t *>(hist)[i] = 0u;
+                __syncthreads();
+                uint32_t rank[RE];
+#pragma unroll
+                for (int e = 0; e < RE; ++e)
+                    if (e < E) {                                                           // (uniform)
+                        const uint32_t d = (uint32_t)(key[e] >> shift) & 255u;
+                        const unsigned peers = __match_any_sync(FULL, d);
+                        const uint32_t r = __popc(peers & ((1u << lane) - 1u));
+                        const uint32_t prev = hist[warp * 256 + d];
+                        __syncwarp();
+                        if (r == 0) hist[warp * 256 + d] = (uint16_t)(prev + __popc(peers));
+                        __syncwarp();
+                        rank[e] = prev + r;
+                    }
+                __syncthreads();
+                uint32_t tot = 0, incl = 0;
+                if (tid < 256) {
+                    for (int w = 0; w < NW; ++w) {                                         // per digit: exclusive scan over the warps
+                        const uint32_t c = hist[w * 256 + tid];
+                        hist[w * 256 + tid] = (uint16_t)tot;
+                        tot += c;
+                    }
+                    incl = tot;
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t o = __shfl_up_sync(FULL, incl, d);
+                        if (lane >= d) incl += o;
+                    }
+                    if (lane == 31) s_wsum[warp] = incl;
+                }
+                __syncthreads();
+                if (tid < 256) {
+                    uint32_t off = 0;
+                    for (int w = 0; w < warp; ++w) off += s_wsum[w];
+                    base[tid] = off + incl - tot;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < RE; ++e)
+                    if (e < E) {
+                        const uint32_t d = (uint32_t)(key[e] >> shift) & 255u;
+                        const uint32_t dst = base[d] + hist[warp * 256 + d] + rank[e];
+                        kb[dst] = key[e];
+                        ib[dst] = (uint16_t)idx[e];
+                    }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < RE; ++e)
+                    if (e < E) {
+                        key[e] = kb[p0 + 32 * e];
+                        idx[e] = ib[p0 + 32 * e];
+                    }
             }
 #pragma unroll
-            for (int e = 0; e < EPT; ++e)
-                if (bi + 32 * e < n) ord[bi + 32 * e] = (uint16_t)el[e].index();
+            for (int e = 0; e < RE; ++e)
+                if (e < E && p0 + 32 * e < n) ord[p0 + 32 * e] = (uint16_t)idx[e];
         } else if (osdbf_bitonic_fits<K>(m, n)) {
             // bitonic sort of (key, index) pairs in the (still unused) transform area: O(n log^2 n) instead of the
             // O(n^2) rank counting -- 78 stages of 2048 compare-exchanges for n = 2592

@@ -960,7 +960,7 @@ __global__ void __launch_bounds__(OSDB_THREADS) osd0_block_kernel(const OSDBlock
 //             are appended with lane = pivot.
 // Four block barriers and one named barrier per 32 candidates (the round-1 kernel spent three per 8 and walked every column
 // through the pivots of the batch one after the other: 1.2 M of its 2.0 M cycles per shot).  2.4e5 -> 1.17e6 failed shots/s on
-// 864 x 2592.
+// 864 x 2592 (with the radix sort of the keys: 1.21e6).
 // Inconsistent syndromes are handed to osd0_block_kernel (redo list).  The checks of a column come from a per-code table
 // packed 3 x 10 bits (m <= 1024, column weight <= 3: the space-time matrices; otherwise from the CSC in global memory).
 // ------------------------------------------------------------------------------------------------
@@ -970,8 +970,8 @@ constexpr int OSDB_BATCH = 32;
 #endif
 constexpr int OSDBF_THREADS = OSDBF_THREADS_N;
 
-// the sort runs as a bitonic sort inside the (still idle) transform area when (key, index) pairs of the padded length fit
-// there; only the rank-counting fallback needs the keys outside of it.
+// the sort runs inside the (still idle) transform area: a radix sort when its buffers fit there (the space-time matrices), else a
+// bitonic sort of the padded length if THAT fits; only the rank-counting fallback needs the keys outside of it.
 template <typename K>
 __host__ __device__ inline bool osdbf_bitonic_fits(int m, int n)
 {
@@ -1003,6 +1003,28 @@ __host__ __device__ inline size_t osdbf_smem_bytes(int m, int n)
     return o + 64;
 }
 
+
+// (key, index) pairs of the register-resident bitonic sort that double keys still use (eight radix passes are slower than it)
+template <typename KBt> struct OsdSortElem;
+template <> struct OsdSortElem<unsigned long long> {
+    unsigned long long k;
+    uint32_t i;
+    static constexpr int BYTES = 10;
+    __device__ __forceinline__ static OsdSortElem make(unsigned long long key, uint32_t idx) { return OsdSortElem{key, idx}; }
+    __device__ __forceinline__ bool after(const OsdSortElem &o) const { return k > o.k || (k == o.k && i > o.i); }
+    __device__ __forceinline__ OsdSortElem shfl_xor(int mask) const { return OsdSortElem{__shfl_xor_sync(0xffffffffu, k, mask), __shfl_xor_sync(0xffffffffu, i, mask)}; }
+    __device__ __forceinline__ uint32_t index() const { return i; }
+    __device__ __forceinline__ void store(unsigned char *base, int N2, int buf, int pos) const
+    {
+        reinterpret_cast<unsigned long long *>(base)[buf * N2 + pos] = k;
+        reinterpret_cast<uint16_t *>(base + 16 * (size_t)N2)[buf * N2 + pos] = (uint16_t)i;
+    }
+    __device__ __forceinline__ static OsdSortElem load(const unsigned char *base, int N2, int buf, int pos)
+    {
+        return OsdSortElem{reinterpret_cast<const unsigned long long *>(base)[buf * N2 + pos], reinterpret_cast<const uint16_t *>(base + 16 * (size_t)N2)[buf * N2 + pos]};
+    }
+};
+constexpr int OSDBF_EPT = 8;                 // elements per thread of the register-resident sort
 
 template <int N> struct OsdIC { static constexpr int value = N; };
 
@@ -1076,9 +1098,8 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
         while (N2 < n) N2 <<= 1;
         constexpr int RE = 8;                                          // elements per thread of the radix sort, at most
         const int E = (n + NT - 1) / NT, NTOT = NT * E;
-        if (E <= RE && (size_t)NTOT * (sizeof(kbits) + 2) + NW * 256 * 2 + 256 * 4 + 16 <= 4 * (size_t)m * WM) {
-            // Stable LSD radix sort of (key, index), 8 bits per pass (4 passes for float keys, 8 for double), in the still unused
-            // transform area.  Thread (warp, lane) holds the elements at positions 32 E warp + 32 e + lane, e < E: within a warp the
+        if (sizeof(kbits) == 4 && E <= RE && (size_t)NTOT * (sizeof(kbits) + 2) + NW * 256 * 2 + 256 * 4 + 16 <= 4 * (size_t)m * WM) {
+            // float keys: stable LSD radix sort of (key, index), 8 bits per pass, in the still unused transform area.  Thread (warp, lane) holds the elements at positions 32 E warp + 32 e + lane, e < E: within a warp the
             // rank of an element among the equal digits before it is popc(match_any & lanes below) plus a running per-warp count per
             // digit; a column scan over the warps and a 256-wide scan of the digit totals give the destinations.  ~200 instructions
             // per thread and pass (the bitonic network it replaces: 78 stages, ~4000 instructions per thread).
@@ -1157,6 +1178,63 @@ __global__ void __launch_bounds__(OSDBF_THREADS, 2) osd0_block_fast_kernel(const
 #pragma unroll
             for (int e = 0; e < RE; ++e)
                 if (e < E && p0 + 32 * e < n) ord[p0 + 32 * e] = (uint16_t)idx[e];
+        } else if (sizeof(kbits) == 8 && N2 == OSDBF_EPT * NT && (size_t)2 * N2 * 10 <= 4 * (size_t)m * WM) {
+            // bitonic sort with the elements in registers: thread (warp, lane) holds the elements 256 warp + 32 e + lane, e < 8.
+            // Partners at distance < 32 come by shuffle, at 32 / 64 / 128 from the thread's own registers; only the 10 stages at
+            // distance >= 256 (of 78) go through shared memory (double-buffered in the still unused transform area: one barrier each).
+            typedef OsdSortElem<unsigned long long> El;
+            constexpr int EPT = OSDBF_EPT;
+            El el[EPT];
+            const int bi = warp * (32 * EPT) + lane;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                const int i = bi + 32 * e;
+                el[e] = (i < n) ? El::make((unsigned long long)KeyBits<K>::get(llr[i]), (uint32_t)i) : El::make(~0ull, 0xFFFFu);
+            }
+            // element i takes its partner's value iff (mine > partner) ^ (i is the upper one of the pair) ^ (i lies in a descending block)
+            auto reg_stage = [&](auto d_c, unsigned descm) {
+                constexpr int D = decltype(d_c)::value;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if ((e & D) == 0) {
+                        if (el[e].after(el[e | D]) != (bool)((descm >> e) & 1u)) { const El t = el[e]; el[e] = el[e | D]; el[e | D] = t; }
+                    }
+            };
+            unsigned char *sbase = reinterpret_cast<unsigned char *>(TCP);
+            int buf = 0;
+            for (int k = 2; k <= N2; k <<= 1) {
+                // bit e of descm: element e of this thread lies in a descending block of length k
+                unsigned descm = 0;
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) descm |= (((bi + 32 * e) & k) != 0 ? 1u : 0u) << e;
+                for (int jd = k >> 1; jd > 0; jd >>= 1) {
+                    if (jd >= 32 * EPT) {
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) el[e].store(sbase, N2, buf, bi + 32 * e);
+                        __syncthreads();
+                        const bool hi = (bi & jd) != 0;                                  // (a warp bit)
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const El o = El::load(sbase, N2, buf, (bi + 32 * e) ^ jd);
+                            if (el[e].after(o) != (hi != (bool)((descm >> e) & 1u))) el[e] = o;
+                        }
+                        buf ^= 1;
+                    } else if (jd == 128) reg_stage(OsdIC<4>(), descm);
+                    else if (jd == 64) reg_stage(OsdIC<2>(), descm);
+                    else if (jd == 32) reg_stage(OsdIC<1>(), descm);
+                    else {
+                        const bool hi = (lane & jd) != 0;
+#pragma unroll
+                        for (int e = 0; e < EPT; ++e) {
+                            const El o = el[e].shfl_xor(jd);
+                            if (el[e].after(o) != (hi != (bool)((descm >> e) & 1u))) el[e] = o;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (bi + 32 * e < n) ord[bi + 32 * e] = (uint16_t)el[e].index();
         } else if (osdbf_bitonic_fits<K>(m, n)) {
             // bitonic sort of (key, index) pairs in the (still unused) transform area: O(n log^2 n) instead of the
             // O(n^2) rank counting -- 78 stages of 2048 compare-exchanges for n = 2592

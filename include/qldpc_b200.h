@@ -239,7 +239,8 @@ int qldpc_words_n(const qldpc_code *code);
 
 /* BP on packed device syndromes.  llr is float32 or float64 per cfg->precision.
  * fail_idx/fail_count (may be NULL): compacted ids of the BP failures, for qldpc_osd_decode_dev.
- * iter_total (may be NULL): device uint64 accumulating executed iterations (roofline accounting). */
+ * iter_total (may be NULL): device uint64 accumulating EXECUTED iterations (roofline accounting): at low error rates the float32 warp
+ * kernel retires all-zero syndromes without running the iteration the reference spends on them (exit iteration 0 either way). */
 int qldpc_bp_decode_dev(qldpc_code *code, const qldpc_bp_config *cfg, const double *prior_host, int64_t B,
                         const uint32_t *synd, uint32_t *hard, uint8_t *conv, int32_t *iters,
                         void *llr, int32_t llr_mode, int32_t *fail_idx, uint32_t *fail_count,

@@ -61,6 +61,8 @@ struct BPParams {
     int sym;                    // sum-product: apply alpha / damping / clip (decoding.py:131)
     double alpha, damping, one_minus_damping, clip;
     int prior_uniform;          // all priors equal (warp kernel: the message state starts as one constant)
+    int zero_ok;                // all priors > 0 (also as float32) and alpha >= 0: a shot with an all-zero syndrome converges at iteration 0
+                                //   with the all-zero hard decision (every message and posterior is positive) -- the warp kernel retires it unseen
     double qpad;                // max(clip, largest prior): start value of padding edge slots (bp_warp / bp_cta kernels)
     uint32_t *hard;             // [B][WN] packed hard decisions (out)
     uint8_t *conv;              // [B] (out)

@@ -125,7 +125,10 @@ struct BPWarpTables {
 
 // VAR: 0 = normalised / damped / clipped min-sum (rework/decoding.py:5-75), 1 = sum-product (beliefPropagation.py:88-144),
 // 2 = sum-product with alpha, damping and clipping (rework/decoding.py:131-191); 1 and 2 in the psi domain (above).
-template <int CPL, int VPL, int RW, bool TWO, int VAR>
+// ZSC: the zero-syndrome shortcut below is compiled in (its own instantiation: it costs three registers, which the [[144,12,12]]
+// kernel at its 128-register cap pays with a spill and 11 % at p = 0.05 -- the launcher picks it when the priors say that at least a
+// tenth of the shots have an all-zero syndrome)
+template <int CPL, int VPL, int RW, bool TWO, int VAR, bool ZSC = false>
 __global__ void __launch_bounds__(BPW_WARPS * 32, (CPL * RW + VPL * 4 > 44) ? 1 : 2)
 bp_warp_kernel(const BPParams P, const BPWarpTables W)
 {
@@ -189,6 +192,32 @@ bp_warp_kernel(const BPParams P, const BPWarpTables W)
         for (int i = 0; i < CPL; ++i) {
             sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
             salpha[i] = __uint_as_float(__float_as_uint(VAR == 1 ? 1.f : alpha) ^ sbit[i]);
+        }
+        // All-zero syndrome (a quarter to a third of the shots at p = 0.01): with positive priors every message and posterior of
+        // iteration 0 is positive, the hard decision is all-zero and reproduces the syndrome -- the reference returns at its first
+        // check (decoding.py:69-73).  The shot is retired with exactly those outputs and costs only its bookkeeping.
+        if (ZSC && P.zero_ok && !(P.llr != nullptr && P.llr_mode == LLR_ALL)) {
+            uint32_t anyb = 0;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) anyb |= sbit[i];
+            if (__all_sync(FULL, anyb == 0)) {
+                if (need_grab) {
+                    grp_next = (long long)__shfl_sync(FULL, s0, 0);
+                    grp_end = grp_next + BPW_GRAB;
+                }
+                next2_shot = grp_next++;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) sw[i] = swn[i];
+                load_synd(next2_shot, swn);
+                if (lane < WN) P.hard[(size_t)shot * WN + lane] = 0u;
+                if (lane == 0) {
+                    P.conv[shot] = 1;
+                    if (P.iters) P.iters[shot] = 0;
+                }
+                shot = next_shot;
+                next_shot = next2_shot;
+                continue;
+            }
         }
         // Q = where(mask, prior, 0) (decoding.py:21): one value when the prior is uniform, else publish the priors and
         // gather them along the edges

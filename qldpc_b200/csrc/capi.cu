@@ -521,10 +521,15 @@ static int set_prior(qldpc_code *c, const double *prior_host, cudaStream_t st)
     c->prior_cache.assign(prior_host, prior_host + c->n);
     c->prior_max = 0.0;
     c->prior_uniform = true;
+    c->prior_positive = true;
+    double log_zero = 0.0;
     for (int i = 0; i < c->n; ++i) {
+        c->prior_positive = c->prior_positive && prior_host[i] > 0.0 && (float)prior_host[i] > 0.f;
+        log_zero -= std::log1p(std::exp(-prior_host[i]));              // log(1 - p_i)
         c->prior_max = std::max(c->prior_max, std::fabs(prior_host[i]));
         c->prior_uniform = c->prior_uniform && (memcmp(&prior_host[i], &prior_host[0], sizeof(double)) == 0);
     }
+    c->zero_frac = std::exp(log_zero);
     return QLDPC_OK;
 }
 
@@ -561,6 +566,7 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.clip = cfg->clip;
     P.qpad = std::max(cfg->clip, c->prior_max);
     P.prior_uniform = c->prior_uniform ? 1 : 0;
+    P.zero_ok = (c->prior_positive && cfg->alpha >= 0.0 && !getenv("QLDPC_NO_ZERO_SHORTCUT")) ? (c->zero_frac >= 0.1 || getenv("QLDPC_FORCE_ZERO_SHORTCUT") ? 2 : 1) : 0;
     P.hard = hard;
     P.conv = conv;
     P.iters = iters;
@@ -933,7 +939,7 @@ extern "C" int qldpc_bp_messages_host(qldpc_code *c, const qldpc_bp_config *cfg,
         P.prior = c->prior64.p;
         P.max_iter = cf.max_iter;
         P.sym = (cf.variant == QLDPC_SUM_PRODUCT_SYM);
-        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip; P.qpad = std::max(cf.clip, c->prior_max); P.prior_uniform = 0;
+        P.alpha = cf.alpha; P.damping = cf.damping; P.one_minus_damping = 1.0 - cf.damping; P.clip = cf.clip; P.qpad = std::max(cf.clip, c->prior_max); P.prior_uniform = 0; P.zero_ok = 0;
         P.hard = c->ws_hard.as<uint32_t>(); P.conv = c->ws_conv.as<uint8_t>(); P.iters = nullptr;
         P.llr = nullptr; P.llr_mode = LLR_NONE;
         P.cursor = &ctrl->cursor; P.fail_idx = nullptr; P.fail_count = &ctrl->fail_count; P.iter_total = nullptr;

@@ -120,6 +120,8 @@ struct qldpc_code {
     int max_row_w = 0;
     double prior_max = 0.0;
     bool prior_uniform = false;
+    bool prior_positive = false;                                   // every prior > 0, also after rounding to float32
+    double zero_frac = 0.0;                                        // prod_i (1 - p_i), p_i = 1 / (1 + e^prior_i): the share of error-free shots the priors imply
     bool tiled_ok = false;
     std::vector<double> prior_cache;
     DevBuf prior32, prior64, ctrl, gstate;

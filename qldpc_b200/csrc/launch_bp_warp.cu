@@ -1,10 +1,10 @@
 // Launchers of the warp-per-shot float32 min-sum kernels (bp_warp_kernel.cuh) and the dispatch to its other variants.
 #include "capi_internal.h"
 
-template <int CPL, int VPL, bool TWO, int VAR>
+template <int CPL, int VPL, bool TWO, int VAR, bool ZSC = false>
 static cudaError_t launch_bp_warp_inst3(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    auto kern = bp_warp_kernel<CPL, VPL, 6, TWO, VAR>;
+    auto kern = bp_warp_kernel<CPL, VPL, 6, TWO, VAR, ZSC>;
     if (G.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
         if (e != cudaSuccess) return e;
@@ -22,6 +22,8 @@ static cudaError_t launch_ms(const qldpc_code *c, const BPParams &P, const BPGeo
     // The iteration-0 addition order only matters for non-uniform priors: with one prior value every message of iteration 0
     // has the same magnitude a = alpha * prior, and (+-a +- a) +- a rounds the same in any order (2a and 0 are exact).
     const bool two = c->two_tables && !P.prior_uniform;
+    if (P.zero_ok == 2)             // many all-zero syndromes expected (low error rates): the instantiation with the shortcut
+        return two ? launch_bp_warp_inst3<CPL, VPL, true, 0, true>(c, P, G, st) : launch_bp_warp_inst3<CPL, VPL, false, 0, true>(c, P, G, st);
     return two ? launch_bp_warp_inst3<CPL, VPL, true, 0>(c, P, G, st) : launch_bp_warp_inst3<CPL, VPL, false, 0>(c, P, G, st);
 }
 

@@ -302,6 +302,41 @@ def test_f32_divergence_is_iteration_resolved():
         assert not (conv64_at[bad] < first[bad]).any()
 
 
+@pytest.mark.parametrize("stem,p", [("[[90, 8, 10]]", 0.01), ("[[144, 12, 12]]", 0.01), ("[[144, 12, 12]]", 0.05)])
+def test_zero_syndrome_shortcut_changes_no_output(stem, p):
+    """Low error rates: a quarter to 40 % of the shots have an all-zero syndrome; with positive priors the reference returns the
+    all-zero correction at its first check (decoding.py:69-73) and the float32 warp kernel retires such shots without running the
+    iteration (its own instantiation, chosen when the priors imply >= 10 % error-free shots).  Hard decisions, flags, exit iterations
+    and posterior LLRs must not change: with the shortcut disabled, chosen by the priors, and forced."""
+    import os
+    H, _ = load_code_file(stem)
+    n = H.shape[1]
+    rng = np.random.default_rng(21)
+    err = (rng.random((6000, n)) < p).astype(np.uint8)
+    synd = _synd(H, err)
+    assert (synd.sum(axis=1) == 0).mean() > (0.15 if p == 0.01 else 0.0)
+    code = _code(H, "min_sum")
+    outs = []
+    for env in ({"QLDPC_NO_ZERO_SHORTCUT": "1"}, {}, {"QLDPC_FORCE_ZERO_SHORTCUT": "1"}):
+        for k in ("QLDPC_NO_ZERO_SHORTCUT", "QLDPC_FORCE_ZERO_SHORTCUT"):
+            os.environ.pop(k, None)
+        os.environ.update(env)
+        try:
+            a = code.bp_decode_batch(synd, _prior(p, n), "min_sum", 50, 0.8, 0.7, 25.0, precision=32)                 # LLRs of every shot
+            b = code.bposd_decode_batch(synd, _prior(p, n), "min_sum", 50, 0.8, 0.7, 25.0, precision=32, osd_order=0)  # LLRs of failures only
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        outs.append((a, b))
+    for a, b in outs[1:]:
+        for x, y in zip(a, outs[0][0]):
+            assert np.array_equal(x, y)
+        for x, y in zip(b, outs[0][1]):
+            assert np.array_equal(x, y)
+    zero = synd.sum(axis=1) == 0
+    assert outs[1][0][1][zero].all() and not outs[1][0][0][zero].any() and (outs[1][0][3][zero] == 0).all()
+
+
 def test_staged_kernel_matches_on_chip_kernel():
     """The HBM-staged instantiation runs the same arithmetic: forcing it on a small code must give
     bit-identical float64 results."""

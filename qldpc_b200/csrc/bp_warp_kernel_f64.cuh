@@ -76,7 +76,8 @@ struct BPW64Mem {
     __device__ static __forceinline__ void st_own(unsigned char *base, int row, int lane, double v) { st(base, 8u * (uint32_t)(row * 32 + lane), v); }
 };
 
-template <int CPL, int VPL, int RW, bool TWO, int VAR = 0>
+// ZSC: zero-syndrome shortcut compiled in (see bp_warp_kernel.cuh; chosen by the launcher at low error rates)
+template <int CPL, int VPL, int RW, bool TWO, int VAR = 0, bool ZSC = false>
 __global__ void __launch_bounds__(BPW64_WARPS * 32, (CPL * RW > 18) ? 2 : 3)
 bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
 {
@@ -138,6 +139,30 @@ bp_warp_kernel_f64(const BPParams P, const BPWarpTables W)
         uint32_t sbit[CPL];                      // syndrome bit of each owned check, at the sign-bit position
 #pragma unroll
         for (int i = 0; i < CPL; ++i) sbit[i] = ((sw[i] >> (cinfo[i] & 31u)) & 1u) << 31;
+        // all-zero syndrome, positive priors: the reference returns the all-zero correction at its first check (decoding.py:69-73)
+        if (ZSC && P.zero_ok && !(P.llr != nullptr && P.llr_mode == LLR_ALL)) {
+            uint32_t anyb = 0;
+#pragma unroll
+            for (int i = 0; i < CPL; ++i) anyb |= sbit[i];
+            if (__all_sync(FULL, anyb == 0)) {
+                if (need_grab) {
+                    grp_next = (long long)__shfl_sync(FULL, s0, 0);
+                    grp_end = grp_next + BPW_GRAB;
+                }
+                next2_shot = grp_next++;
+#pragma unroll
+                for (int i = 0; i < CPL; ++i) sw[i] = swn[i];
+                load_synd(next2_shot, swn);
+                if (lane < WN) P.hard[(size_t)shot * WN + lane] = 0u;
+                if (lane == 0) {
+                    P.conv[shot] = 1;
+                    if (P.iters) P.iters[shot] = 0;
+                }
+                shot = next_shot;
+                next_shot = next2_shot;
+                continue;
+            }
+        }
         // Q = where(mask, prior, 0) (decoding.py:21): one value when the prior is uniform, else publish the priors and
         // gather them along the edges
         double Q[CPL][RW];

@@ -7,10 +7,10 @@
 #error "define QLDPC_F64_VAR (0: min-sum, 1: the sum-product variants) and QLDPC_F64_ENTRY before including this file"
 #endif
 
-template <int CPL, int VPL, bool TWO, int VAR>
+template <int CPL, int VPL, bool TWO, int VAR, bool ZSC = false>
 static cudaError_t launch_f64_inst(const qldpc_code *c, const BPParams &P, const BPGeom &G, cudaStream_t st)
 {
-    auto kern = bp_warp_kernel_f64<CPL, VPL, 6, TWO, VAR>;
+    auto kern = bp_warp_kernel_f64<CPL, VPL, 6, TWO, VAR, ZSC>;
     if (G.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem);
         if (e != cudaSuccess) return e;
@@ -29,6 +29,8 @@ static cudaError_t launch_f64(const qldpc_code *c, const BPParams &P, const BPGe
     // (sum-product too: every check of these codes has the same weight, so the messages of iteration 0 share one magnitude)
     const bool two = c->two_tables && !P.prior_uniform;
 #if QLDPC_F64_VAR == 0
+    if (P.zero_ok == 2)             // many all-zero syndromes expected (low error rates): the instantiation with the shortcut
+        return two ? launch_f64_inst<CPL, VPL, true, 0, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 0, true>(c, P, G, st);
     return two ? launch_f64_inst<CPL, VPL, true, 0>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 0>(c, P, G, st);
 #else
     if (G.warp_var == 4)

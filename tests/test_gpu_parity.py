@@ -305,7 +305,7 @@ def test_f32_divergence_is_iteration_resolved():
 @pytest.mark.parametrize("stem,p", [("[[90, 8, 10]]", 0.01), ("[[144, 12, 12]]", 0.01), ("[[144, 12, 12]]", 0.05)])
 def test_zero_syndrome_shortcut_changes_no_output(stem, p):
     """Low error rates: a quarter to 40 % of the shots have an all-zero syndrome; with positive priors the reference returns the
-    all-zero correction at its first check (decoding.py:69-73) and the float32 warp kernel retires such shots without running the
+    all-zero correction at its first check (decoding.py:69-73) and the warp kernels (float32, float64) retire such shots without running the
     iteration (its own instantiation, chosen when the priors imply >= 10 % error-free shots).  Hard decisions, flags, exit iterations
     and posterior LLRs must not change: with the shortcut disabled, chosen by the priors, and forced."""
     import os
@@ -324,6 +324,7 @@ def test_zero_syndrome_shortcut_changes_no_output(stem, p):
         try:
             a = code.bp_decode_batch(synd, _prior(p, n), "min_sum", 50, 0.8, 0.7, 25.0, precision=32)                 # LLRs of every shot
             b = code.bposd_decode_batch(synd, _prior(p, n), "min_sum", 50, 0.8, 0.7, 25.0, precision=32, osd_order=0)  # LLRs of failures only
+            b = b + code.bposd_decode_batch(synd, _prior(p, n), "min_sum", 50, 0.8, 0.7, 25.0, precision=64, osd_order=0)   # the float64 kernel
         finally:
             for k in env:
                 os.environ.pop(k, None)

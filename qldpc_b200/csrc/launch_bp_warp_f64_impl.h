@@ -33,6 +33,11 @@ static cudaError_t launch_f64(const qldpc_code *c, const BPParams &P, const BPGe
         return two ? launch_f64_inst<CPL, VPL, true, 0, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 0, true>(c, P, G, st);
     return two ? launch_f64_inst<CPL, VPL, true, 0>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 0>(c, P, G, st);
 #else
+    if (P.zero_ok == 2) {
+        if (G.warp_var == 4)
+            return two ? launch_f64_inst<CPL, VPL, true, 1, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 1, true>(c, P, G, st);
+        return two ? launch_f64_inst<CPL, VPL, true, 2, true>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 2, true>(c, P, G, st);
+    }
     if (G.warp_var == 4)
         return two ? launch_f64_inst<CPL, VPL, true, 1>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 1>(c, P, G, st);
     return two ? launch_f64_inst<CPL, VPL, true, 2>(c, P, G, st) : launch_f64_inst<CPL, VPL, false, 2>(c, P, G, st);

@@ -566,7 +566,10 @@ static int bp_decode_impl(qldpc_code *c, const qldpc_bp_config *cfg, const doubl
     P.clip = cfg->clip;
     P.qpad = std::max(cfg->clip, c->prior_max);
     P.prior_uniform = c->prior_uniform ? 1 : 0;
-    P.zero_ok = (c->prior_positive && cfg->alpha >= 0.0 && !getenv("QLDPC_NO_ZERO_SHORTCUT")) ? (c->zero_frac >= 0.1 || getenv("QLDPC_FORCE_ZERO_SHORTCUT") ? 2 : 1) : 0;
+    // 2: launch the instantiation with the zero-syndrome shortcut -- worth its registers from ~30 % error-free shots on for min-sum
+    // (measured: [[144,12,12]] at p = 0.01, 23 %: -2 %; [[108,8,10]], 34 %: +7 %), from 10 % on for the costlier sum-product iteration
+    const double zero_min = (cfg->variant == QLDPC_MIN_SUM) ? 0.3 : 0.1;
+    P.zero_ok = (c->prior_positive && cfg->alpha >= 0.0 && !getenv("QLDPC_NO_ZERO_SHORTCUT")) ? (c->zero_frac >= zero_min || getenv("QLDPC_FORCE_ZERO_SHORTCUT") ? 2 : 1) : 0;
     P.hard = hard;
     P.conv = conv;
     P.iters = iters;
